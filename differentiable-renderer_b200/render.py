@@ -1,0 +1,146 @@
+"""Thin Python host over the C ABI (include/drtb.h): the call a user makes in
+place of the pixel loop of src/render.cpp:72-86.  Nothing here computes
+radiance; every number comes out of libdrtb.so's CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import abi
+from .scene import SceneDesc, make_opts
+
+_dp = C.POINTER(C.c_double)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def shard_rows(height: int, shard_index: int = 0, shard_count: int = 1, band_rows: int = 8) -> int:
+    return int(abi.load_library().drtb_shard_rows(height, shard_index, shard_count, band_rows))
+
+
+def stream_draw(key: int, slot: int) -> int:
+    return int(abi.load_library().drtb_stream_draw(key & (2**64 - 1), slot))
+
+
+class Context:
+    """Owns a drtb_ctx: one CUDA device, one uploaded scene."""
+
+    def __init__(self, device: int = 0):
+        self._lib = abi.load_library()
+        h = C.c_void_p()
+        rc = self._lib.drtb_create(int(device), C.byref(h))
+        if rc != abi.OK:
+            msg = self._lib.drtb_last_error(None)
+            raise abi.DrtbError(rc, msg.decode() if msg else "drtb_create failed")
+        self._h = h
+        self.device = int(device)
+        self.scene: Optional[SceneDesc] = None
+        self._abi_scene = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.drtb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != abi.OK:
+            msg = self._lib.drtb_last_error(self._h)
+            raise abi.DrtbError(rc, msg.decode() if msg else "")
+
+    # -- scene ----------------------------------------------------------------
+    def upload(self, scene: SceneDesc):
+        sc = scene.flatten()
+        self._check(self._lib.drtb_scene_upload(self._h, C.byref(sc)))
+        self.scene, self._abi_scene = scene, sc
+        return self
+
+    def set_params(self, values: np.ndarray):
+        v = np.ascontiguousarray(values, dtype=np.float64).reshape(-1, 3)
+        self._check(self._lib.drtb_set_params(self._h, _ptr(v), v.shape[0]))
+
+    # -- hot path, host buffers --------------------------------------------------
+    def render(self, opts: abi.RenderOpts, seed_img: Optional[np.ndarray] = None,
+               *, stats: bool = False):
+        """Returns (img[rows,W,3], grad[P,3]) (+ abi.Stats when stats=True)."""
+        assert self.scene is not None, "upload a scene first"
+        cam = self.scene.camera
+        rows = shard_rows(cam.height, opts.shard_index, max(1, opts.shard_count),
+                          max(1, opts.band_rows))
+        img = np.empty((rows, cam.width, 3), dtype=np.float64) if opts.flags & abi.FLAG_IMAGE else None
+        grad = np.empty((len(self.scene.params), 3), dtype=np.float64) if opts.flags & abi.FLAG_GRAD else None
+        if seed_img is not None:
+            seed_img = np.ascontiguousarray(seed_img, dtype=np.float64)
+            assert seed_img.shape == (rows, cam.width, 3)
+        st = abi.Stats()
+        if stats:
+            opts.flags |= abi.FLAG_STATS
+        self._check(self._lib.drtb_render(self._h, C.byref(opts), _ptr(seed_img), _ptr(img),
+                                          _ptr(grad), C.byref(st)))
+        return (img, grad, st) if stats else (img, grad)
+
+    def render_host_ptrs(self, opts: abi.RenderOpts, seed_ptr: int, img_ptr: int, grad_ptr: int,
+                         st: Optional[abi.Stats] = None):
+        """drtb_render on caller-owned (e.g. pinned) host memory, by address."""
+        self._check(self._lib.drtb_render(
+            self._h, C.byref(opts), C.cast(seed_ptr, _dp) if seed_ptr else None,
+            C.cast(img_ptr, _dp) if img_ptr else None, C.cast(grad_ptr, _dp) if grad_ptr else None,
+            C.byref(st) if st is not None else None))
+
+    # -- hot path, device buffers ------------------------------------------------
+    def render_device(self, opts: abi.RenderOpts, d_seed_img: int, d_img: int, d_grad: int,
+                      d_stats: int = 0, stream: int = 0):
+        """Raw device addresses (e.g. torch.Tensor.data_ptr()) and a cudaStream_t
+        handle; asynchronous."""
+        self._check(self._lib.drtb_render_device(self._h, C.byref(opts), d_seed_img or None,
+                                                 d_img or None, d_grad or None, d_stats or None,
+                                                 stream or None))
+
+    def trace_rays(self, opts: abi.RenderOpts, orig: np.ndarray, dirs: np.ndarray,
+                   keys: np.ndarray, *, jac: bool = True) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+        """Pathtracer::trace on explicit rays (pathtracer.hpp:121-136)."""
+        orig = np.ascontiguousarray(orig, dtype=np.float64).reshape(-1, 3)
+        dirs = np.ascontiguousarray(dirs, dtype=np.float64).reshape(-1, 3)
+        keys = np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1)
+        n = orig.shape[0]
+        rad = np.empty((n, 3), dtype=np.float64)
+        J = np.empty((n, len(self.scene.params), 3), dtype=np.float64) if jac else None
+        self._check(self._lib.drtb_trace_rays(self._h, C.byref(opts), n, _ptr(orig), _ptr(dirs),
+                                              keys.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                              _ptr(rad), _ptr(J)))
+        return rad, J
+
+    def fma_peak(self, precision: int) -> float:
+        out = C.c_double()
+        self._check(self._lib.drtb_fma_peak(self._h, precision, C.byref(out)))
+        return out.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.drtb_launch_count(self._h))
+
+
+def render(scene: SceneDesc, spp: int, min_bounces: int = 1, absorb: float = 0.5, *,
+           device: int = 0, **kw):
+    """One-shot convenience: the whole of src/render.cpp:62-86 for `scene`.
+    Adds the gradients into each `Param.grad` like VariableNode::backward does
+    (vector.hpp:185-188) and returns (img, grad)."""
+    with Context(device) as ctx:
+        ctx.upload(scene)
+        img, grad = ctx.render(make_opts(spp, min_bounces, absorb, **kw))
+    if grad is not None:
+        for p in scene.params:
+            p.grad = p.grad + grad[p.index]
+    return img, grad

@@ -1,0 +1,224 @@
+/*
+ * drtb.h — C ABI of the B200-native differentiable path tracer hot path.
+ *
+ * The reference (thalesfm/differentiable-renderer) is a header-only C++17
+ * template library with NO FFI layer: its hot path is the triple loop of
+ * src/render.cpp:72-86 and everything that loop reaches in include/drt.
+ * This header is the boundary a binding for that loop would target: plain C,
+ * plain pointers and sizes, integer status codes, no exceptions, no torch
+ * types.  Every entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - all scene numbers cross the boundary as IEEE double (the reference
+ *     instantiates T = double, src/render.cpp:22);
+ *   - RGB triples are 3 consecutive doubles;
+ *   - images are row-major, row 0 = top (include/drt/camera.hpp:57),
+ *     img[(y*W + x)*3 + c];
+ *   - gradients are n_params x 3 doubles, UNNORMALISED sums over every sample
+ *     of every pixel of seed . d(radiance)/d(param)  (src/render.cpp:78-82 with
+ *     the commented `radiance.backward(seed)` enabled);
+ *   - every function returns DRTB_OK (0) or a negative DRTB_ERR_* code and
+ *     never throws; drtb_last_error() gives the message for the calling ctx;
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute
+ *     entry point fails with DRTB_ERR_NO_DEVICE.
+ */
+#ifndef DRTB_H
+#define DRTB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRTB_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+#define DRTB_OK                 0
+#define DRTB_ERR_INVALID       -1   /* bad argument / inconsistent scene       */
+#define DRTB_ERR_NO_DEVICE     -2   /* no CUDA device / driver                 */
+#define DRTB_ERR_CUDA          -3   /* a CUDA runtime call failed              */
+#define DRTB_ERR_UNSUPPORTED   -4   /* valid request this build cannot serve   */
+#define DRTB_ERR_NOMEM         -5
+
+/* ---- scene description (flattened include/drt objects) ------------------ */
+
+/* Shape<T> subclasses, include/drt/shape.hpp:37-111 */
+#define DRTB_SPHERE 0               /* Sphere: v = {cx, cy, cz, radius}        */
+#define DRTB_PLANE  1               /* Plane : v = {nx, ny, nz, offset}; the
+                                       normal is used RAW, never normalised
+                                       (shape.hpp:58-59)                        */
+
+/* BxDF<T> subclasses, include/drt/bxdf.hpp:56-124 */
+#define DRTB_DIFFUSE  0             /* DiffuseBxDF(color)                      */
+
+typedef struct drtb_prim {
+    int32_t type;                   /* DRTB_SPHERE | DRTB_PLANE                */
+    int32_t material;               /* index into materials[], -1 = null BxDF
+                                       (shape.hpp:14-16, pathtracer.hpp:25-26) */
+    int32_t emission;               /* index into params[] of the AreaEmitter's
+                                       RGB (emitter.hpp:18), -1 = no emitter   */
+    int32_t reserved;
+    double  v[4];
+} drtb_prim;                        /* 48 bytes; array order == Scene<T> order,
+                                       which is the closest-hit tie-break
+                                       priority (pathtracer.hpp:78-87)         */
+
+typedef struct drtb_material {
+    int32_t type;                   /* DRTB_DIFFUSE                            */
+    int32_t color;                  /* index into params[] of the albedo RGB
+                                       (bxdf.hpp:59-60); shapes sharing one
+                                       Vector<T,3,true> share one index         */
+    double  exponent;               /* reserved (SpecularBxDF, bxdf.hpp:88-91) */
+} drtb_material;                    /* 16 bytes                                */
+
+/* Camera<T>, include/drt/camera.hpp:13-37 (after look_at) */
+typedef struct drtb_camera {
+    int32_t width, height;
+    double  vfov;                   /* radians, default 1.3963                 */
+    double  eye[3], forward[3], right[3], up[3];
+} drtb_camera;
+
+typedef struct drtb_scene {
+    const drtb_prim*     prims;      int32_t n_prims;
+    const drtb_material* materials;  int32_t n_materials;
+    const double*        params;     int32_t n_params;   /* n_params x 3       */
+    drtb_camera          camera;
+} drtb_scene;
+
+/* ---- render options ------------------------------------------------------ */
+
+#define DRTB_F64   0    /* every path in IEEE double: the parity instantiation  */
+#define DRTB_F32   1    /* every path in float (throughput mode; image/gradient
+                           accumulators stay double)                            */
+#define DRTB_MIXED 2    /* float fast path; any path with a decision closer than
+                           its float error bound is re-traced in double          */
+
+#define DRTB_FLAG_IMAGE   1u    /* write the image                              */
+#define DRTB_FLAG_GRAD    2u    /* run the adjoint and write the gradients      */
+#define DRTB_FLAG_STATS   4u    /* fill drtb_stats (segments, lit paths, ...)   */
+
+typedef struct drtb_render_opts {
+    int32_t  spp;               /* samples per pixel  (args.hpp:32-37 `-n`)     */
+    int32_t  min_bounces;       /* Pathtracer::m_min_bounces (`-b`)             */
+    double   absorb;            /* Pathtracer::m_absorb      (`-p`)             */
+    uint64_t seed;              /* stream selector; 0 reproduces SURVEY KATs    */
+    int32_t  precision;         /* DRTB_F64 | DRTB_F32 | DRTB_MIXED             */
+    uint32_t flags;             /* DRTB_FLAG_*                                  */
+    /* data-parallel shard: image rows are cut into bands of band_rows rows and
+       band b belongs to shard (b % shard_count).  shard_count <= 1 = whole
+       image.  The shard's rows are written COMPACTLY, in increasing y.        */
+    int32_t  shard_index, shard_count, band_rows;
+    int32_t  max_depth;         /* vertex-record capacity per path; 0 = default
+                                   (min_bounces when absorb == 1, else 64).
+                                   Paths still alive at max_depth are cut and
+                                   counted in drtb_stats.truncated_paths.       */
+    double   seed_scale;        /* adjoint seed = seed_scale * (seed_img ?
+                                   seed_img[pixel] : (1,1,1))                    */
+    uint64_t adjoint_seed;      /* reserved (decorrelated adjoint); must be 0   */
+} drtb_render_opts;
+
+typedef struct drtb_stats {
+    uint64_t paths;             /* camera samples traced                        */
+    uint64_t segments;          /* ray segments that were intersected           */
+    uint64_t lit_paths;         /* paths with non-zero radiance                 */
+    uint64_t truncated_paths;   /* paths cut at max_depth                       */
+    uint64_t retraced_paths;    /* DRTB_MIXED: paths re-traced in double        */
+    double   kernel_ms;         /* device time of the render kernels (events)   */
+} drtb_stats;
+
+typedef struct drtb_ctx drtb_ctx;
+
+/* ---- lifetime ------------------------------------------------------------ */
+
+/* Library/ABI version; callable without a GPU. */
+int drtb_abi_version(void);
+
+/* Number of usable CUDA devices (0 without a driver); callable without a GPU. */
+int drtb_device_count(void);
+
+/* Create a context on CUDA device `device`.  Replaces nothing in the reference
+ * (it has no device); it is the owner of the uploaded scene and scratch. */
+int drtb_create(int device, drtb_ctx** out);
+void drtb_destroy(drtb_ctx* ctx);
+
+/* Message for the last failing call on ctx (ctx == NULL: last create error). */
+const char* drtb_last_error(const drtb_ctx* ctx);
+
+/* ---- scene --------------------------------------------------------------- */
+
+/* Flatten-and-upload: replaces the object graph built at src/render.cpp:26-65
+ * (parameters, materials, shapes, Scene<T>, Camera<T>).  Copies everything. */
+int drtb_scene_upload(drtb_ctx* ctx, const drtb_scene* scene);
+
+/* Overwrite parameter values only (n_params x 3 doubles); the cheap call an
+ * optimisation loop makes between renders. */
+int drtb_set_params(drtb_ctx* ctx, const double* params, int32_t n_params);
+
+/* Rows of the image that shard (index, count, band_rows) owns, for sizing the
+ * compact shard buffers; callable without a GPU. */
+int32_t drtb_shard_rows(int32_t height, int32_t shard_index, int32_t shard_count,
+                        int32_t band_rows);
+
+/* ---- the hot path -------------------------------------------------------- */
+
+/* Forward render + adjoint with HOST buffers: replaces the pixel loop of
+ * src/render.cpp:72-86 (cam.sample -> tracer.trace -> accumulate ->
+ * radiance.backward(seed)), i.e. Camera::sample (camera.hpp:51-60),
+ * Pathtracer::trace/raycast/scatter (pathtracer.hpp:72-136), DiffuseBxDF
+ * (bxdf.hpp:63-79), AreaEmitter (emitter.hpp:20-21) and the reverse tape
+ * (vector.hpp:120-318, 418-557).
+ *   seed_img : NULL or shard_rows*W*3 doubles, per-pixel adjoint seed
+ *   img      : shard_rows*W*3 doubles (may be NULL without DRTB_FLAG_IMAGE)
+ *   grad     : n_params*3 doubles     (may be NULL without DRTB_FLAG_GRAD);
+ *              OVERWRITTEN with this call's sums (the caller adds them to
+ *              VariableNode::m_grad, vector.hpp:185-188)
+ *   stats    : NULL or filled
+ * Blocking.  Host->device and device->host copies happen inside the call. */
+int drtb_render(drtb_ctx* ctx, const drtb_render_opts* opts,
+                const double* seed_img, double* img, double* grad,
+                drtb_stats* stats);
+
+/* Same, DEVICE buffers on ctx's device, enqueued on `stream` (a cudaStream_t
+ * passed as void*; NULL = the legacy default stream).  Asynchronous: returns
+ * after the launches; the caller synchronises the stream.  d_stats is NULL or
+ * a device drtb_stats (kernel_ms is not filled). */
+int drtb_render_device(drtb_ctx* ctx, const drtb_render_opts* opts,
+                       const double* d_seed_img, double* d_img, double* d_grad,
+                       drtb_stats* d_stats, void* stream);
+
+/* Batch of explicit rays: replaces Pathtracer<T>::trace(scene, orig, dir)
+ * (pathtracer.hpp:121-136) called from user code, plus radiance.backward().
+ *   orig, dir : n x 3 doubles (dir is used as given, as the reference does)
+ *   keys      : n stream keys; ray i draws u(keys[i], slot) with the first
+ *               scatter draw at slot 2 (slots 0,1 are the camera's)
+ *   radiance  : n x 3 doubles
+ *   jac       : NULL or n x n_params x 3 doubles, d radiance_c / d param_{k,c}
+ *               (channels never mix) so that
+ *               backward(g) == param_k.grad[c] += g[c] * jac[i][k][c]        */
+int drtb_trace_rays(drtb_ctx* ctx, const drtb_render_opts* opts, int64_t n,
+                    const double* orig, const double* dir, const uint64_t* keys,
+                    double* radiance, double* jac);
+
+/* ---- measurement helpers -------------------------------------------------- */
+
+/* Dependent-free FMA issue-rate micro-benchmark on ctx's device: the roofline
+ * denominator for this compute-bound path (MEASURED_PEAKS.json has only HBM
+ * and tensor numbers).  precision = DRTB_F64 | DRTB_F32; result in TFLOP/s
+ * (FMA = 2 FLOP). */
+int drtb_fma_peak(drtb_ctx* ctx, int32_t precision, double* tflops);
+
+/* Number of kernels this context has launched so far (bench `gpu_launches`). */
+uint64_t drtb_launch_count(const drtb_ctx* ctx);
+
+/* The counter-based sample stream, exposed so hosts and tests can reproduce
+ * it: k = splitmix64(key * 0x100000001B3 + slot) % 2147483647, the value the
+ * reference's random::uniform() (random.hpp:7-10) would get from rand().
+ * key = seed * 0x9E3779B97F4A7C15 + (y*W + x)*spp + i.  Callable without GPU. */
+uint32_t drtb_stream_draw(uint64_t key, uint32_t slot);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRTB_H */
