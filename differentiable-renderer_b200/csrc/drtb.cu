@@ -1,0 +1,698 @@
+// drtb.cu — kernels + the C ABI of include/drtb.h.
+//
+// Kernel inventory
+//   render_kernel<R, SMALLP>   persistent megakernel: one lane = one path
+//                              (camera sample -> trace -> radiance -> adjoint),
+//                              lanes of a warp = consecutive samples of one pixel
+//   reduce_grad_kernel         fixed-order sum of the per-block gradient partials
+//   trace_rays_kernel<R>       Pathtracer::trace on explicit rays (+ Jacobian)
+//   fma_peak_kernel<R>         FMA issue-rate micro-benchmark (roofline denominator)
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a (see build.py).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "path.cuh"
+
+using namespace drtb;
+
+// ===========================================================================
+// device code
+// ===========================================================================
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Gradient sinks ------------------------------------------------------------
+// Small parameter sets (the Cornell box has 4): every thread owns one column of
+// a [n_params*3][kBlock] shared array -- no atomics, no bank conflicts, and a
+// fixed summation order, so gradients are bit-reproducible run to run.
+struct SmemSink {
+    double* col;                                   // &acc[threadIdx.x]
+    template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
+    {
+        col[(3 * p + c) * kBlock] += double(v);
+    }
+};
+// Large parameter sets: one red.global.add.f64 per contribution.
+struct AtomicSink {
+    double* grad;
+    template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
+    {
+        atomicAdd(grad + 3 * p + c, double(v));
+    }
+};
+struct JacSink {
+    double* row;                                   // this ray's n_params x 3 block
+    template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
+    {
+        row[3 * p + c] += double(v);
+    }
+};
+
+// The pixel loop of src/render.cpp:72-86.
+template <typename R, bool SMALLP>
+__global__ void __launch_bounds__(kBlock)
+render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ RenderArgs a)
+{
+    extern __shared__ double s_acc[];              // SMALLP && grad: [n_params*3][kBlock]
+    __shared__ BlockScene<R> bs;
+    __shared__ double s_red[kSmallP * 3][kWarpsPerBlock];
+
+    const bool want_grad = (a.flags & DRTB_FLAG_GRAD) != 0;
+    const int P3 = sc.n_params * 3;
+    load_block_scene(bs, sc, a.params);
+    if (SMALLP && want_grad)
+        for (int i = threadIdx.x; i < P3 * kBlock; i += kBlock) s_acc[i] = 0.0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = sc.width, spp = a.spp;
+    const long long npix = (long long)a.shard_rows * W;
+    // spp >= 32: one pixel per warp task, ceil(spp/32) passes over its samples;
+    // spp <  32: floor(32/spp) pixels per warp task, one pass.
+    const int ppw = spp >= 32 ? 1 : 32 / spp;
+    const int passes = spp >= 32 ? (spp + 31) / 32 : 1;
+    const long long n_tasks = (npix + ppw - 1) / ppw;
+    const long long n_warps = (long long)gridDim.x * kWarpsPerBlock;
+    const R inv_p = a.absorb < 1.0 ? R(1.0 / (1.0 - a.absorb)) : R(0);
+
+    SmemSink ssink{s_acc + threadIdx.x};
+    AtomicSink asink{a.grad_atomic};
+    uint32_t n_seg = 0, n_lit = 0, n_trunc = 0;
+
+    for (long long task = (long long)blockIdx.x * kWarpsPerBlock + warp; task < n_tasks; task += n_warps) {
+        const int sub = spp >= 32 ? 0 : lane / spp;           // pixel within the task
+        const int i0 = spp >= 32 ? lane : lane % spp;         // first sample of this lane
+        const long long pix = task * ppw + sub;
+        const bool lane_ok = sub < ppw && pix < npix;
+        int x = 0, y = 0;
+        R g0[3] = {R(0), R(0), R(0)};
+        if (lane_ok) {
+            const int r = int(pix / W);
+            x = int(pix - (long long)r * W);
+            y = a.shard_count > 1 ? ((r / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + r % a.band_rows
+                                  : r;
+            if (want_grad) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    g0[c] = R(a.seed_scale * (a.seed_img ? a.seed_img[pix * 3 + c] : 1.0));
+            }
+        }
+        double acc[3] = {0.0, 0.0, 0.0};
+        for (int pass = 0; pass < passes; ++pass) {
+            const int i = i0 + pass * 32;
+            if (lane_ok && i < spp) {
+                const uint64_t key = a.key0 + ((uint64_t)y * W + x) * (uint64_t)spp + (uint64_t)i;
+                const uint64_t base = key * kKeyMul;
+                V3<R> o = {sc.eye[0], sc.eye[1], sc.eye[2]};
+                V3<R> d = camera_ray(sc, x, y, base);
+                PathRecord<R> rec;
+                bool lit, truncated;
+                int n = trace_path(sc, bs, base, 2u, o, d, a.min_bounces, a.absorb, a.max_depth,
+                                   rec, lit, n_seg, truncated);
+                n_trunc += truncated;
+                if (lit) {
+                    R L0[3];
+                    if (SMALLP) radiance_and_adjoint(bs, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ssink);
+                    else        radiance_and_adjoint(bs, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, asink);
+                    acc[0] += double(L0[0]); acc[1] += double(L0[1]); acc[2] += double(L0[2]);   // render.cpp:78
+                    n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
+                }
+            }
+        }
+        // pixel_radiance / samples (render.cpp:82): sum the lanes of each pixel
+        if (a.img) {
+            if (spp >= 32) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[c] = warp_sum(acc[c]);
+                if (lane == 0 && lane_ok) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) a.img[pix * 3 + c] = acc[c] / double(spp);
+                }
+            } else {
+                double tot[3] = {acc[0], acc[1], acc[2]};
+                for (int j = 1; j < spp; ++j) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        double o = __shfl_down_sync(0xffffffffu, acc[c], j);
+                        if (i0 + j < spp) tot[c] += o;
+                    }
+                }
+                if (lane_ok && i0 == 0) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) a.img[pix * 3 + c] = tot[c] / double(spp);
+                }
+            }
+        }
+    }
+
+    if (SMALLP && want_grad) {
+        // block reduction in a fixed order: lanes (xor tree) -> warps (0..7)
+        for (int j = 0; j < P3; ++j) {
+            double v = warp_sum(s_acc[j * kBlock + threadIdx.x]);
+            if (lane == 0) s_red[j][warp] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < P3) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarpsPerBlock; ++w) v += s_red[threadIdx.x][w];
+            a.grad_partial[(size_t)blockIdx.x * P3 + threadIdx.x] = v;
+        }
+    }
+    if (a.stats) {
+        n_seg = __reduce_add_sync(0xffffffffu, n_seg);
+        n_lit = __reduce_add_sync(0xffffffffu, n_lit);
+        n_trunc = __reduce_add_sync(0xffffffffu, n_trunc);
+        if (lane == 0) {
+            atomicAdd((unsigned long long*)&a.stats->segments, (unsigned long long)n_seg);
+            atomicAdd((unsigned long long*)&a.stats->lit_paths, (unsigned long long)n_lit);
+            if (n_trunc) atomicAdd((unsigned long long*)&a.stats->truncated_paths, (unsigned long long)n_trunc);
+        }
+    }
+}
+
+// grad[j] = sum_b partial[b][j], b ascending inside each thread, then a fixed tree.
+__global__ void __launch_bounds__(256)
+reduce_grad_kernel(const double* __restrict__ partial, int n_blocks, int P3, double* __restrict__ grad)
+{
+    __shared__ double s[256];
+    for (int j = 0; j < P3; ++j) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < n_blocks; b += 256) v += partial[(size_t)b * P3 + j];
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) grad[j] = s[0];
+        __syncthreads();
+    }
+}
+
+// Pathtracer<T>::trace(scene, orig, dir) for user-supplied rays (pathtracer.hpp:121-136).
+template <typename R>
+__global__ void __launch_bounds__(kBlock)
+trace_rays_kernel(const __grid_constant__ DevScene<R> sc, const double* __restrict__ params,
+                  int min_bounces, double absorb, int max_depth, long long n,
+                  const double* __restrict__ orig, const double* __restrict__ dir,
+                  const uint64_t* __restrict__ keys, double* __restrict__ radiance, double* jac)
+{
+    __shared__ BlockScene<R> bs;
+    load_block_scene(bs, sc, params);
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const R inv_p = absorb < 1.0 ? R(1.0 / (1.0 - absorb)) : R(0);
+    V3<R> o = {R(orig[3 * i]), R(orig[3 * i + 1]), R(orig[3 * i + 2])};
+    V3<R> d = {R(dir[3 * i]), R(dir[3 * i + 1]), R(dir[3 * i + 2])};
+    PathRecord<R> rec;
+    bool lit, truncated;
+    uint32_t seg = 0;
+    int nv = trace_path(sc, bs, keys[i] * kKeyMul, 2u, o, d, min_bounces, absorb, max_depth, rec, lit, seg, truncated);
+    R L0[3] = {R(0), R(0), R(0)};
+    if (lit) {
+        const R one[3] = {R(1), R(1), R(1)};
+        JacSink sink{jac ? jac + (size_t)i * sc.n_params * 3 : nullptr};
+        radiance_and_adjoint(bs, rec, nv, min_bounces, inv_p, jac != nullptr, one, L0, sink);
+    }
+    radiance[3 * i] = double(L0[0]); radiance[3 * i + 1] = double(L0[1]); radiance[3 * i + 2] = double(L0[2]);
+}
+
+// 8 independent FMA chains per thread, operands in registers: the non-tensor
+// FMA pipe at its issue limit.
+template <typename R>
+__global__ void __launch_bounds__(256) fma_peak_kernel(R* out, int iters, R a, R b)
+{
+    R x0 = R(threadIdx.x), x1 = x0 + R(1), x2 = x0 + R(2), x3 = x0 + R(3);
+    R x4 = x0 + R(4), x5 = x0 + R(5), x6 = x0 + R(6), x7 = x0 + R(7);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = Real<R>::fma(x0, a, b); x1 = Real<R>::fma(x1, a, b); x2 = Real<R>::fma(x2, a, b); x3 = Real<R>::fma(x3, a, b);
+            x4 = Real<R>::fma(x4, a, b); x5 = Real<R>::fma(x5, a, b); x6 = Real<R>::fma(x6, a, b); x7 = Real<R>::fma(x7, a, b);
+        }
+    }
+    R s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == R(-1)) out[0] = s;                    // never true; keeps the chains alive
+}
+
+} // namespace
+
+// ===========================================================================
+// host side
+// ===========================================================================
+struct drtb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    bool has_scene = false;
+    std::vector<drtb_prim> prims;
+    std::vector<drtb_material> materials;
+    std::vector<double> params;
+    drtb_camera camera{};
+    DevScene<double> sc64{};
+    DevScene<float> sc32{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double* d_params = nullptr;   size_t params_cap = 0;
+    double* d_partial = nullptr;  size_t partial_cap = 0;
+    double* d_img = nullptr;      size_t img_cap = 0;
+    double* d_seed = nullptr;     size_t seed_cap = 0;
+    double* d_grad = nullptr;     size_t grad_cap = 0;
+    drtb_stats* d_stats = nullptr;
+    unsigned long long launches = 0;
+    int occ[2][2] = {{0, 0}, {0, 0}};               // [precision][smallp] blocks per SM
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+
+int fail(drtb_ctx* ctx, int code, const std::string& msg)
+{
+    if (ctx) ctx->err = msg; else g_create_err = msg;
+    return code;
+}
+
+#define CK(ctx, call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, DRTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+int ensure(drtb_ctx* ctx, T*& p, size_t& cap, size_t n)
+{
+    if (n <= cap && p) return DRTB_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e != cudaSuccess) return fail(ctx, DRTB_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    cap = n;
+    return DRTB_OK;
+}
+
+template <typename R>
+void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
+{
+    memset(&d, 0, sizeof d);
+    d.n_prims = int(c.prims.size());
+    d.n_params = int(c.params.size() / 3);
+    for (int i = 0; i < d.n_prims; ++i) {
+        const drtb_prim& p = c.prims[i];
+        for (int j = 0; j < 4; ++j) d.prim[i][j] = R(p.v[j]);
+        d.type[i] = int8_t(p.type);
+        d.color[i] = int8_t(p.material >= 0 ? c.materials[p.material].color : -1);
+        d.emis[i] = int8_t(p.emission);
+    }
+    const drtb_camera& cam = c.camera;
+    for (int j = 0; j < 3; ++j) {
+        d.eye[j] = R(cam.eye[j]); d.fwd[j] = R(cam.forward[j]); d.right[j] = R(cam.right[j]);
+        d.nup[j] = R(-1.0 * cam.up[j]);                       // operator-: -1*v (vector.hpp:320-325)
+    }
+    d.aspect = R(double(cam.width) / cam.height);            // camera.hpp:48-49
+    d.tan_half = R(std::tan(cam.vfov / 2.));                 // camera.hpp:56-57, host libm
+    d.inv_w = R(1.0 / cam.width); d.inv_h = R(1.0 / cam.height);
+    d.width = cam.width; d.height = cam.height;
+}
+
+int shard_rows_impl(int H, int idx, int cnt, int band)
+{
+    if (H <= 0) return 0;
+    if (cnt <= 1) return H;
+    if (band < 1) band = 1;
+    int rows = 0;
+    const int nb = (H + band - 1) / band;
+    for (int b = idx; b < nb; b += cnt) rows += std::min(band, H - b * band);
+    return rows;
+}
+
+struct Plan {
+    RenderArgs a;
+    int P3;
+    bool smallp;
+    int grid;
+    size_t smem;
+    uint64_t paths;
+};
+
+template <typename R, bool SMALLP>
+int occupancy(drtb_ctx* ctx, size_t smem, int& out)
+{
+    int& cached = ctx->occ[sizeof(R) == 4][SMALLP];
+    if (cached == 0 || SMALLP) {
+        CK(ctx, cudaFuncSetAttribute(render_kernel<R, SMALLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        int nb = 0;
+        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<R, SMALLP>, kBlock, smem));
+        if (nb < 1) return fail(ctx, DRTB_ERR_CUDA, "render kernel does not fit on an SM");
+        cached = nb;
+    }
+    out = cached;
+    return DRTB_OK;
+}
+
+int validate_opts(drtb_ctx* ctx, const drtb_render_opts* o)
+{
+    if (!ctx->has_scene) return fail(ctx, DRTB_ERR_INVALID, "no scene uploaded");
+    if (!o) return fail(ctx, DRTB_ERR_INVALID, "opts is NULL");
+    if (o->spp < 1) return fail(ctx, DRTB_ERR_INVALID, "spp must be >= 1");
+    if (o->min_bounces < 0) return fail(ctx, DRTB_ERR_INVALID, "min_bounces must be >= 0");
+    if (!(o->absorb >= 0.0 && o->absorb <= 1.0)) return fail(ctx, DRTB_ERR_INVALID, "absorb must be in [0, 1]");
+    if (o->precision == DRTB_MIXED) return fail(ctx, DRTB_ERR_UNSUPPORTED, "DRTB_MIXED is not implemented in this build");
+    if (o->precision != DRTB_F64 && o->precision != DRTB_F32) return fail(ctx, DRTB_ERR_INVALID, "unknown precision");
+    if (o->adjoint_seed != 0) return fail(ctx, DRTB_ERR_UNSUPPORTED, "decorrelated adjoint is not implemented in this build");
+    if (o->shard_count > 1 && (o->shard_index < 0 || o->shard_index >= o->shard_count || o->band_rows < 1))
+        return fail(ctx, DRTB_ERR_INVALID, "bad shard (index, count, band_rows)");
+    if (o->max_depth < 0 || o->max_depth > kMaxDepth)
+        return fail(ctx, DRTB_ERR_UNSUPPORTED, "max_depth must be in [0, 64]");
+    if (o->absorb == 1.0 && o->min_bounces > kMaxDepth)
+        return fail(ctx, DRTB_ERR_UNSUPPORTED, "min_bounces > 64 with absorb == 1 exceeds the vertex record");
+    return DRTB_OK;
+}
+
+int effective_max_depth(const drtb_render_opts* o)
+{
+    if (o->max_depth > 0) return o->max_depth;
+    return o->absorb == 1.0 ? std::max(1, o->min_bounces) : kMaxDepth;
+}
+
+// Enqueue the render (+ gradient reduction) on `stream`; all pointers device.
+int launch_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed, double* d_img,
+                  double* d_grad, drtb_stats* d_stats, cudaStream_t stream)
+{
+    const int W = ctx->camera.width, H = ctx->camera.height;
+    const int P = int(ctx->params.size() / 3), P3 = P * 3;
+    const bool want_grad = (o->flags & DRTB_FLAG_GRAD) != 0;
+    const bool want_img = (o->flags & DRTB_FLAG_IMAGE) != 0;
+    if (want_grad && !d_grad) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_GRAD set but grad is NULL");
+    if (want_img && !d_img) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_IMAGE set but img is NULL");
+    const int cnt = o->shard_count > 1 ? o->shard_count : 1;
+    const int rows = shard_rows_impl(H, o->shard_index, cnt, o->band_rows);
+
+    RenderArgs a{};
+    a.spp = o->spp; a.min_bounces = o->min_bounces; a.max_depth = effective_max_depth(o);
+    a.flags = o->flags; a.absorb = o->absorb; a.key0 = o->seed * kSeedMul;
+    a.shard_index = o->shard_index; a.shard_count = cnt; a.band_rows = o->band_rows > 0 ? o->band_rows : 1;
+    a.shard_rows = rows; a.seed_scale = o->seed_scale;
+    a.params = ctx->d_params; a.seed_img = d_seed; a.img = want_img ? d_img : nullptr;
+    a.stats = (o->flags & DRTB_FLAG_STATS) ? d_stats : nullptr;
+
+    const bool smallp = P <= kSmallP;
+    const size_t smem = (smallp && want_grad) ? size_t(P3) * kBlock * sizeof(double) : 0;
+    int per_sm = 0, rc;
+    const bool f32 = o->precision == DRTB_F32;
+    if (f32) rc = smallp ? occupancy<float, true>(ctx, smem, per_sm) : occupancy<float, false>(ctx, smem, per_sm);
+    else     rc = smallp ? occupancy<double, true>(ctx, smem, per_sm) : occupancy<double, false>(ctx, smem, per_sm);
+    if (rc != DRTB_OK) return rc;
+    const long long npix = (long long)rows * W;
+    const int ppw = o->spp >= 32 ? 1 : 32 / o->spp;
+    const long long n_tasks = (npix + ppw - 1) / ppw;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    const long long need = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+
+    if (a.stats) {
+        CK(ctx, cudaMemsetAsync(d_stats, 0, sizeof(drtb_stats), stream));
+    }
+    if (want_grad) {
+        if (smallp) {
+            rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, size_t(grid) * P3);
+            if (rc != DRTB_OK) return rc;
+            a.grad_partial = ctx->d_partial;
+        } else {
+            CK(ctx, cudaMemsetAsync(d_grad, 0, sizeof(double) * P3, stream));
+            a.grad_atomic = d_grad;
+        }
+    }
+    if (f32) {
+        if (smallp) render_kernel<float, true><<<int(grid), kBlock, smem, stream>>>(ctx->sc32, a);
+        else        render_kernel<float, false><<<int(grid), kBlock, smem, stream>>>(ctx->sc32, a);
+    } else {
+        if (smallp) render_kernel<double, true><<<int(grid), kBlock, smem, stream>>>(ctx->sc64, a);
+        else        render_kernel<double, false><<<int(grid), kBlock, smem, stream>>>(ctx->sc64, a);
+    }
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    if (want_grad && smallp) {
+        reduce_grad_kernel<<<1, 256, 0, stream>>>(ctx->d_partial, int(grid), P3, d_grad);
+        CK(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    return DRTB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int drtb_abi_version(void) { return DRTB_ABI_VERSION; }
+
+int drtb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int drtb_create(int device, drtb_ctx** out)
+{
+    if (!out) return fail(nullptr, DRTB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, DRTB_ERR_NO_DEVICE,
+                    std::string("no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                        "); this library has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, DRTB_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, DRTB_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, DRTB_ERR_UNSUPPORTED,
+                    std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                        "; this library carries sm_100a code only");
+    drtb_ctx* ctx = new (std::nothrow) drtb_ctx;
+    if (!ctx) return fail(nullptr, DRTB_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_stats, sizeof(drtb_stats)) != cudaSuccess) {
+        std::string m = cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return fail(nullptr, DRTB_ERR_CUDA, "context setup failed: " + m);
+    }
+    *out = ctx;
+    return DRTB_OK;
+}
+
+void drtb_destroy(drtb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    cudaFree(ctx->d_params); cudaFree(ctx->d_partial); cudaFree(ctx->d_img);
+    cudaFree(ctx->d_seed); cudaFree(ctx->d_grad); cudaFree(ctx->d_stats);
+    delete ctx;
+}
+
+const char* drtb_last_error(const drtb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int drtb_scene_upload(drtb_ctx* ctx, const drtb_scene* s)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    if (!s || s->n_prims < 0 || s->n_materials < 0 || s->n_params < 0 || (s->n_prims && !s->prims) ||
+        (s->n_materials && !s->materials) || (s->n_params && !s->params))
+        return fail(ctx, DRTB_ERR_INVALID, "scene has NULL arrays or negative counts");
+    if (s->camera.width < 1 || s->camera.height < 1) return fail(ctx, DRTB_ERR_INVALID, "camera width/height must be >= 1");
+    if (s->n_prims > kMaxPrims)
+        return fail(ctx, DRTB_ERR_UNSUPPORTED, "more than 32 analytic primitives is not supported by this build");
+    if (s->n_params > kMaxParams)
+        return fail(ctx, DRTB_ERR_UNSUPPORTED, "more than 64 RGB parameters is not supported by this build");
+    for (int m = 0; m < s->n_materials; ++m) {
+        if (s->materials[m].type != DRTB_DIFFUSE) return fail(ctx, DRTB_ERR_UNSUPPORTED, "only DRTB_DIFFUSE materials are supported");
+        if (s->materials[m].color < 0 || s->materials[m].color >= s->n_params) return fail(ctx, DRTB_ERR_INVALID, "material colour index out of range");
+    }
+    for (int i = 0; i < s->n_prims; ++i) {
+        const drtb_prim& p = s->prims[i];
+        if (p.type != DRTB_SPHERE && p.type != DRTB_PLANE) return fail(ctx, DRTB_ERR_INVALID, "unknown primitive type");
+        if (p.material < -1 || p.material >= s->n_materials) return fail(ctx, DRTB_ERR_INVALID, "primitive material index out of range");
+        if (p.emission < -1 || p.emission >= s->n_params) return fail(ctx, DRTB_ERR_INVALID, "primitive emission index out of range");
+    }
+    CK(ctx, cudaSetDevice(ctx->device));
+    ctx->prims.assign(s->prims, s->prims + s->n_prims);
+    ctx->materials.assign(s->materials, s->materials + s->n_materials);
+    ctx->params.assign(s->params, s->params + size_t(s->n_params) * 3);
+    ctx->camera = s->camera;
+    fill_dev_scene(ctx->sc64, *ctx);
+    fill_dev_scene(ctx->sc32, *ctx);
+    int rc = ensure(ctx, ctx->d_params, ctx->params_cap, std::max<size_t>(3, ctx->params.size()));
+    if (rc != DRTB_OK) return rc;
+    if (!ctx->params.empty())
+        CK(ctx, cudaMemcpy(ctx->d_params, ctx->params.data(), sizeof(double) * ctx->params.size(), cudaMemcpyHostToDevice));
+    ctx->has_scene = true;
+    return DRTB_OK;
+}
+
+int drtb_set_params(drtb_ctx* ctx, const double* params, int32_t n_params)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, DRTB_ERR_INVALID, "no scene uploaded");
+    if (!params || size_t(n_params) * 3 != ctx->params.size()) return fail(ctx, DRTB_ERR_INVALID, "n_params does not match the uploaded scene");
+    CK(ctx, cudaSetDevice(ctx->device));
+    ctx->params.assign(params, params + size_t(n_params) * 3);
+    // stream-ordered so that it cannot overtake a render still in flight
+    CK(ctx, cudaMemcpyAsync(ctx->d_params, ctx->params.data(), sizeof(double) * ctx->params.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return DRTB_OK;
+}
+
+int32_t drtb_shard_rows(int32_t height, int32_t shard_index, int32_t shard_count, int32_t band_rows)
+{
+    if (shard_count > 1 && (shard_index < 0 || shard_index >= shard_count)) return 0;
+    return shard_rows_impl(height, shard_index, shard_count, band_rows);
+}
+
+int drtb_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* seed_img, double* img,
+                double* grad, drtb_stats* stats)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    int rc = validate_opts(ctx, o);
+    if (rc != DRTB_OK) return rc;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int W = ctx->camera.width, H = ctx->camera.height;
+    const int P3 = int(ctx->params.size());
+    const int rows = shard_rows_impl(H, o->shard_index, o->shard_count, o->band_rows);
+    const size_t npx3 = size_t(rows) * W * 3;
+    const bool want_grad = (o->flags & DRTB_FLAG_GRAD) != 0, want_img = (o->flags & DRTB_FLAG_IMAGE) != 0;
+    if (want_img && !img) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_IMAGE set but img is NULL");
+    if (want_grad && !grad) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_GRAD set but grad is NULL");
+    if (want_img && (rc = ensure(ctx, ctx->d_img, ctx->img_cap, std::max<size_t>(npx3, 3))) != DRTB_OK) return rc;
+    if (want_grad && (rc = ensure(ctx, ctx->d_grad, ctx->grad_cap, std::max<size_t>(P3, 3))) != DRTB_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    if (seed_img) {
+        if ((rc = ensure(ctx, ctx->d_seed, ctx->seed_cap, std::max<size_t>(npx3, 3))) != DRTB_OK) return rc;
+        CK(ctx, cudaMemcpyAsync(ctx->d_seed, seed_img, sizeof(double) * npx3, cudaMemcpyHostToDevice, st));
+    }
+    drtb_render_opts oo = *o;
+    if (stats) oo.flags |= DRTB_FLAG_STATS;
+    CK(ctx, cudaEventRecord(ctx->ev0, st));
+    rc = launch_render(ctx, &oo, seed_img ? ctx->d_seed : nullptr, ctx->d_img, ctx->d_grad, ctx->d_stats, st);
+    if (rc != DRTB_OK) return rc;
+    CK(ctx, cudaEventRecord(ctx->ev1, st));
+    if (want_img && npx3) CK(ctx, cudaMemcpyAsync(img, ctx->d_img, sizeof(double) * npx3, cudaMemcpyDeviceToHost, st));
+    if (want_grad && P3) CK(ctx, cudaMemcpyAsync(grad, ctx->d_grad, sizeof(double) * P3, cudaMemcpyDeviceToHost, st));
+    if (stats) CK(ctx, cudaMemcpyAsync(stats, ctx->d_stats, sizeof(drtb_stats), cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    if (stats) {
+        float ms = 0.f;
+        CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        stats->kernel_ms = ms;
+        stats->paths = uint64_t(rows) * W * o->spp;
+        stats->retraced_paths = 0;
+    }
+    return DRTB_OK;
+}
+
+int drtb_render_device(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed_img, double* d_img,
+                       double* d_grad, drtb_stats* d_stats, void* stream)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    int rc = validate_opts(ctx, o);
+    if (rc != DRTB_OK) return rc;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if ((o->flags & DRTB_FLAG_STATS) && !d_stats) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_STATS set but d_stats is NULL");
+    return launch_render(ctx, o, d_seed_img, d_img, d_grad, d_stats, (cudaStream_t)stream);
+}
+
+int drtb_trace_rays(drtb_ctx* ctx, const drtb_render_opts* o, int64_t n, const double* orig, const double* dir,
+                    const uint64_t* keys, double* radiance, double* jac)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    int rc = validate_opts(ctx, o);
+    if (rc != DRTB_OK) return rc;
+    if (n < 0 || (n && (!orig || !dir || !keys || !radiance))) return fail(ctx, DRTB_ERR_INVALID, "NULL ray buffers");
+    if (n == 0) return DRTB_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int P3 = int(ctx->params.size());
+    double *d_o = nullptr, *d_d = nullptr, *d_r = nullptr, *d_j = nullptr;
+    uint64_t* d_k = nullptr;
+    auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_r); cudaFree(d_j); cudaFree(d_k); };
+#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, DRTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    const size_t b3 = sizeof(double) * 3 * size_t(n);
+    CKF(cudaMalloc((void**)&d_o, b3)); CKF(cudaMalloc((void**)&d_d, b3)); CKF(cudaMalloc((void**)&d_r, b3));
+    CKF(cudaMalloc((void**)&d_k, sizeof(uint64_t) * size_t(n)));
+    if (jac && P3) { CKF(cudaMalloc((void**)&d_j, sizeof(double) * P3 * size_t(n))); CKF(cudaMemsetAsync(d_j, 0, sizeof(double) * P3 * size_t(n), ctx->stream)); }
+    CKF(cudaMemcpyAsync(d_o, orig, b3, cudaMemcpyHostToDevice, ctx->stream));
+    CKF(cudaMemcpyAsync(d_d, dir, b3, cudaMemcpyHostToDevice, ctx->stream));
+    CKF(cudaMemcpyAsync(d_k, keys, sizeof(uint64_t) * size_t(n), cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = int((n + kBlock - 1) / kBlock);
+    const int md = effective_max_depth(o);
+    if (o->precision == DRTB_F32)
+        trace_rays_kernel<float><<<grid, kBlock, 0, ctx->stream>>>(ctx->sc32, ctx->d_params, o->min_bounces, o->absorb, md, n, d_o, d_d, d_k, d_r, d_j);
+    else
+        trace_rays_kernel<double><<<grid, kBlock, 0, ctx->stream>>>(ctx->sc64, ctx->d_params, o->min_bounces, o->absorb, md, n, d_o, d_d, d_k, d_r, d_j);
+    CKF(cudaGetLastError());
+    ctx->launches++;
+    CKF(cudaMemcpyAsync(radiance, d_r, b3, cudaMemcpyDeviceToHost, ctx->stream));
+    if (jac && P3) CKF(cudaMemcpyAsync(jac, d_j, sizeof(double) * P3 * size_t(n), cudaMemcpyDeviceToHost, ctx->stream));
+    CKF(cudaStreamSynchronize(ctx->stream));
+#undef CKF
+    cleanup();
+    return DRTB_OK;
+}
+
+int drtb_fma_peak(drtb_ctx* ctx, int32_t precision, double* tflops)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    if (!tflops) return fail(ctx, DRTB_ERR_INVALID, "tflops is NULL");
+    if (precision != DRTB_F64 && precision != DRTB_F32) return fail(ctx, DRTB_ERR_INVALID, "unknown precision");
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, ctx->d_grad, ctx->grad_cap, 3);
+    if (rc != DRTB_OK) return rc;
+    const int grid = ctx->sm_count * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        if (precision == DRTB_F64) fma_peak_kernel<double><<<grid, 256, 0, ctx->stream>>>(ctx->d_grad, iters, 0.999999, 1e-7);
+        else fma_peak_kernel<float><<<grid, 256, 0, ctx->stream>>>((float*)ctx->d_grad, iters, 0.999999f, 1e-7f);
+        CK(ctx, cudaGetLastError());
+        ctx->launches++;
+        CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double flop = double(grid) * 256.0 * iters * 64.0 * 2.0;
+        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
+    return DRTB_OK;
+}
+
+uint64_t drtb_launch_count(const drtb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+uint32_t drtb_stream_draw(uint64_t key, uint32_t slot) { return drtb::stream_draw(key, slot); }
+
+} // extern "C"

@@ -1,0 +1,284 @@
+// path.cuh — the hot path: camera ray, closest hit, diffuse sampling, vertex
+// record, radiance recurrence and the tape-free adjoint.  One device function
+// per reference function; see each for the file:line it replaces.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/drtb.h"
+#include "real.cuh"
+#include "rng.cuh"
+
+namespace drtb {
+
+constexpr int kMaxPrims   = 32;    // analytic scenes ride in the kernel-parameter constant bank
+constexpr int kMaxParams  = 64;    // RGB parameters staged in shared memory
+constexpr int kMaxDepth   = 64;    // vertex-record capacity per path
+constexpr int kSmallP     = 8;     // <= this many parameters: per-thread smem gradient columns
+constexpr int kBlock      = 256;
+constexpr int kWarpsPerBlock = kBlock / 32;
+
+// Scene as the kernels see it.  Passed BY VALUE as a __grid_constant__ kernel
+// parameter: the closest-hit scan indexes prim[] with a warp-uniform i, so
+// every operand comes straight out of the constant bank with no load
+// instruction.  (Flattened Scene<T>/Shape<T>/Camera<T>, src/render.cpp:26-65.)
+template <typename R>
+struct DevScene {
+    R       prim[kMaxPrims][4];          // sphere: c.xyz, r ; plane: n.xyz (RAW), offset
+    int8_t  type[kMaxPrims];             // DRTB_SPHERE | DRTB_PLANE
+    int8_t  color[kMaxPrims];            // param index of the albedo, -1 = null BxDF
+    int8_t  emis[kMaxPrims];             // param index of the emission, -1 = no emitter
+    int32_t n_prims;
+    int32_t n_params;
+    // Camera (camera.hpp:51-60), constants folded on the host in double with the
+    // host libm (the same tan() the reference calls):
+    R eye[3], fwd[3], right[3], nup[3];  // nup = -1 * up
+    R aspect, tan_half;                  // W/H, tan(vfov/2)
+    R inv_w, inv_h;                      // only used by the float instantiation
+    int32_t width, height;
+};
+
+struct RenderArgs {
+    int32_t  spp, min_bounces, max_depth;
+    uint32_t flags;
+    double   absorb;
+    uint64_t key0;                       // seed * kSeedMul
+    int32_t  shard_index, shard_count, band_rows, shard_rows;
+    double   seed_scale;
+    const double* params;                // n_params x 3 (device)
+    const double* seed_img;              // shard_rows x W x 3 or null
+    double*  img;                        // shard_rows x W x 3 or null
+    double*  grad_partial;               // gridDim.x x (n_params*3)  (small-P path)
+    double*  grad_atomic;                // n_params*3, pre-zeroed     (large-P path)
+    drtb_stats* stats;                   // or null
+};
+
+template <typename R> struct V3 { R x, y, z; };
+
+template <typename R> __device__ __forceinline__ R dot(V3<R> a, V3<R> b)
+{
+    return a.x * b.x + a.y * b.y + a.z * b.z;        // vector.hpp:573-578
+}
+template <typename R> __device__ __forceinline__ V3<R> operator+(V3<R> a, V3<R> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename R> __device__ __forceinline__ V3<R> operator-(V3<R> a, V3<R> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <typename R> __device__ __forceinline__ V3<R> operator*(V3<R> a, R s) { return {a.x * s, a.y * s, a.z * s}; }
+template <typename R> __device__ __forceinline__ V3<R> cross(V3<R> a, V3<R> b)
+{
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};   // vector.hpp:592-600
+}
+template <typename R> __device__ __forceinline__ V3<R> normalize(V3<R> a)
+{
+    return a * Real<R>::rsqrt(dot(a, a));             // vector.hpp:580-590
+}
+
+// Per-block shared copy of what is looked up with a PER-LANE index (the prim a
+// lane actually hit, the parameters of its material).
+template <typename R>
+struct BlockScene {
+    R      prim[kMaxPrims][4];
+    R      param[kMaxParams * 3];
+    int8_t type[kMaxPrims], color[kMaxPrims], emis[kMaxPrims];
+};
+
+template <typename R>
+__device__ __forceinline__ void load_block_scene(BlockScene<R>& bs, const DevScene<R>& sc,
+                                                 const double* __restrict__ params)
+{
+    for (int i = threadIdx.x; i < sc.n_prims * 4; i += blockDim.x) bs.prim[i >> 2][i & 3] = sc.prim[i >> 2][i & 3];
+    for (int i = threadIdx.x; i < sc.n_prims; i += blockDim.x) {
+        bs.type[i] = sc.type[i]; bs.color[i] = sc.color[i]; bs.emis[i] = sc.emis[i];
+    }
+    for (int i = threadIdx.x; i < sc.n_params * 3; i += blockDim.x) bs.param[i] = R(params[i]);
+}
+
+// ---------------------------------------------------------------------------
+// Camera<T>::sample, camera.hpp:51-60: two draws (slots 0, 1), pdf = 1.
+// ---------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ V3<R> camera_ray(const DevScene<R>& sc, int x, int y, uint64_t base)
+{
+    R u0 = Real<R>::uniform(stream_draw_base(base, 0));
+    R u1 = Real<R>::uniform(stream_draw_base(base, 1));
+    R s = Real<R>::div(R(x) + u0, R(sc.width));
+    R t = Real<R>::div(R(y) + u1, R(sc.height));
+    R cx = (R(2) * s - R(1)) * sc.aspect * sc.tan_half;
+    R cy = (R(2) * t - R(1)) * sc.tan_half;
+    V3<R> d = {sc.fwd[0] + cx * sc.right[0] + cy * sc.nup[0],
+               sc.fwd[1] + cx * sc.right[1] + cy * sc.nup[1],
+               sc.fwd[2] + cx * sc.right[2] + cy * sc.nup[2]};
+    return normalize(d);
+}
+
+// ---------------------------------------------------------------------------
+// Pathtracer::raycast, pathtracer.hpp:72-89 with Plane::intersect
+// (shape.hpp:49-56) and Sphere::intersect (shape.hpp:78-103, a == 1).
+// Linear scan in scene order; `t > 0` acceptance, strict `<` so the first
+// shape wins ties.  i is warp-uniform: operands come from the constant bank.
+// ---------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R> d, R& tmin)
+{
+    tmin = Real<R>::inf();
+    int best = -1;
+    for (int i = 0; i < sc.n_prims; ++i) {
+        const R a0 = sc.prim[i][0], a1 = sc.prim[i][1], a2 = sc.prim[i][2], a3 = sc.prim[i][3];
+        R t;
+        if (sc.type[i] == DRTB_PLANE) {
+            R h = (o.x * a0 + o.y * a1 + o.z * a2) - a3;
+            R den = -(d.x * a0 + d.y * a1 + d.z * a2);       // dot(dir, -n)
+            t = Real<R>::div(h, den);
+        } else {
+            V3<R> oc = {o.x - a0, o.y - a1, o.z - a2};
+            R b = R(2) * dot(oc, d);
+            R c = dot(oc, oc) - a3 * a3;
+            R disc = b * b - R(4) * c;
+            t = R(-1);
+            if (disc >= R(0)) {
+                R sq = Real<R>::sqrt(disc);
+                R t1 = (-b - sq) * R(0.5);
+                R t2 = (-b + sq) * R(0.5);
+                t = t1 > R(0) ? t1 : t2;                      // t1 <= t2 always
+            }
+        }
+        if (t > R(0) && t < tmin) { tmin = t; best = i; }    // NaN fails both
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------
+// DiffuseBxDF::sample (bxdf.hpp:69-79) + make_frame (:29-41) + angle_to_dir
+// (:43-52), then cos = dot(n, dir_out) (pathtracer.hpp:103).  Returns
+// w = cos / pdf.  n is used RAW (the non-unit green-wall normal stays non-unit).
+// sin(asin(sqrt u)) = sqrt u and cos(asin(sqrt u)) = sqrt(1 - u); u < 1 always.
+// ---------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, R u_theta, R u_phi, R& w)
+{
+    R st = Real<R>::sqrt(u_theta);
+    R ct = Real<R>::sqrt(R(1) - u_theta);
+    R sp, cp;
+    Real<R>::sincos2pi(u_phi, &sp, &cp);
+    V3<R> tg;
+    if (Real<R>::abs(n.x) < Real<R>::abs(n.y)) tg = {R(1) - n.x * n.x, -n.y * n.x, -n.z * n.x};
+    else                                       tg = {-n.x * n.y, R(1) - n.y * n.y, -n.z * n.y};
+    tg = normalize(tg);
+    V3<R> bt = normalize(cross(n, tg));
+    R x = cp * st, y = sp * st;
+    V3<R> dout = {x * tg.x + y * bt.x + ct * n.x,
+                  x * tg.y + y * bt.y + ct * n.y,
+                  x * tg.z + y * bt.z + ct * n.z};
+    // pdf = cos(theta)/pi ; w = dot(n, dout) / pdf
+    w = Real<R>::div(dot(n, dout) * Real<R>::kPi, ct);
+    return dout;
+}
+
+// Per-path vertex record: what the reference keeps as ~17 heap-allocated tape
+// nodes per segment (vector.hpp:194-213) shrinks to (prim id, w) per vertex;
+// p_v is a function of the depth alone (pathtracer.hpp:130).
+template <typename R>
+struct PathRecord {
+    R       w[kMaxDepth];
+    uint8_t prim[kMaxDepth];
+};
+
+// ---------------------------------------------------------------------------
+// Pathtracer::trace + scatter (pathtracer.hpp:91-136), recursion unrolled into
+// a loop that only records vertices.  Returns the vertex count; `lit` tells
+// whether any vertex carries an emitter (otherwise radiance and every
+// gradient of the path are exactly zero and the sweeps are skipped).
+// `slot` is the next stream slot (2 after the camera draws).
+// ---------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScene<R>& bs,
+                                          uint64_t base, uint32_t slot, V3<R> o, V3<R> d,
+                                          int min_bounces, double absorb, int max_depth,
+                                          PathRecord<R>& rec, bool& lit, uint32_t& segments,
+                                          bool& truncated)
+{
+    int n = 0;
+    lit = false;
+    truncated = false;
+    for (int depth = 0;; ++depth) {
+        if (depth >= min_bounces) {                         // Russian roulette, :128-130
+            double u = Real<double>::uniform(stream_draw_base(base, slot++));
+            if (u < absorb) break;
+        }
+        if (n >= max_depth) { truncated = true; break; }
+        R t;
+        int k = closest_hit(sc, o, d, t);
+        ++segments;
+        if (k < 0) break;                                   // miss, :134-135
+        V3<R> pt = {o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
+        const int em = bs.emis[k], col = bs.color[k];
+        lit |= em >= 0;
+        rec.prim[n] = uint8_t(k);
+        if (col < 0) {                                      // null BxDF, :25-26, 38-39
+            rec.w[n++] = R(0);
+            break;
+        }
+        V3<R> nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]};
+        if (bs.type[k] == DRTB_SPHERE)                      // shape.hpp:105-106
+            nrm = normalize(V3<R>{pt.x - nrm.x, pt.y - nrm.y, pt.z - nrm.z});
+        R u_theta = Real<R>::uniform(stream_draw_base(base, slot));
+        R u_phi   = Real<R>::uniform(stream_draw_base(base, slot + 1));
+        slot += 2;
+        R w;
+        V3<R> dout = diffuse_sample(nrm, u_theta, u_phi, w);
+        rec.w[n++] = w;
+        o = {pt.x + R(1e-3) * dout.x, pt.y + R(1e-3) * dout.y, pt.z + R(1e-3) * dout.z};   // :99
+        d = dout;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// Radiance recurrence + adjoint: replaces the reverse tape (vector.hpp:120-318,
+// 418-557).  Backward sweep  L_v = (E_v + (rho_v/pi) L_{v+1} w_v) / p_v  gives
+// the path radiance L_0; forward sweep with g_0 = seed:
+//   gp = g_v / p_v ; grad[E_v] += gp ; grad[rho_v] += gp w_v L_{v+1} / pi ;
+//   g_{v+1} = gp w_v rho_v / pi.           (per channel; channels never mix)
+// Sink::add(param_index, channel, value) receives the contributions.
+// ---------------------------------------------------------------------------
+template <typename R, typename Sink>
+__device__ __forceinline__ void radiance_and_adjoint(const BlockScene<R>& bs, const PathRecord<R>& rec,
+                                                     int n, int min_bounces, R inv_p,
+                                                     bool want_grad, const R g0[3], R L0[3], Sink& sink)
+{
+    R Ls[kMaxDepth + 1][3];
+    R L[3] = {R(0), R(0), R(0)};
+    for (int v = n - 1; v >= 0; --v) {
+        const int k = rec.prim[v];
+        const int em = bs.emis[k], col = bs.color[k];
+        const R ip = v >= min_bounces ? inv_p : R(1);
+        const R f = rec.w[v] * Real<R>::kInvPi;
+        if (want_grad) { Ls[v + 1][0] = L[0]; Ls[v + 1][1] = L[1]; Ls[v + 1][2] = L[2]; }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            R E = em >= 0 ? bs.param[3 * em + c] : R(0);
+            R rho = col >= 0 ? bs.param[3 * col + c] : R(0);
+            L[c] = (E + rho * f * L[c]) * ip;
+        }
+    }
+    L0[0] = L[0]; L0[1] = L[1]; L0[2] = L[2];
+    if (!want_grad) return;
+    R g[3] = {g0[0], g0[1], g0[2]};
+    for (int v = 0; v < n; ++v) {
+        const int k = rec.prim[v];
+        const int em = bs.emis[k], col = bs.color[k];
+        const R ip = v >= min_bounces ? inv_p : R(1);
+        const R f = rec.w[v] * Real<R>::kInvPi;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            R gp = g[c] * ip;
+            if (em >= 0) sink.add(em, c, gp);
+            if (col >= 0) {
+                sink.add(col, c, gp * f * Ls[v + 1][c]);
+                g[c] = gp * f * bs.param[3 * col + c];
+            } else {
+                g[c] = R(0);
+            }
+        }
+    }
+}
+
+} // namespace drtb
