@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — Mpaths/s, forward + adjoint, Cornell box 1024x1024, 256 spp, 8 bounces.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path
+
+A step is one full render of the workload: every camera sample of every pixel
+traced to termination plus its gradient contribution (BASELINE.json `metric`).
+`value`  : device-resident throughput (outputs stay in HBM), CUDA-event timed.
+`e2e`    : the same through the C ABI call with HOST buffers (drtb_set_params +
+           drtb_render), parameter H2D and image/gradient D2H inside the timing.
+N > 1    : launched under torchrun, one rank per GPU; image rows are sharded in
+           interleaved bands, gradients summed with one NCCL all-reduce, image
+           bands all-gathered; max over ranks; weak scaling is NOT used -- the
+           workload is fixed, so "scaling" is "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Mpaths/s fwd+adjoint (Cornell 1024^2, 8 bounces)"
+UNIT = "Mpaths/s"
+FLOP_PER_SEGMENT = 280.0      # algorithmic FLOP per ray segment
+FLOP_PER_PATH = 30.0          # + camera ray per path
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=1024)
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--spp", type=int, default=256)
+    ap.add_argument("--bounces", type=int, default=8)
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--band-rows", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"cornell_box {a.width}x{a.height}, {a.spp} spp, min_bounces={a.bounces}, absorb=1 "
+            f"(= {a.bounces} bounces), grad wrt red/green/white albedo + emission, seed (1,1,1)")
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# --------------------------------------------------------------------------- CPU legs
+def cpu_render_rate(a, seconds_budget: float, threads: int | None = None):
+    """Times the reference's CPU path (oracle/_ref when built, else the C port)
+    on a bounded sample of the SAME workload (same scene, mb, absorb, stream);
+    Mpaths/s is resolution independent, so the sample is a smaller image."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib
+    import drt_b200 as drt
+    kind = "reference" if oracle_lib.have_ref() else "port"
+    if kind == "reference":
+        lib = oracle_lib.load_ref()
+        nthr = threads or lib.drt_ref_max_threads()
+        run = lambda sc, o: oracle_lib.ref_render(sc, o, threads=nthr)
+    else:
+        lib = oracle_lib.load_restate()
+        nthr = threads or lib.drt_oracle_max_threads()
+        run = lambda sc, o: oracle_lib.restate_render(sc, o, threads=nthr)
+    spp = min(a.spp, 16)
+    # pilot to size the sample
+    sc = drt.cornell_box(64, 64)
+    o = drt.make_opts(spp, a.bounces, 1.0)
+    side = 64
+    for _ in range(4):                     # grow the sample until one step fills the budget
+        t = time.perf_counter(); run(sc, o); pilot = time.perf_counter() - t
+        if pilot >= seconds_budget / 2 or side >= 1024:
+            break
+        rate = side * side * spp / max(pilot, 1e-6)
+        side = int(min(1024, max(64, (rate * seconds_budget / spp) ** 0.5))) // 8 * 8
+        sc = drt.cornell_box(side, side)
+
+    def step():
+        t = time.perf_counter(); run(sc, o); dt = time.perf_counter() - t
+        return side * side * spp, dt
+    sample = f"{side}x{side}, {spp} spp, min_bounces={a.bounces}, absorb=1, same stream, {nthr} OpenMP threads"
+    return kind, nthr, sample, step
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, nthr, sample, step = cpu_render_rate(a, seconds_budget=6.0)
+    for _ in range(a.warmup):
+        step()
+    paths, secs = 0, 0.0
+    for _ in range(a.steps):
+        p, dt = step(); paths += p; secs += dt
+    v = paths / secs / 1e6
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample_per_step": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthr, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_b200_arm(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import drt_b200 as drt
+    from differentiable_renderer_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus != world:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched under torchrun (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    W, H, spp, B = a.width, a.height, a.spp, a.bounces
+    prec = drt.F64 if a.precision == "f64" else drt.F32
+    scene = drt.cornell_box(W, H)
+    ctx = drt.Context(local)
+    ctx.upload(scene)
+    P = len(scene.params)
+    band = a.band_rows
+    rows = drt.shard_rows(H, rank, world, band)
+    equal = H % (band * world) == 0
+    stream = torch.cuda.current_stream()
+
+    opts = drt.make_opts(spp, B, 1.0, precision=prec, shard_index=rank, shard_count=world, band_rows=band)
+    d_img = torch.empty((rows, W, 3), dtype=torch.float64, device=dev)
+    d_grad = torch.empty((P, 3), dtype=torch.float64, device=dev)
+    d_full = torch.empty((H, W, 3), dtype=torch.float64, device=dev) if world > 1 else d_img
+    perm = sharding.deinterleave_index(H, world, band, dev) if (world > 1 and equal) else None
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def step_device():
+        ctx.render_device(opts, 0, d_img.data_ptr(), d_grad.data_ptr(), 0, stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(d_grad, op=dist.ReduceOp.SUM)          # the one collective of the path
+            if equal:
+                dist.all_gather_into_tensor(d_full.view(world, rows, W, 3), d_img)
+
+    # ---- stats run (untimed): segments/path for the algorithmic FLOP count
+    d_stats = torch.zeros(6, dtype=torch.int64, device=dev)
+    so = drt.make_opts(spp, B, 1.0, precision=prec, shard_index=rank, shard_count=world, band_rows=band,
+                       flags=drt.FLAG_IMAGE | drt.FLAG_GRAD | drt.FLAG_STATS)
+    ctx.render_device(so, 0, d_img.data_ptr(), d_grad.data_ptr(), d_stats.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    segs_local = int(d_stats[1].item()); lit_local = int(d_stats[2].item())
+    paths_local = rows * W * spp
+    tot = torch.tensor([paths_local, segs_local, lit_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    paths_total, segs_total, lit_total = (float(x) for x in tot.tolist())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(max(3, a.warmup)):
+        step_device()
+    sync_all()
+    sampler = ClockSampler(local); sampler.start(); time.sleep(0.25)
+    l0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    t0 = time.time()
+    sync_all()
+    for s0, s1, s2 in ev:
+        flush.zero_()                                  # evict L2 between timed iterations (untimed)
+        s0.record(stream)
+        ctx.render_device(opts, 0, d_img.data_ptr(), d_grad.data_ptr(), 0, stream.cuda_stream)
+        s1.record(stream)                              # render + gradient reduction kernels only
+        if world > 1:
+            dist.all_reduce(d_grad, op=dist.ReduceOp.SUM)
+            if equal:
+                dist.all_gather_into_tensor(d_full.view(world, rows, W, 3), d_img)
+        s2.record(stream)
+    sync_all()
+    t1 = time.time()
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop(t0, t1)
+    step_ms = sum(s0.elapsed_time(s2) for s0, s1, s2 in ev)
+    kern_ms = sum(s0.elapsed_time(s1) for s0, s1, s2 in ev) / a.steps
+    tt = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    ms_per_step = total_ms / a.steps
+    value = paths_total / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers
+    h_img = torch.empty((rows, W, 3), dtype=torch.float64).pin_memory()
+    h_grad = torch.empty((P, 3), dtype=torch.float64).pin_memory()
+    g_dev = torch.empty((P, 3), dtype=torch.float64, device=dev)
+    pvals = scene.param_values()
+
+    def step_e2e():
+        ctx.set_params(pvals)                                            # H2D: this step's inputs
+        ctx.render_host_ptrs(opts, 0, h_img.data_ptr(), h_grad.data_ptr())   # render + D2H image, gradients
+        if world > 1:
+            g_dev.copy_(h_grad, non_blocking=True)
+            dist.all_reduce(g_dev, op=dist.ReduceOp.SUM)
+            h_grad.copy_(g_dev)
+    for _ in range(2):
+        step_e2e()
+    sync_all()
+    te = time.perf_counter()
+    for _ in range(a.steps):
+        step_e2e()
+    sync_all()
+    e2e_s = time.perf_counter() - te
+    te_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+    e2e_value = paths_total / (float(te_t.item()) / a.steps) / 1e6
+    h2d = P * 3 * 8 * world
+    d2h = (H * W * 3 * 8) + P * 3 * 8 * world
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (render_kernel), rank 0's launch
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    fma_peak = ctx.fma_peak(prec)                                       # TFLOP/s, measured live
+    flop_launch = FLOP_PER_PATH * paths_local + FLOP_PER_SEGMENT * segs_local
+    achieved_tf = flop_launch / (kern_ms * 1e-3) / 1e12
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = rows * W * 3 * 8 + P * 3 * 8                            # the outputs; the scene is 0.4 KB
+    traffic = None
+    prof = ROOT / "profiles" / "ncu_render_kernel.json"
+    if prof.exists():
+        try:
+            pj = json.loads(prof.read_text())
+            key = f"{a.precision}_{W}x{H}_{spp}spp_b{B}"
+            traffic = pj.get(key, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {
+        "bound": "fma_" + a.precision, "kernel": "render_kernel",
+        "achieved": achieved_tf, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved_tf / fma_peak,
+        "traffic": traffic,
+        "peak_source": "measured live: drtb_fma_peak (dependent-free FMA chains, all SMs); "
+                       "MEASURED_PEAKS.json has no non-tensor FMA figure",
+        "algorithmic_flop_per_launch": flop_launch, "kernel_ms": kern_ms,
+        "hbm": {"bound": "hbm", "achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "note": "outputs only (24 B/pixel); the path is FMA-issue bound, not HBM bound"},
+    }
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": a.precision, "data": "synthetic",
+        "config": {"workload": workload_name(a), "width": W, "height": H, "spp": spp, "bounces": B,
+                   "paths_per_step": int(paths_total), "segments_per_path": segs_total / paths_total,
+                   "lit_path_fraction": lit_total / paths_total,
+                   "parallelism": f"pixel-band dp{world} (bands of {band} rows), 1 NCCL all-reduce of {P * 3} doubles"
+                                  + (" + image all-gather" if world > 1 else ""),
+                   "l2": "flushed between timed iterations (256 MiB memset, untimed)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "drtb_set_params + drtb_render (host buffers, pinned)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+
+    if world == 1 and not a.no_cpu_baseline:
+        kind, nthr, sample, step = cpu_render_rate(a, seconds_budget=12.0)
+        p, dt = step()
+        out["cpu_baseline"] = {"value": p / dt / 1e6, "unit": UNIT, "cores": nthr, "kind": kind, "sample": sample}
+    print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_b200_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,7 @@ _dp = C.POINTER(C.c_double)
 SYMBOLS = [
     ("drtb_abi_version", C.c_int, []),
     ("drtb_device_count", C.c_int, []),
+    ("drtb_struct_size", C.c_size_t, [C.c_int]),
     ("drtb_create", C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     ("drtb_destroy", None, [C.c_void_p]),
     ("drtb_last_error", C.c_char_p, [C.c_void_p]),
@@ -111,6 +112,9 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         fn.argtypes = args
     if lib.drtb_abi_version() != ABI_VERSION:
         raise DrtbLibraryMissing(f"{p}: ABI {lib.drtb_abi_version()} != {ABI_VERSION}")
+    for which, st in enumerate((Prim, Material, Camera, Scene, RenderOpts, Stats)):
+        if lib.drtb_struct_size(which) != C.sizeof(st):
+            raise DrtbLibraryMissing(f"{p}: layout of {st.__name__} differs from the ctypes mirror")
     if path is None:
         _lib = lib
     return lib

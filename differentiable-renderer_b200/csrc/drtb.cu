@@ -471,6 +471,19 @@ int drtb_device_count(void)
     return n;
 }
 
+size_t drtb_struct_size(int which)
+{
+    switch (which) {
+        case 0: return sizeof(drtb_prim);
+        case 1: return sizeof(drtb_material);
+        case 2: return sizeof(drtb_camera);
+        case 3: return sizeof(drtb_scene);
+        case 4: return sizeof(drtb_render_opts);
+        case 5: return sizeof(drtb_stats);
+        default: return 0;
+    }
+}
+
 int drtb_create(int device, drtb_ctx** out)
 {
     if (!out) return fail(nullptr, DRTB_ERR_INVALID, "out is NULL");

@@ -138,6 +138,11 @@ int drtb_abi_version(void);
 /* Number of usable CUDA devices (0 without a driver); callable without a GPU. */
 int drtb_device_count(void);
 
+/* sizeof() of the ABI structs as this library was compiled, so a binding can
+ * verify its mirror: 0 drtb_prim, 1 drtb_material, 2 drtb_camera, 3 drtb_scene,
+ * 4 drtb_render_opts, 5 drtb_stats; anything else returns 0. */
+size_t drtb_struct_size(int which);
+
 /* Create a context on CUDA device `device`.  Replaces nothing in the reference
  * (it has no device); it is the owner of the uploaded scene and scratch. */
 int drtb_create(int device, drtb_ctx** out);

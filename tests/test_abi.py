@@ -1,0 +1,94 @@
+"""The C-ABI library loads on a CPU-only machine, exports every symbol that
+include/drtb.h declares, agrees with the ctypes mirror on struct layout, and
+fails LOUDLY (no CPU fallback) when asked to compute without a GPU."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import drt_b200 as drt
+from drt_b200 import abi
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "drtb.h"
+
+
+def declared_symbols():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(drtb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_what_the_binding_binds():
+    assert declared_symbols() == sorted(name for name, _, _ in abi.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = drt.load_library()
+    out = subprocess.run(["nm", "-D", "--defined-only", str(abi.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (drtb_[a-z0-9_]+)", out))
+    for name in declared_symbols():
+        assert name in exported, f"{name} declared in drtb.h but not exported"
+        assert getattr(lib, name) is not None
+    assert lib.drtb_abi_version() == abi.ABI_VERSION
+
+
+def test_struct_layouts_match_the_ctypes_mirror():
+    lib = drt.load_library()
+    for which, st in enumerate((abi.Prim, abi.Material, abi.Camera, abi.Scene, abi.RenderOpts, abi.Stats)):
+        assert lib.drtb_struct_size(which) == C.sizeof(st)
+    assert lib.drtb_struct_size(99) == 0
+    assert C.sizeof(abi.Prim) == 48 and C.sizeof(abi.Material) == 16
+
+
+def test_no_gpu_means_a_loud_error_not_a_fallback():
+    lib = drt.load_library()
+    if lib.drtb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    h = C.c_void_p()
+    rc = lib.drtb_create(0, C.byref(h))
+    assert rc == abi.ERR_NO_DEVICE and not h.value
+    assert b"no CPU fallback" in lib.drtb_last_error(None)
+    with pytest.raises(drt.DrtbError):
+        drt.Context(0)
+    with pytest.raises(drt.DrtbError):
+        drt.render(drt.cornell_box(8, 8), 1)
+
+
+def test_missing_library_is_an_import_error():
+    with pytest.raises(drt.DrtbLibraryMissing):
+        abi.load_library(ROOT / "no" / "such" / "libdrtb.so")
+
+
+def test_null_context_is_rejected_without_crashing():
+    lib = drt.load_library()
+    o = drt.make_opts(1)
+    assert lib.drtb_render(None, C.byref(o), None, None, None, None) == abi.ERR_INVALID
+    assert lib.drtb_scene_upload(None, None) == abi.ERR_INVALID
+    assert lib.drtb_launch_count(None) == 0
+    lib.drtb_destroy(None)
+
+
+@pytest.mark.parametrize("H,count,band", [(22, 3, 4), (1024, 8, 8), (7, 2, 8), (16, 5, 1), (5, 8, 2), (0, 2, 4)])
+def test_shard_rows_partition_the_image(H, count, band):
+    from differentiable_renderer_b200 import sharding
+    lib = drt.load_library()
+    rows = [lib.drtb_shard_rows(H, r, count, band) for r in range(count)]
+    assert sum(rows) == H
+    assert rows == [len(sharding.shard_row_indices(H, r, count, band)) for r in range(count)]
+    assert lib.drtb_shard_rows(H, 0, 1, band) == H
+    assert lib.drtb_shard_rows(H, count, count, band) == 0          # index out of range
+
+
+def test_scene_flattening_matches_src_render_cpp():
+    sc = drt.cornell_box(640, 480).flatten()
+    assert (sc.n_prims, sc.n_materials, sc.n_params) == (9, 3, 4)
+    assert [sc.prims[i].type for i in range(9)] == [0, 0, 1, 1, 1, 1, 1, 1, 0]
+    assert list(sc.prims[3].v) == [1.0, 0.0, 0.1, -3.0]             # the non-unit green wall
+    assert sc.prims[8].material == -1 and sc.prims[8].emission == 3  # light: null BxDF
+    mats = [sc.materials[sc.prims[i].material].color for i in range(8)]
+    assert mats == [2, 2, 0, 1, 2, 2, 2, 2]                          # white shared by six shapes
+    assert np.allclose(list(sc.camera.forward), [0, 0, 1]) and np.allclose(list(sc.camera.right), [-1, 0, 0])
+    assert np.allclose(list(sc.camera.up), [0, 1, 0]) and sc.camera.vfov == 1.3963
