@@ -314,9 +314,21 @@ void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
     memset(&d, 0, sizeof d);
     d.n_prims = int(c.prims.size());
     d.n_params = int(c.params.size() / 3);
+    // scan slots: planes first, then spheres, each group in scene order
+    int slot = 0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int i = 0; i < d.n_prims; ++i) {
+            const drtb_prim& p = c.prims[i];
+            if ((pass == 0) != (p.type == DRTB_PLANE)) continue;
+            for (int j = 0; j < 4; ++j) d.prim[slot][j] = R(p.v[j]);
+            d.id[slot] = int8_t(i);
+            d.slot[i] = int8_t(slot);
+            ++slot;
+        }
+    d.n_planes = 0;
     for (int i = 0; i < d.n_prims; ++i) {
         const drtb_prim& p = c.prims[i];
-        for (int j = 0; j < 4; ++j) d.prim[i][j] = R(p.v[j]);
+        d.n_planes += p.type == DRTB_PLANE;
         d.type[i] = int8_t(p.type);
         d.color[i] = int8_t(p.material >= 0 ? c.materials[p.material].color : -1);
         d.emis[i] = int8_t(p.emission);

@@ -15,7 +15,7 @@ constexpr int kMaxPrims   = 32;    // analytic scenes ride in the kernel-paramet
 constexpr int kMaxParams  = 64;    // RGB parameters staged in shared memory
 constexpr int kMaxDepth   = 64;    // vertex-record capacity per path
 constexpr int kSmallP     = 8;     // <= this many parameters: per-thread smem gradient columns
-constexpr int kBlock      = 256;
+constexpr int kBlock      = 128;
 constexpr int kWarpsPerBlock = kBlock / 32;
 
 // Scene as the kernels see it.  Passed BY VALUE as a __grid_constant__ kernel
@@ -24,11 +24,16 @@ constexpr int kWarpsPerBlock = kBlock / 32;
 // instruction.  (Flattened Scene<T>/Shape<T>/Camera<T>, src/render.cpp:26-65.)
 template <typename R>
 struct DevScene {
-    R       prim[kMaxPrims][4];          // sphere: c.xyz, r ; plane: n.xyz (RAW), offset
+    // Scan order: all planes, then all spheres (two branch-free loops); id[] is
+    // the position in Scene<T>, which decides exact ties (pathtracer.hpp:80).
+    R       prim[kMaxPrims][4];          // plane: n.xyz (RAW), offset ; sphere: c.xyz, r
+    int8_t  id[kMaxPrims];               // scan slot -> scene index
+    // Indexed by SCENE index:
     int8_t  type[kMaxPrims];             // DRTB_SPHERE | DRTB_PLANE
     int8_t  color[kMaxPrims];            // param index of the albedo, -1 = null BxDF
     int8_t  emis[kMaxPrims];             // param index of the emission, -1 = no emitter
-    int32_t n_prims;
+    int8_t  slot[kMaxPrims];             // scene index -> scan slot
+    int32_t n_prims, n_planes;
     int32_t n_params;
     // Camera (camera.hpp:51-60), constants folded on the host in double with the
     // host libm (the same tan() the reference calls):
@@ -84,7 +89,8 @@ template <typename R>
 __device__ __forceinline__ void load_block_scene(BlockScene<R>& bs, const DevScene<R>& sc,
                                                  const double* __restrict__ params)
 {
-    for (int i = threadIdx.x; i < sc.n_prims * 4; i += blockDim.x) bs.prim[i >> 2][i & 3] = sc.prim[i >> 2][i & 3];
+    for (int i = threadIdx.x; i < sc.n_prims * 4; i += blockDim.x)      // bs.prim is by SCENE index
+        bs.prim[i >> 2][i & 3] = sc.prim[sc.slot[i >> 2]][i & 3];
     for (int i = threadIdx.x; i < sc.n_prims; i += blockDim.x) {
         bs.type[i] = sc.type[i]; bs.color[i] = sc.color[i]; bs.emis[i] = sc.emis[i];
     }
@@ -112,36 +118,45 @@ __device__ __forceinline__ V3<R> camera_ray(const DevScene<R>& sc, int x, int y,
 // ---------------------------------------------------------------------------
 // Pathtracer::raycast, pathtracer.hpp:72-89 with Plane::intersect
 // (shape.hpp:49-56) and Sphere::intersect (shape.hpp:78-103, a == 1).
-// Linear scan in scene order; `t > 0` acceptance, strict `<` so the first
-// shape wins ties.  i is warp-uniform: operands come from the constant bank.
+//
+// The reference divides once per plane (t = h / dot(dir, -n)).  Here every
+// candidate is kept as a fraction num/den with den > 0 and compared by
+// cross-multiplication, so a segment costs ONE division (for the winner)
+// instead of one per plane.  Acceptance is the reference's: t > 0, strictly
+// closer than the best so far, the lower scene index winning exact ties.
+// The slot index is warp-uniform: operands come from the constant bank.
 // ---------------------------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R> d, R& tmin)
 {
-    tmin = Real<R>::inf();
+    R bn = Real<R>::inf(), bd = R(1);                  // best t = bn / bd
     int best = -1;
-    for (int i = 0; i < sc.n_prims; ++i) {
+    const int np = sc.n_planes;
+#pragma unroll 2
+    for (int i = 0; i < np; ++i) {
         const R a0 = sc.prim[i][0], a1 = sc.prim[i][1], a2 = sc.prim[i][2], a3 = sc.prim[i][3];
-        R t;
-        if (sc.type[i] == DRTB_PLANE) {
-            R h = (o.x * a0 + o.y * a1 + o.z * a2) - a3;
-            R den = -(d.x * a0 + d.y * a1 + d.z * a2);       // dot(dir, -n)
-            t = Real<R>::div(h, den);
-        } else {
-            V3<R> oc = {o.x - a0, o.y - a1, o.z - a2};
-            R b = R(2) * dot(oc, d);
-            R c = dot(oc, oc) - a3 * a3;
-            R disc = b * b - R(4) * c;
-            t = R(-1);
-            if (disc >= R(0)) {
-                R sq = Real<R>::sqrt(disc);
-                R t1 = (-b - sq) * R(0.5);
-                R t2 = (-b + sq) * R(0.5);
-                t = t1 > R(0) ? t1 : t2;                      // t1 <= t2 always
-            }
-        }
-        if (t > R(0) && t < tmin) { tmin = t; best = i; }    // NaN fails both
+        const R h = Real<R>::fma(o.x, a0, Real<R>::fma(o.y, a1, Real<R>::fma(o.z, a2, -a3)));   // o.n - offset
+        const R g = Real<R>::fma(d.x, a0, Real<R>::fma(d.y, a1, d.z * a2));                     // d.n ; t = h / -g
+        const R num = g > R(0) ? -h : h;
+        const R den = Real<R>::abs(g);
+        // t > 0  <=>  num > 0 (den > 0);  den == 0 gives t = +-inf / NaN: rejected as in the reference
+        if (num > R(0) && den > R(0) && num * bd < bn * den) { bn = num; bd = den; best = sc.id[i]; }
     }
+    for (int i = np; i < sc.n_prims; ++i) {
+        const R a0 = sc.prim[i][0], a1 = sc.prim[i][1], a2 = sc.prim[i][2], a3 = sc.prim[i][3];
+        const V3<R> oc = {o.x - a0, o.y - a1, o.z - a2};
+        const R hb = dot(oc, d);                       // b/2
+        const R c = Real<R>::fma(-a3, a3, dot(oc, oc));
+        const R disc = Real<R>::fma(hb, hb, -c);       // (b^2 - 4c)/4, an exact rescaling
+        const R sq = Real<R>::sqrt(disc > R(0) ? disc : R(0));
+        const R t1 = -hb - sq, t2 = sq - hb;           // t1 <= t2
+        const R t = t1 > R(0) ? t1 : t2;
+        const int id = sc.id[i];
+        const R lhs = t * bd;
+        const bool closer = lhs < bn || (lhs == bn && id < best);
+        if (disc >= R(0) && t > R(0) && closer) { bn = t; bd = R(1); best = id; }
+    }
+    tmin = Real<R>::div(bn, bd);
     return best;
 }
 
@@ -149,26 +164,28 @@ __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R>
 // DiffuseBxDF::sample (bxdf.hpp:69-79) + make_frame (:29-41) + angle_to_dir
 // (:43-52), then cos = dot(n, dir_out) (pathtracer.hpp:103).  Returns
 // w = cos / pdf.  n is used RAW (the non-unit green-wall normal stays non-unit).
-// sin(asin(sqrt u)) = sqrt u and cos(asin(sqrt u)) = sqrt(1 - u); u < 1 always.
+// sin(asin(sqrt u)) = sqrt u, cos(asin(sqrt u)) = sqrt(1 - u); u < 1 always, so
+// one rsqrt(1 - u) yields both cos(theta) and the 1/cos(theta) that pdf needs.
 // ---------------------------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, R u_theta, R u_phi, R& w)
 {
-    R st = Real<R>::sqrt(u_theta);
-    R ct = Real<R>::sqrt(R(1) - u_theta);
+    const R st = Real<R>::sqrt(u_theta);
+    const R om = R(1) - u_theta;
+    const R inv_ct = Real<R>::rsqrt(om);
+    const R ct = om * inv_ct;
     R sp, cp;
     Real<R>::sincos2pi(u_phi, &sp, &cp);
     V3<R> tg;
-    if (Real<R>::abs(n.x) < Real<R>::abs(n.y)) tg = {R(1) - n.x * n.x, -n.y * n.x, -n.z * n.x};
-    else                                       tg = {-n.x * n.y, R(1) - n.y * n.y, -n.z * n.y};
+    if (Real<R>::abs(n.x) < Real<R>::abs(n.y)) tg = {Real<R>::fma(-n.x, n.x, R(1)), -n.y * n.x, -n.z * n.x};
+    else                                       tg = {-n.x * n.y, Real<R>::fma(-n.y, n.y, R(1)), -n.z * n.y};
     tg = normalize(tg);
-    V3<R> bt = normalize(cross(n, tg));
-    R x = cp * st, y = sp * st;
-    V3<R> dout = {x * tg.x + y * bt.x + ct * n.x,
-                  x * tg.y + y * bt.y + ct * n.y,
-                  x * tg.z + y * bt.z + ct * n.z};
-    // pdf = cos(theta)/pi ; w = dot(n, dout) / pdf
-    w = Real<R>::div(dot(n, dout) * Real<R>::kPi, ct);
+    const V3<R> bt = normalize(cross(n, tg));
+    const R x = cp * st, y = sp * st;
+    const V3<R> dout = {x * tg.x + y * bt.x + ct * n.x,
+                        x * tg.y + y * bt.y + ct * n.y,
+                        x * tg.z + y * bt.z + ct * n.z};
+    w = dot(n, dout) * Real<R>::kPi * inv_ct;          // dot(n, dout) / (cos(theta) / pi)
     return dout;
 }
 
