@@ -100,6 +100,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
+    if path is None and os.environ.get("DRTB_LIB"):          # development: A/B a variant build
+        path = os.environ["DRTB_LIB"]
     p = Path(path) if path else LIB_PATH
     if not p.exists():
         raise DrtbLibraryMissing(

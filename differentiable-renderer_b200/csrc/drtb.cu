@@ -63,8 +63,11 @@ struct JacSink {
 };
 
 // The pixel loop of src/render.cpp:72-86.
+#ifndef DRTB_MIN_BLOCKS
+#define DRTB_MIN_BLOCKS 1
+#endif
 template <typename R, bool SMALLP>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, DRTB_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ RenderArgs a)
 {
     extern __shared__ double s_acc[];              // SMALLP && grad: [n_params*3][kBlock]

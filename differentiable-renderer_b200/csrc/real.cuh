@@ -29,28 +29,25 @@ template <> struct Real<double> {
     static __device__ __forceinline__ double rcp(double x)
     {
         double r;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-        double e = ::fma(-x, r, 1.0); r = ::fma(r, e, r);       // 2^-44
-        e = ::fma(-x, r, 1.0);        r = ::fma(r, e, r);       // 2^-88
-        return r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // e0 <= 2^-23
+        const double e = ::fma(-x, r, 1.0);
+        return ::fma(r, ::fma(e, e, e), r);                      // r (1 + e + e^2): e0^3 = 2^-69
     }
     static __device__ __forceinline__ double div(double a, double b)
     {
-        double r = rcp(b), q = a * r;
+        const double r = rcp(b), q = a * r;
         return ::fma(::fma(-q, b, a), r, q);                     // one residual step
     }
     static __device__ __forceinline__ double rsqrt(double x)
     {
         double y;
-        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-        double e = ::fma(-x * y, y, 1.0); y = ::fma(y, 0.5 * e, y);          // 2^-43
-        e = ::fma(-x * y, y, 1.0);        y = ::fma(y, ::fma(0.375, e, 0.5) * e, y);
-        return y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); // e0 <= 2^-22
+        const double e = ::fma(-x * y, y, 1.0);                  // 1 - x y^2
+        return ::fma(y, ::fma(0.375, e, 0.5) * e, y);            // y (1 + e/2 + 3e^2/8): ~e0^3
     }
     static __device__ __forceinline__ double sqrt(double x)      // x >= 0
     {
-        double y = rsqrt(x), s = x * y;
-        s = ::fma(::fma(-s, s, x), 0.5 * y, s);
+        const double s = x * rsqrt(x);
         return x > 0.0 ? s : 0.0;                                // 0 * inf guard
     }
     // sin/cos(2*pi*u): the reference forms phi = 2*pi*u in double then calls

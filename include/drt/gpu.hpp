@@ -1,0 +1,157 @@
+// drt/gpu.hpp — the bridge from the include/drt object graph to the C ABI
+// (include/drtb.h -> libdrtb.so -> sm_100a kernels).  NEW relative to the
+// reference, which has no device code; everything here is host plumbing:
+// flatten Scene<T>/Camera<T> into PODs, own one drtb_ctx per device, turn
+// status codes into exceptions.  There is no CPU fallback: without a GPU every
+// call throws std::runtime_error carrying drtb_last_error().
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../drtb.h"
+#include "camera.hpp"
+#include "shape.hpp"
+#include "vector.hpp"
+
+namespace drt {
+
+template <typename T>
+using Scene = std::vector<Shape<T>*>;        // non-owning, caller order == tie-break priority
+
+namespace gpu {
+
+// Scene<T> as the C ABI wants it, plus the handles the gradients go back to.
+template <typename T>
+struct FlatScene {
+    std::vector<drtb_prim> prims;
+    std::vector<drtb_material> materials;
+    std::vector<double> params;                          // n x 3
+    std::vector<Vector<T, 3, true>> handles;             // one per unique parameter node
+
+    int param_index(const Vector<T, 3, true>& h)
+    {
+        for (std::size_t k = 0; k < handles.size(); ++k)
+            if (handles[k].id() == h.id()) return int(k);  // aliases share one accumulator
+        handles.push_back(h);
+        for (int c = 0; c < 3; ++c) params.push_back(double(h.detach()[c]));
+        return int(handles.size()) - 1;
+    }
+};
+
+template <typename T>
+FlatScene<T> flatten(const Scene<T>& scene)
+{
+    FlatScene<T> f;
+    std::vector<const BxDF<T>*> seen;
+    for (Shape<T>* s : scene) {
+        if (!s) throw std::runtime_error("drt::gpu::flatten: null shape in scene");
+        drtb_prim p{};
+        s->describe(p);
+        p.material = -1;
+        p.emission = -1;
+        if (const BxDF<T>* b = s->bxdf()) {
+            if (b->kind() != BxDFKind::Diffuse)
+                throw std::runtime_error("drt::gpu: only DiffuseBxDF is supported by the GPU path");
+            int m = -1;
+            for (std::size_t i = 0; i < seen.size(); ++i)
+                if (seen[i] == b) m = int(i);
+            if (m < 0) {
+                m = int(seen.size());
+                seen.push_back(b);
+                f.materials.push_back(drtb_material{DRTB_DIFFUSE, f.param_index(b->color()), 0.0});
+            }
+            p.material = m;
+        }
+        if (const Emitter<T>* e = s->emitter()) p.emission = f.param_index(e->emission());
+        f.prims.push_back(p);
+    }
+    return f;
+}
+
+template <typename T>
+drtb_camera flatten(const Camera<T>& cam)
+{
+    drtb_camera c{};
+    c.width = int32_t(cam.width());
+    c.height = int32_t(cam.height());
+    c.vfov = cam.vfov();
+    for (int i = 0; i < 3; ++i) {
+        c.eye[i] = double(cam.eye()[i]);
+        c.forward[i] = double(cam.forward()[i]);
+        c.right[i] = double(cam.right()[i]);
+        c.up[i] = double(cam.up()[i]);
+    }
+    return c;
+}
+
+// One drtb_ctx per device, created on first use, shared by every call.
+class Device {
+    drtb_ctx* ctx_ = nullptr;
+    std::vector<unsigned char> uploaded_;                 // bytes of the last uploaded geometry
+    std::vector<double> uploaded_params_;
+
+    [[noreturn]] void raise(const char* what, int rc) const
+    {
+        const char* m = drtb_last_error(ctx_);
+        throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + (m ? m : ""));
+    }
+
+public:
+    std::mutex lock;                                       // a ctx serves one host thread at a time
+
+    explicit Device(int index)
+    {
+        int rc = drtb_create(index, &ctx_);
+        if (rc != DRTB_OK) raise("drtb_create", rc);
+    }
+    ~Device() { drtb_destroy(ctx_); }
+    Device(const Device&) = delete;
+    Device& operator=(const Device&) = delete;
+    drtb_ctx* ctx() { return ctx_; }
+    void check(const char* what, int rc) const { if (rc != DRTB_OK) raise(what, rc); }
+
+    // Upload only what changed: an optimisation loop that moves parameters
+    // between renders pays for drtb_set_params, not for a scene rebuild.
+    template <typename T>
+    void sync(const FlatScene<T>& f, const drtb_camera& cam)
+    {
+        std::vector<unsigned char> bytes(sizeof cam + f.prims.size() * sizeof(drtb_prim) +
+                                         f.materials.size() * sizeof(drtb_material));
+        unsigned char* w = bytes.data();
+        std::memcpy(w, &cam, sizeof cam); w += sizeof cam;
+        if (!f.prims.empty()) std::memcpy(w, f.prims.data(), f.prims.size() * sizeof(drtb_prim));
+        w += f.prims.size() * sizeof(drtb_prim);
+        if (!f.materials.empty()) std::memcpy(w, f.materials.data(), f.materials.size() * sizeof(drtb_material));
+        if (bytes != uploaded_ || f.params.size() != uploaded_params_.size()) {
+            drtb_scene s{};
+            s.prims = f.prims.data(); s.n_prims = int32_t(f.prims.size());
+            s.materials = f.materials.data(); s.n_materials = int32_t(f.materials.size());
+            s.params = f.params.data(); s.n_params = int32_t(f.params.size() / 3);
+            s.camera = cam;
+            check("drtb_scene_upload", drtb_scene_upload(ctx_, &s));
+            uploaded_ = std::move(bytes);
+            uploaded_params_ = f.params;
+        } else if (f.params != uploaded_params_) {
+            check("drtb_set_params", drtb_set_params(ctx_, f.params.data(), int32_t(f.params.size() / 3)));
+            uploaded_params_ = f.params;
+        }
+    }
+};
+
+inline Device& device(int index = 0)
+{
+    static std::mutex m;
+    static std::map<int, std::unique_ptr<Device>> devices;
+    std::lock_guard<std::mutex> g(m);
+    auto& slot = devices[index];
+    if (!slot) slot.reset(new Device(index));
+    return *slot;
+}
+
+} // namespace gpu
+} // namespace drt

@@ -188,3 +188,34 @@ def test_max_depth_truncation_is_counted(drt, ctx):
     assert st.truncated_paths > 0
     img, grad, st = ctx.render(drt.make_opts(8, 1, 0.5), stats=True)
     assert st.truncated_paths == 0
+
+
+def test_cpp_dropin_program_matches_survey_kat(tmp_path):
+    """build/render = the reference application on the new include/drt headers:
+    Cornell box 96x64, 8 spp, -b 8 -p 1 must print the gradients of SURVEY KAT-1."""
+    import re
+    import subprocess
+    import sys
+    root = __import__("pathlib").Path(__file__).resolve().parent.parent
+    exe = root / "build" / "render"
+    if not exe.exists():
+        sys.path.insert(0, str(root))
+        import __graft_entry__
+        __graft_entry__.build()
+    out = tmp_path / "kat1.pfm"
+    r = subprocess.run([str(exe), "-x", "96", "-y", "64", "-n", "8", "-b", "8", "-p", "1", "-o", str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = {m.group(1): [float(x) for x in m.group(2).split()]
+           for m in re.finditer(r"^(\w+)\.grad = (.*)$", r.stdout, flags=re.M)}
+    want = {"red": [898.343750000, 888.701315078, 768.609375000], "green": [704.396093750, 691.322352896, 583.843125000],
+            "white": [1704.328125000, 1575.104482379, 1048.875000000],
+            "emission": [1850.101562500, 1752.005372524, 1434.281250000]}
+    for k, v in want.items():
+        assert np.abs(np.array(got[k]) - np.array(v)).max() < 1e-6
+    # the PFM holds the image (float32, bottom-up rows)
+    raw = out.read_bytes()
+    header_end = raw.index(b"-1.0\n") + 5
+    pix = np.frombuffer(raw[header_end:], dtype="<f4").reshape(64, 96, 3)[::-1]
+    ref_img, _ = restate_render(__import__("drt_b200").cornell_box(96, 64), __import__("drt_b200").make_opts(8, 8, 1.0))
+    assert np.abs(pix - ref_img).max() <= 1e-6
