@@ -103,8 +103,8 @@ __device__ __forceinline__ void load_block_scene(BlockScene<R>& bs, const DevSce
 template <typename R>
 __device__ __forceinline__ V3<R> camera_ray(const DevScene<R>& sc, int x, int y, uint64_t base)
 {
-    R u0 = Real<R>::uniform(stream_draw_base(base, 0));
-    R u1 = Real<R>::uniform(stream_draw_base(base, 1));
+    R u0 = Real<R>::uniform_fast(stream_draw_base(base, 0));
+    R u1 = Real<R>::uniform_fast(stream_draw_base(base, 1));
     R s = Real<R>::div(R(x) + u0, R(sc.width));
     R t = Real<R>::div(R(y) + u1, R(sc.height));
     R cx = (R(2) * s - R(1)) * sc.aspect * sc.tan_half;
@@ -137,10 +137,10 @@ __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R>
         const R a0 = sc.prim[i][0], a1 = sc.prim[i][1], a2 = sc.prim[i][2], a3 = sc.prim[i][3];
         const R h = Real<R>::fma(o.x, a0, Real<R>::fma(o.y, a1, Real<R>::fma(o.z, a2, -a3)));   // o.n - offset
         const R g = Real<R>::fma(d.x, a0, Real<R>::fma(d.y, a1, d.z * a2));                     // d.n ; t = h / -g
-        const R num = g > R(0) ? -h : h;
+        const R num = Real<R>::flip_if_pos(h, g);
         const R den = Real<R>::abs(g);
         // t > 0  <=>  num > 0 (den > 0);  den == 0 gives t = +-inf / NaN: rejected as in the reference
-        if (num > R(0) && den > R(0) && num * bd < bn * den) { bn = num; bd = den; best = sc.id[i]; }
+        if (Real<R>::is_pos(num) && Real<R>::is_nonzero(g) && num * bd < bn * den) { bn = num; bd = den; best = sc.id[i]; }
     }
     for (int i = np; i < sc.n_prims; ++i) {
         const R a0 = sc.prim[i][0], a1 = sc.prim[i][1], a2 = sc.prim[i][2], a3 = sc.prim[i][3];
@@ -148,13 +148,13 @@ __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R>
         const R hb = dot(oc, d);                       // b/2
         const R c = Real<R>::fma(-a3, a3, dot(oc, oc));
         const R disc = Real<R>::fma(hb, hb, -c);       // (b^2 - 4c)/4, an exact rescaling
-        const R sq = Real<R>::sqrt(disc > R(0) ? disc : R(0));
+        const R sq = Real<R>::sqrt(disc);              // NaN when disc < 0: every compare below fails
         const R t1 = -hb - sq, t2 = sq - hb;           // t1 <= t2
-        const R t = t1 > R(0) ? t1 : t2;
+        const R t = Real<R>::select(Real<R>::is_pos(t1), t1, t2);
         const int id = sc.id[i];
         const R lhs = t * bd;
         const bool closer = lhs < bn || (lhs == bn && id < best);
-        if (disc >= R(0) && t > R(0) && closer) { bn = t; bd = R(1); best = id; }
+        if (Real<R>::is_pos(t) && closer) { bn = t; bd = R(1); best = id; }
     }
     tmin = Real<R>::div(bn, bd);
     return best;
@@ -236,8 +236,8 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
         V3<R> nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]};
         if (bs.type[k] == DRTB_SPHERE)                      // shape.hpp:105-106
             nrm = normalize(V3<R>{pt.x - nrm.x, pt.y - nrm.y, pt.z - nrm.z});
-        R u_theta = Real<R>::uniform(stream_draw_base(base, slot));
-        R u_phi   = Real<R>::uniform(stream_draw_base(base, slot + 1));
+        R u_theta = Real<R>::uniform_fast(stream_draw_base(base, slot));
+        R u_phi   = Real<R>::uniform_fast(stream_draw_base(base, slot + 1));
         slot += 2;
         R w;
         V3<R> dout = diffuse_sample(nrm, u_theta, u_phi, w);

@@ -21,6 +21,23 @@ template <> struct Real<double> {
     static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000ll); }
     static __device__ __forceinline__ double abs(double a) { return ::fabs(a); }
     static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
+    // Sign logic on the high word: an FP64 compare/negate/select occupies the
+    // (half-rate) FP64 pipe, an integer op on the sign word does not.  These
+    // treat positive subnormals below 2^-1022 as zero -- nothing on this path
+    // gets within 300 orders of magnitude of that.
+    static __device__ __forceinline__ bool is_pos(double x) { return __double2hiint(x) > 0; }
+    static __device__ __forceinline__ bool is_nonzero(double x) { return (__double2hiint(x) << 1) != 0; }
+    // g > 0 ? -h : h   (sign(g) == + flips h)
+    static __device__ __forceinline__ double flip_if_pos(double h, double g)
+    {
+        const int gh = __double2hiint(g);
+        const int flip = (gh > 0) ? int(0x80000000u) : 0;
+        return __hiloint2double(__double2hiint(h) ^ flip, __double2loint(h));
+    }
+    static __device__ __forceinline__ double select(bool c, double a, double b)
+    {
+        return __hiloint2double(c ? __double2hiint(a) : __double2hiint(b), c ? __double2loint(a) : __double2loint(b));
+    }
     // The compiler's IEEE double division / sqrt cost ~25-40 instructions each
     // with a divergent slow-path call.  These are MUFU-seeded (2^-22) Newton
     // iterations with no branches: <= 1-2 ulp, i.e. ~2e-16 relative, twelve
@@ -45,15 +62,50 @@ template <> struct Real<double> {
         const double e = ::fma(-x * y, y, 1.0);                  // 1 - x y^2
         return ::fma(y, ::fma(0.375, e, 0.5) * e, y);            // y (1 + e/2 + 3e^2/8): ~e0^3
     }
-    static __device__ __forceinline__ double sqrt(double x)      // x >= 0
+    static __device__ __forceinline__ double sqrt(double x)      // x >= 0; NaN for x < 0
     {
         const double s = x * rsqrt(x);
-        return x > 0.0 ? s : 0.0;                                // 0 * inf guard
+        return select(is_nonzero(x), s, 0.0);                    // 0 * inf guard
     }
-    // sin/cos(2*pi*u): the reference forms phi = 2*pi*u in double then calls
-    // libm cos/sin (bxdf.hpp:74, 48-49); sincospi(2u) has exact range reduction
-    // and differs from that by ~1 ulp of phi.
-    static __device__ __forceinline__ void sincos2pi(double u, double* s, double* c) { ::sincospi(2.0 * u, s, c); }
+    // sin/cos(2*pi*u), u in [0, 1).  The reference forms phi = 2*pi*u in double and
+    // calls libm cos/sin (bxdf.hpp:74, 48-49).  Here: x = 4u = q + r with q the
+    // nearest integer and |r| <= 1/2, i.e. phi = q*pi/2 + r*pi/2 exactly; Taylor
+    // polynomials of sin/cos(r*pi/2) on |r*pi/2| <= pi/4 (truncation < 5e-17),
+    // then a quadrant rotation.  ~35 instructions against ~64 for sincospi().
+    static __device__ __forceinline__ void sincos2pi(double u, double* s, double* c)
+    {
+        const double x = 4.0 * u;
+        const int q = __double2int_rn(x);
+        const double r = x - double(q);                          // exact, |r| <= 0.5
+        const double t = r * 1.5707963267948966;                 // r * pi/2, |t| <= pi/4
+        const double t2 = t * t;
+        double ps = 2.8114572543455206e-15;                      //  1/17!
+        ps = ::fma(ps, t2, -7.6471637318198164e-13);             // -1/15!
+        ps = ::fma(ps, t2, 1.6059043836821613e-10);              //  1/13!
+        ps = ::fma(ps, t2, -2.5052108385441720e-08);             // -1/11!
+        ps = ::fma(ps, t2, 2.7557319223985893e-06);              //  1/9!
+        ps = ::fma(ps, t2, -1.9841269841269841e-04);             // -1/7!
+        ps = ::fma(ps, t2, 8.3333333333333332e-03);              //  1/5!
+        ps = ::fma(ps, t2, -1.6666666666666666e-01);             // -1/3!
+        const double sn = ::fma(ps * t2, t, t);
+        double pc = -1.5619206968586225e-16;                     // -1/18!
+        pc = ::fma(pc, t2, 4.7794773323873853e-14);              //  1/16!
+        pc = ::fma(pc, t2, -1.1470745597729725e-11);             // -1/14!
+        pc = ::fma(pc, t2, 2.0876756987868100e-09);              //  1/12!
+        pc = ::fma(pc, t2, -2.7557319223985888e-07);             // -1/10!
+        pc = ::fma(pc, t2, 2.4801587301587302e-05);              //  1/8!
+        pc = ::fma(pc, t2, -1.3888888888888889e-03);             // -1/6!
+        pc = ::fma(pc, t2, 4.1666666666666664e-02);              //  1/4!
+        pc = ::fma(pc, t2, -0.5);
+        const double cs = ::fma(pc, t2, 1.0);
+        // rotate by q quarter turns: (sin, cos)(a + q pi/2)
+        const bool swap = q & 1;
+        const double a = select(swap, cs, sn), b = select(swap, sn, cs);
+        const int sflip = (q & 2) ? int(0x80000000u) : 0;                 // sin: - for q = 2, 3
+        const int cflip = ((q + 1) & 2) ? int(0x80000000u) : 0;           // cos: - for q = 1, 2
+        *s = __hiloint2double(__double2hiint(a) ^ sflip, __double2loint(a));
+        *c = __hiloint2double(__double2hiint(b) ^ cflip, __double2loint(b));
+    }
     // random::uniform(): double(k) / RAND_MAX (random.hpp:9), correctly rounded:
     // q0 = RN(k/M) up to 1 ulp, one FMA residual step makes it exact (Markstein).
     static __device__ __forceinline__ double uniform(uint32_t k)
@@ -64,6 +116,9 @@ template <> struct Real<double> {
         double r = ::fma(-q, M, a);
         return ::fma(r, inv, q);
     }
+    // The same to 1 ulp (k * RN(1/M)) for draws that feed continuous quantities
+    // (pixel jitter, theta, phi); Russian roulette keeps the exact one.
+    static __device__ __forceinline__ double uniform_fast(uint32_t k) { return double(k) * (1.0 / 2147483647.0); }
 };
 
 template <> struct Real<float> {
@@ -72,6 +127,10 @@ template <> struct Real<float> {
     static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
     static __device__ __forceinline__ float abs(float a) { return ::fabsf(a); }
     static __device__ __forceinline__ float fma(float a, float b, float c) { return ::fmaf(a, b, c); }
+    static __device__ __forceinline__ bool is_pos(float x) { return x > 0.0f; }
+    static __device__ __forceinline__ bool is_nonzero(float x) { return x != 0.0f; }
+    static __device__ __forceinline__ float flip_if_pos(float h, float g) { return g > 0.0f ? -h : h; }
+    static __device__ __forceinline__ float select(bool c, float a, float b) { return c ? a : b; }
     static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
     static __device__ __forceinline__ float rsqrt(float x) { return ::rsqrtf(x); }
@@ -89,6 +148,7 @@ template <> struct Real<float> {
     {
         return float(k >> 7) * (1.0f / 16777216.0f);
     }
+    static __device__ __forceinline__ float uniform_fast(uint32_t k) { return uniform(k); }
 };
 
 } // namespace drtb
