@@ -63,22 +63,26 @@ struct JacSink {
 };
 
 // The pixel loop of src/render.cpp:72-86.
+//   SMALLP: <= kSmallP parameters, gradients in per-thread shared columns
+//   QUEUE : spp >= 32 and max_depth <= kQueueDepth: lit paths are compacted
+//           through a per-warp shared-memory ring before the sweeps
 #ifndef DRTB_MIN_BLOCKS
 #define DRTB_MIN_BLOCKS 1
 #endif
-template <typename R, bool SMALLP>
+template <typename R, bool SMALLP, bool QUEUE>
 __global__ void __launch_bounds__(kBlock, DRTB_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ RenderArgs a)
 {
-    extern __shared__ double s_acc[];              // SMALLP && grad: [n_params*3][kBlock]
+    extern __shared__ double s_dyn[];              // [acc: n_params*3*kBlock doubles][rings]
     __shared__ BlockScene<R> bs;
     __shared__ double s_red[kSmallP * 3][kWarpsPerBlock];
 
     const bool want_grad = (a.flags & DRTB_FLAG_GRAD) != 0;
     const int P3 = sc.n_params * 3;
+    double* s_acc = s_dyn;
+    const int acc_doubles = (SMALLP && want_grad) ? P3 * kBlock : 0;
     load_block_scene(bs, sc, a.params);
-    if (SMALLP && want_grad)
-        for (int i = threadIdx.x; i < P3 * kBlock; i += kBlock) s_acc[i] = 0.0;
+    for (int i = threadIdx.x; i < acc_doubles; i += kBlock) s_acc[i] = 0.0;
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -91,6 +95,15 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     const long long n_tasks = (npix + ppw - 1) / ppw;
     const long long n_warps = (long long)gridDim.x * kWarpsPerBlock;
     const R inv_p = a.absorb < 1.0 ? R(1.0 / (1.0 - a.absorb)) : R(0);
+
+    // this warp's ring (QUEUE only)
+    const int qdepth = a.max_depth;
+    unsigned char* ring = reinterpret_cast<unsigned char*>(s_dyn + acc_doubles) +
+                          (QUEUE ? size_t(warp) * queue_bytes_per_warp(qdepth, sizeof(R)) : 0);
+    R* ring_w = reinterpret_cast<R*>(ring);
+    uint8_t* ring_prim = ring + size_t(qdepth) * kQueueSlots * sizeof(R);
+    uint8_t* ring_n = ring_prim + size_t(qdepth) * kQueueSlots;
+    int q_head = 0, q_count = 0;                   // warp-uniform
 
     SmemSink ssink{s_acc + threadIdx.x};
     AtomicSink asink{a.grad_atomic};
@@ -115,27 +128,60 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
             }
         }
         double acc[3] = {0.0, 0.0, 0.0};
+
+        // sweeps over one record; accumulates this lane's share of the pixel and the gradients
+        auto sweep = [&](const auto& rec, int n) {
+            R L0[3];
+            if (SMALLP) radiance_and_adjoint(bs, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ssink);
+            else        radiance_and_adjoint(bs, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, asink);
+            acc[0] += double(L0[0]); acc[1] += double(L0[1]); acc[2] += double(L0[2]);       // render.cpp:78
+            n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
+        };
+        // run the sweeps on the first m queued records, one per lane
+        auto drain = [&](int m) {
+            __syncwarp();
+            if (lane < m) {
+                const int slot = (q_head + lane) & (kQueueSlots - 1);
+                QueueView<R> qv{ring_w + slot, ring_prim + slot};
+                sweep(qv, ring_n[slot]);
+            }
+            __syncwarp();
+            q_head = (q_head + m) & (kQueueSlots - 1);
+            q_count -= m;
+        };
+
         for (int pass = 0; pass < passes; ++pass) {
             const int i = i0 + pass * 32;
+            bool lit = false;
+            int n = 0;
+            PathRecord<R> rec;
             if (lane_ok && i < spp) {
                 const uint64_t key = a.key0 + ((uint64_t)y * W + x) * (uint64_t)spp + (uint64_t)i;
                 const uint64_t base = key * kKeyMul;
                 V3<R> o = {sc.eye[0], sc.eye[1], sc.eye[2]};
                 V3<R> d = camera_ray(sc, x, y, base);
-                PathRecord<R> rec;
-                bool lit, truncated;
-                int n = trace_path(sc, bs, base, 2u, o, d, a.min_bounces, a.absorb, a.max_depth,
-                                   rec, lit, n_seg, truncated);
+                bool truncated;
+                n = trace_path(sc, bs, base, 2u, o, d, a.min_bounces, a.absorb, a.max_depth, rec, lit, n_seg, truncated);
                 n_trunc += truncated;
+                if (!QUEUE && lit) sweep(rec, n);
+            }
+            if (QUEUE) {
+                const unsigned m = __ballot_sync(0xffffffffu, lit);
                 if (lit) {
-                    R L0[3];
-                    if (SMALLP) radiance_and_adjoint(bs, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ssink);
-                    else        radiance_and_adjoint(bs, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, asink);
-                    acc[0] += double(L0[0]); acc[1] += double(L0[1]); acc[2] += double(L0[2]);   // render.cpp:78
-                    n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
+                    const int slot = (q_head + q_count + __popc(m & ((1u << lane) - 1u))) & (kQueueSlots - 1);
+                    for (int v = 0; v < n; ++v) {
+                        ring_w[v * kQueueSlots + slot] = rec.w_[v];
+                        ring_prim[v * kQueueSlots + slot] = rec.prim_[v];
+                    }
+                    ring_n[slot] = uint8_t(n);
                 }
+                q_count += __popc(m);
+                if (q_count >= 32) drain(32);
             }
         }
+        // every queued record belongs to this task's pixel: finish them before the pixel is written
+        if (QUEUE && q_count > 0) drain(q_count);
+
         // pixel_radiance / samples (render.cpp:82): sum the lanes of each pixel
         if (a.img) {
             if (spp >= 32) {
@@ -163,7 +209,7 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     }
 
     if (SMALLP && want_grad) {
-        // block reduction in a fixed order: lanes (xor tree) -> warps (0..7)
+        // block reduction in a fixed order: lanes (xor tree) -> warps (0..3)
         for (int j = 0; j < P3; ++j) {
             double v = warp_sum(s_acc[j * kBlock + threadIdx.x]);
             if (lane == 0) s_red[j][warp] = v;
@@ -279,7 +325,6 @@ struct drtb_ctx {
     double* d_grad = nullptr;     size_t grad_cap = 0;
     drtb_stats* d_stats = nullptr;
     unsigned long long launches = 0;
-    int occ[2][2] = {{0, 0}, {0, 0}};               // [precision][smallp] blocks per SM
 };
 
 namespace {
@@ -367,19 +412,48 @@ struct Plan {
     uint64_t paths;
 };
 
-template <typename R, bool SMALLP>
-int occupancy(drtb_ctx* ctx, size_t smem, int& out)
+// Resident blocks per SM of one render_kernel instantiation at `smem` dynamic bytes.
+template <typename K>
+int occupancy(drtb_ctx* ctx, K kernel, size_t smem, int& out)
 {
-    int& cached = ctx->occ[sizeof(R) == 4][SMALLP];
-    if (cached == 0 || SMALLP) {
-        CK(ctx, cudaFuncSetAttribute(render_kernel<R, SMALLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        int nb = 0;
-        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<R, SMALLP>, kBlock, smem));
-        if (nb < 1) return fail(ctx, DRTB_ERR_CUDA, "render kernel does not fit on an SM");
-        cached = nb;
-    }
-    out = cached;
+    CK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int nb = 0;
+    CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kBlock, smem));
+    if (nb < 1) return fail(ctx, DRTB_ERR_CUDA, "render kernel does not fit on an SM");
+    out = nb;
     return DRTB_OK;
+}
+
+template <typename R, bool SMALLP, bool QUEUE>
+int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t smem, long long need_blocks,
+                   int P3, bool want_grad, cudaStream_t stream, int& grid_out)
+{
+    int per_sm = 0;
+    int rc = occupancy(ctx, render_kernel<R, SMALLP, QUEUE>, smem, per_sm);
+    if (rc != DRTB_OK) return rc;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > need_blocks) grid = need_blocks;
+    if (grid < 1) grid = 1;
+    if (want_grad && SMALLP) {
+        rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, size_t(grid) * P3);
+        if (rc != DRTB_OK) return rc;
+        a.grad_partial = ctx->d_partial;
+    }
+    render_kernel<R, SMALLP, QUEUE><<<int(grid), kBlock, smem, stream>>>(sc, a);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    grid_out = int(grid);
+    return DRTB_OK;
+}
+
+template <typename R>
+int launch_precision(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, bool smallp, bool queue, size_t smem,
+                     long long need_blocks, int P3, bool want_grad, cudaStream_t stream, int& grid)
+{
+    if (smallp) return queue ? launch_variant<R, true, true>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid)
+                             : launch_variant<R, true, false>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid);
+    return queue ? launch_variant<R, false, true>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid)
+                 : launch_variant<R, false, false>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid);
 }
 
 int validate_opts(drtb_ctx* ctx, const drtb_render_opts* o)
@@ -429,42 +503,28 @@ int launch_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed
     a.stats = (o->flags & DRTB_FLAG_STATS) ? d_stats : nullptr;
 
     const bool smallp = P <= kSmallP;
-    const size_t smem = (smallp && want_grad) ? size_t(P3) * kBlock * sizeof(double) : 0;
-    int per_sm = 0, rc;
     const bool f32 = o->precision == DRTB_F32;
-    if (f32) rc = smallp ? occupancy<float, true>(ctx, smem, per_sm) : occupancy<float, false>(ctx, smem, per_sm);
-    else     rc = smallp ? occupancy<double, true>(ctx, smem, per_sm) : occupancy<double, false>(ctx, smem, per_sm);
-    if (rc != DRTB_OK) return rc;
+    // lit-path compaction needs whole-pixel warp tasks and records that fit the ring
+    const bool queue = o->spp >= 32 && a.max_depth <= kQueueDepth;
+    size_t smem = (smallp && want_grad) ? size_t(P3) * kBlock * sizeof(double) : 0;
+    if (queue) smem += kWarpsPerBlock * queue_bytes_per_warp(a.max_depth, f32 ? sizeof(float) : sizeof(double));
+    smem = (smem + 15) & ~size_t(15);
     const long long npix = (long long)rows * W;
     const int ppw = o->spp >= 32 ? 1 : 32 / o->spp;
     const long long n_tasks = (npix + ppw - 1) / ppw;
-    long long grid = (long long)ctx->sm_count * per_sm;
     const long long need = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
 
     if (a.stats) {
         CK(ctx, cudaMemsetAsync(d_stats, 0, sizeof(drtb_stats), stream));
     }
-    if (want_grad) {
-        if (smallp) {
-            rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, size_t(grid) * P3);
-            if (rc != DRTB_OK) return rc;
-            a.grad_partial = ctx->d_partial;
-        } else {
-            CK(ctx, cudaMemsetAsync(d_grad, 0, sizeof(double) * P3, stream));
-            a.grad_atomic = d_grad;
-        }
+    if (want_grad && !smallp) {
+        CK(ctx, cudaMemsetAsync(d_grad, 0, sizeof(double) * P3, stream));
+        a.grad_atomic = d_grad;
     }
-    if (f32) {
-        if (smallp) render_kernel<float, true><<<int(grid), kBlock, smem, stream>>>(ctx->sc32, a);
-        else        render_kernel<float, false><<<int(grid), kBlock, smem, stream>>>(ctx->sc32, a);
-    } else {
-        if (smallp) render_kernel<double, true><<<int(grid), kBlock, smem, stream>>>(ctx->sc64, a);
-        else        render_kernel<double, false><<<int(grid), kBlock, smem, stream>>>(ctx->sc64, a);
-    }
-    CK(ctx, cudaGetLastError());
-    ctx->launches++;
+    int grid = 0;
+    int rc = f32 ? launch_precision<float>(ctx, ctx->sc32, a, smallp, queue, smem, need, P3, want_grad, stream, grid)
+                 : launch_precision<double>(ctx, ctx->sc64, a, smallp, queue, smem, need, P3, want_grad, stream, grid);
+    if (rc != DRTB_OK) return rc;
     if (want_grad && smallp) {
         reduce_grad_kernel<<<1, 256, 0, stream>>>(ctx->d_partial, int(grid), P3, d_grad);
         CK(ctx, cudaGetLastError());

@@ -194,9 +194,32 @@ __device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, R u_theta, R u_phi, R& 
 // p_v is a function of the depth alone (pathtracer.hpp:130).
 template <typename R>
 struct PathRecord {
-    R       w[kMaxDepth];
-    uint8_t prim[kMaxDepth];
+    R       w_[kMaxDepth];
+    uint8_t prim_[kMaxDepth];
+    __device__ __forceinline__ R w(int v) const { return w_[v]; }
+    __device__ __forceinline__ int prim(int v) const { return prim_[v]; }
 };
+
+// Lit-path compaction.  Only ~16 % of the Cornell box's paths reach the light,
+// so running the sweeps right after each trace keeps ~5 of 32 lanes busy.
+// Instead every lit lane appends its record to a per-warp ring in shared
+// memory (SoA, slot-contiguous => conflict-free) and the warp runs the sweeps
+// on 32 queued records at a time.  Ballot-ordered, hence deterministic.
+constexpr int kQueueSlots = 64;    // ring capacity per warp (power of two)
+constexpr int kQueueDepth = 16;    // deepest record the ring stores; deeper runs use the direct path
+
+template <typename R>
+struct QueueView {                 // one record of one warp's ring
+    const R* w_;                   // &ring_w[slot], stride kQueueSlots
+    const uint8_t* prim_;
+    __device__ __forceinline__ R w(int v) const { return w_[v * kQueueSlots]; }
+    __device__ __forceinline__ int prim(int v) const { return prim_[v * kQueueSlots]; }
+};
+
+__host__ __device__ constexpr size_t queue_bytes_per_warp(int depth, size_t real_size)
+{
+    return size_t(depth) * kQueueSlots * real_size + size_t(depth) * kQueueSlots + kQueueSlots;
+}
 
 // ---------------------------------------------------------------------------
 // Pathtracer::trace + scatter (pathtracer.hpp:91-136), recursion unrolled into
@@ -228,9 +251,9 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
         V3<R> pt = {o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
         const int em = bs.emis[k], col = bs.color[k];
         lit |= em >= 0;
-        rec.prim[n] = uint8_t(k);
+        rec.prim_[n] = uint8_t(k);
         if (col < 0) {                                      // null BxDF, :25-26, 38-39
-            rec.w[n++] = R(0);
+            rec.w_[n++] = R(0);
             break;
         }
         V3<R> nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]};
@@ -241,7 +264,7 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
         slot += 2;
         R w;
         V3<R> dout = diffuse_sample(nrm, u_theta, u_phi, w);
-        rec.w[n++] = w;
+        rec.w_[n++] = w;
         o = {pt.x + R(1e-3) * dout.x, pt.y + R(1e-3) * dout.y, pt.z + R(1e-3) * dout.z};   // :99
         d = dout;
     }
@@ -256,18 +279,18 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
 //   g_{v+1} = gp w_v rho_v / pi.           (per channel; channels never mix)
 // Sink::add(param_index, channel, value) receives the contributions.
 // ---------------------------------------------------------------------------
-template <typename R, typename Sink>
-__device__ __forceinline__ void radiance_and_adjoint(const BlockScene<R>& bs, const PathRecord<R>& rec,
+template <typename R, typename Rec, typename Sink>
+__device__ __forceinline__ void radiance_and_adjoint(const BlockScene<R>& bs, const Rec& rec,
                                                      int n, int min_bounces, R inv_p,
                                                      bool want_grad, const R g0[3], R L0[3], Sink& sink)
 {
     R Ls[kMaxDepth + 1][3];
     R L[3] = {R(0), R(0), R(0)};
     for (int v = n - 1; v >= 0; --v) {
-        const int k = rec.prim[v];
+        const int k = rec.prim(v);
         const int em = bs.emis[k], col = bs.color[k];
         const R ip = v >= min_bounces ? inv_p : R(1);
-        const R f = rec.w[v] * Real<R>::kInvPi;
+        const R f = rec.w(v) * Real<R>::kInvPi;
         if (want_grad) { Ls[v + 1][0] = L[0]; Ls[v + 1][1] = L[1]; Ls[v + 1][2] = L[2]; }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -280,10 +303,10 @@ __device__ __forceinline__ void radiance_and_adjoint(const BlockScene<R>& bs, co
     if (!want_grad) return;
     R g[3] = {g0[0], g0[1], g0[2]};
     for (int v = 0; v < n; ++v) {
-        const int k = rec.prim[v];
+        const int k = rec.prim(v);
         const int em = bs.emis[k], col = bs.color[k];
         const R ip = v >= min_bounces ? inv_p : R(1);
-        const R f = rec.w[v] * Real<R>::kInvPi;
+        const R f = rec.w(v) * Real<R>::kInvPi;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             R gp = g[c] * ip;
