@@ -465,7 +465,6 @@ int validate_opts(drtb_ctx* ctx, const drtb_render_opts* o)
     if (!(o->absorb >= 0.0 && o->absorb <= 1.0)) return fail(ctx, DRTB_ERR_INVALID, "absorb must be in [0, 1]");
     if (o->precision == DRTB_MIXED) return fail(ctx, DRTB_ERR_UNSUPPORTED, "DRTB_MIXED is not implemented in this build");
     if (o->precision != DRTB_F64 && o->precision != DRTB_F32) return fail(ctx, DRTB_ERR_INVALID, "unknown precision");
-    if (o->adjoint_seed != 0) return fail(ctx, DRTB_ERR_UNSUPPORTED, "decorrelated adjoint is not implemented in this build");
     if (o->shard_count > 1 && (o->shard_index < 0 || o->shard_index >= o->shard_count || o->band_rows < 1))
         return fail(ctx, DRTB_ERR_INVALID, "bad shard (index, count, band_rows)");
     if (o->max_depth < 0 || o->max_depth > kMaxDepth)
@@ -481,9 +480,9 @@ int effective_max_depth(const drtb_render_opts* o)
     return o->absorb == 1.0 ? std::max(1, o->min_bounces) : kMaxDepth;
 }
 
-// Enqueue the render (+ gradient reduction) on `stream`; all pointers device.
-int launch_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed, double* d_img,
-                  double* d_grad, drtb_stats* d_stats, cudaStream_t stream)
+// Enqueue one render (+ gradient reduction) on `stream`; all pointers device.
+int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed, double* d_img,
+                       double* d_grad, drtb_stats* d_stats, cudaStream_t stream)
 {
     const int W = ctx->camera.width, H = ctx->camera.height;
     const int P = int(ctx->params.size() / 3), P3 = P * 3;
@@ -531,6 +530,28 @@ int launch_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed
         ctx->launches++;
     }
     return DRTB_OK;
+}
+
+// Decorrelated adjoint (the reference's integrate_unbiased idea, integrate.hpp:39-52:
+// fresh samples for the backward pass): the image comes from stream `seed`, the
+// gradients from stream `adjoint_seed`.  With a counter-based RNG that is simply
+// a second, gradient-only launch keyed differently.
+int launch_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed, double* d_img,
+                  double* d_grad, drtb_stats* d_stats, cudaStream_t stream)
+{
+    const bool split = o->adjoint_seed != 0 && (o->flags & DRTB_FLAG_GRAD) && (o->flags & DRTB_FLAG_IMAGE);
+    if (!split) {
+        drtb_render_opts one = *o;
+        if (o->adjoint_seed != 0 && (o->flags & DRTB_FLAG_GRAD)) one.seed = o->adjoint_seed;   // gradient-only call
+        return launch_render_once(ctx, &one, d_seed, d_img, d_grad, d_stats, stream);
+    }
+    drtb_render_opts fwd = *o, adj = *o;
+    fwd.flags &= ~DRTB_FLAG_GRAD;
+    adj.flags &= ~(DRTB_FLAG_IMAGE | DRTB_FLAG_STATS);       // stats describe the image pass
+    adj.seed = o->adjoint_seed;
+    int rc = launch_render_once(ctx, &fwd, nullptr, d_img, nullptr, d_stats, stream);
+    if (rc != DRTB_OK) return rc;
+    return launch_render_once(ctx, &adj, d_seed, nullptr, d_grad, nullptr, stream);
 }
 
 } // namespace

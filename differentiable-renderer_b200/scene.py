@@ -199,11 +199,11 @@ def cornell_box(width: int, height: int, *, red=(0.5, 0, 0), green=(0, 0.5, 0),
 def make_opts(spp: int, min_bounces: int = 1, absorb: float = 0.5, *, seed: int = 0,
               precision: int = abi.F64, flags: int = abi.FLAG_IMAGE | abi.FLAG_GRAD,
               shard_index: int = 0, shard_count: int = 1, band_rows: int = 8,
-              max_depth: int = 0, seed_scale: float = 1.0) -> abi.RenderOpts:
+              max_depth: int = 0, seed_scale: float = 1.0, adjoint_seed: int = 0) -> abi.RenderOpts:
     """Defaults are the reference CLI's (-b 1 -p 0.5, args.hpp:44-59)."""
     o = abi.RenderOpts()
     o.spp, o.min_bounces, o.absorb, o.seed = spp, min_bounces, absorb, seed
     o.precision, o.flags = precision, flags
     o.shard_index, o.shard_count, o.band_rows = shard_index, shard_count, band_rows
-    o.max_depth, o.seed_scale, o.adjoint_seed = max_depth, seed_scale, 0
+    o.max_depth, o.seed_scale, o.adjoint_seed = max_depth, seed_scale, adjoint_seed
     return o

@@ -24,6 +24,7 @@ struct RenderOptions {
     const Vector<double, 3>* seed_image = nullptr; // optional per-pixel cotangent (w*h), multiplies `seed`
     double seed_scale = 1.0;                       // e.g. 1/samples for d(loss)/d(pixel) seeds
     std::uint64_t stream = 0;                      // independent sample streams
+    std::uint64_t adjoint_stream = 0;              // != 0: decorrelated adjoint (fresh samples in backward)
     int precision = DRTB_F64;                      // DRTB_F64 (parity) | DRTB_F32 (throughput)
     int device = 0;
     drtb_stats* stats = nullptr;
@@ -48,6 +49,7 @@ void render(const Scene<T>& scene, const Camera<T>& cam, const Pathtracer<T>& tr
     o.precision = opt.precision;
     o.flags = (img ? DRTB_FLAG_IMAGE : 0u) | (opt.gradients ? DRTB_FLAG_GRAD : 0u);
     o.seed_scale = opt.seed_scale;
+    o.adjoint_seed = opt.adjoint_stream;
     std::vector<double> grad(flat.params.size(), 0.0);
     {
         gpu::Device& dev = gpu::device(opt.device);

@@ -116,7 +116,10 @@ typedef struct drtb_render_opts {
                                    counted in drtb_stats.truncated_paths.       */
     double   seed_scale;        /* adjoint seed = seed_scale * (seed_img ?
                                    seed_img[pixel] : (1,1,1))                    */
-    uint64_t adjoint_seed;      /* reserved (decorrelated adjoint); must be 0   */
+    uint64_t adjoint_seed;      /* 0: gradients from the same paths as the image
+                                   (the reference's biased mode).  != 0: the
+                                   adjoint re-traces with stream `adjoint_seed`
+                                   (decorrelated, cf. integrate.hpp:39-52)      */
 } drtb_render_opts;
 
 typedef struct drtb_stats {

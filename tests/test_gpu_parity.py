@@ -219,3 +219,18 @@ def test_cpp_dropin_program_matches_survey_kat(tmp_path):
     pix = np.frombuffer(raw[header_end:], dtype="<f4").reshape(64, 96, 3)[::-1]
     ref_img, _ = restate_render(__import__("drt_b200").cornell_box(96, 64), __import__("drt_b200").make_opts(8, 8, 1.0))
     assert np.abs(pix - ref_img).max() <= 1e-6
+
+
+def test_decorrelated_adjoint_uses_an_independent_stream(drt, ctx):
+    """adjoint_seed != 0: image from stream `seed`, gradients from stream
+    `adjoint_seed` -- identical to two separate calls, and to the oracle on each."""
+    scene = drt.cornell_box(48, 32)
+    ctx.upload(scene)
+    img, grad = ctx.render(drt.make_opts(40, 3, 0.3, seed=5, adjoint_seed=9))
+    img_a, _ = ctx.render(drt.make_opts(40, 3, 0.3, seed=5, flags=drt.FLAG_IMAGE))
+    _, grad_b = ctx.render(drt.make_opts(40, 3, 0.3, seed=9, flags=drt.FLAG_GRAD))
+    assert np.array_equal(img, img_a) and np.array_equal(grad, grad_b)
+    _, ref_grad = restate_render(scene, drt.make_opts(40, 3, 0.3, seed=9))
+    assert rel_err(grad, ref_grad).max() <= 1e-9
+    _, same = ctx.render(drt.make_opts(40, 3, 0.3, seed=5))
+    assert not np.array_equal(grad, same)
