@@ -207,7 +207,7 @@ def run_b200_arm(a):
                 dist.all_gather_into_tensor(d_full.view(world, rows, W, 3), d_img)
 
     # ---- stats run (untimed): segments/path for the algorithmic FLOP count
-    d_stats = torch.zeros(6, dtype=torch.int64, device=dev)
+    d_stats = torch.zeros(8, dtype=torch.int64, device=dev)      # sizeof(drtb_stats) = 64
     so = drt.make_opts(spp, B, 1.0, precision=prec, shard_index=rank, shard_count=world, band_rows=band,
                        flags=drt.FLAG_IMAGE | drt.FLAG_GRAD | drt.FLAG_STATS)
     ctx.render_device(so, 0, d_img.data_ptr(), d_grad.data_ptr(), d_stats.data_ptr(), stream.cuda_stream)

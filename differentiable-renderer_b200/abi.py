@@ -18,7 +18,7 @@ OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2
 SPHERE, PLANE = 0, 1
 DIFFUSE = 0
 F64, F32, MIXED = 0, 1, 2
-FLAG_IMAGE, FLAG_GRAD, FLAG_STATS = 1, 2, 4
+FLAG_IMAGE, FLAG_GRAD, FLAG_STATS, FLAG_NO_BVH = 1, 2, 4, 8
 
 STREAM_KEY_MUL = 0x9E3779B97F4A7C15
 
@@ -56,7 +56,14 @@ class RenderOpts(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("lit_paths", C.c_uint64),
                 ("truncated_paths", C.c_uint64), ("retraced_paths", C.c_uint64),
+                ("bvh_nodes", C.c_uint64), ("tri_tests", C.c_uint64),
                 ("kernel_ms", C.c_double)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("vertices", C.POINTER(C.c_double)), ("n_vertices", C.c_int64),
+                ("indices", C.POINTER(C.c_int32)), ("n_triangles", C.c_int64),
+                ("color", C.POINTER(C.c_int32)), ("emission", C.POINTER(C.c_int32))]
 
 
 # every symbol include/drtb.h declares: (name, restype, argtypes)
@@ -69,6 +76,7 @@ SYMBOLS = [
     ("drtb_destroy", None, [C.c_void_p]),
     ("drtb_last_error", C.c_char_p, [C.c_void_p]),
     ("drtb_scene_upload", C.c_int, [C.c_void_p, C.POINTER(Scene)]),
+    ("drtb_mesh_upload", C.c_int, [C.c_void_p, C.POINTER(Mesh)]),
     ("drtb_set_params", C.c_int, [C.c_void_p, _dp, C.c_int32]),
     ("drtb_shard_rows", C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("drtb_render", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), _dp, _dp, _dp, C.POINTER(Stats)]),
@@ -114,7 +122,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         fn.argtypes = args
     if lib.drtb_abi_version() != ABI_VERSION:
         raise DrtbLibraryMissing(f"{p}: ABI {lib.drtb_abi_version()} != {ABI_VERSION}")
-    for which, st in enumerate((Prim, Material, Camera, Scene, RenderOpts, Stats)):
+    for which, st in enumerate((Prim, Material, Camera, Scene, RenderOpts, Stats, Mesh)):
         if lib.drtb_struct_size(which) != C.sizeof(st):
             raise DrtbLibraryMissing(f"{p}: layout of {st.__name__} differs from the ctypes mirror")
     if path is None:

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "path.cuh"
 
@@ -69,10 +70,12 @@ struct JacSink {
 #ifndef DRTB_MIN_BLOCKS
 #define DRTB_MIN_BLOCKS 1
 #endif
-template <typename R, bool SMALLP, bool QUEUE>
+//   MESH  : a triangle mesh + BVH is attached (ids are 32-bit, parameters in global memory)
+template <typename R, bool SMALLP, bool QUEUE, bool MESH>
 __global__ void __launch_bounds__(kBlock, DRTB_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ RenderArgs a)
 {
+    using Id = typename PrimId<MESH>::type;
     extern __shared__ double s_dyn[];              // [acc: n_params*3*kBlock doubles][rings]
     __shared__ BlockScene<R> bs;
     __shared__ double s_red[kSmallP * 3][kWarpsPerBlock];
@@ -99,15 +102,20 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     // this warp's ring (QUEUE only)
     const int qdepth = a.max_depth;
     unsigned char* ring = reinterpret_cast<unsigned char*>(s_dyn + acc_doubles) +
-                          (QUEUE ? size_t(warp) * queue_bytes_per_warp(qdepth, sizeof(R)) : 0);
+                          (QUEUE ? size_t(warp) * queue_bytes_per_warp(qdepth, sizeof(R), sizeof(Id)) : 0);
     R* ring_w = reinterpret_cast<R*>(ring);
-    uint8_t* ring_prim = ring + size_t(qdepth) * kQueueSlots * sizeof(R);
-    uint8_t* ring_n = ring_prim + size_t(qdepth) * kQueueSlots;
+    Id* ring_prim = reinterpret_cast<Id*>(ring + size_t(qdepth) * kQueueSlots * sizeof(R));
+    uint8_t* ring_n = reinterpret_cast<uint8_t*>(ring_prim + size_t(qdepth) * kQueueSlots);
     int q_head = 0, q_count = 0;                   // warp-uniform
 
     SmemSink ssink{s_acc + threadIdx.x};
     AtomicSink asink{a.grad_atomic};
-    uint32_t n_seg = 0, n_lit = 0, n_trunc = 0;
+    Materials<R, MESH> mat;
+    mat.bs = &bs;
+    if constexpr (MESH) { mat.mesh = a.mesh; mat.params = a.params; }
+    const bool no_bvh = (a.flags & DRTB_FLAG_NO_BVH) != 0;
+    TraceCounters cnt;
+    uint32_t n_lit = 0;
 
     for (long long task = (long long)blockIdx.x * kWarpsPerBlock + warp; task < n_tasks; task += n_warps) {
         const int sub = spp >= 32 ? 0 : lane / spp;           // pixel within the task
@@ -132,8 +140,8 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
         // sweeps over one record; accumulates this lane's share of the pixel and the gradients
         auto sweep = [&](const auto& rec, int n) {
             R L0[3];
-            if (SMALLP) radiance_and_adjoint(bs, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ssink);
-            else        radiance_and_adjoint(bs, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, asink);
+            if (SMALLP) radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ssink);
+            else        radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, asink);
             acc[0] += double(L0[0]); acc[1] += double(L0[1]); acc[2] += double(L0[2]);       // render.cpp:78
             n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
         };
@@ -142,7 +150,7 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
             __syncwarp();
             if (lane < m) {
                 const int slot = (q_head + lane) & (kQueueSlots - 1);
-                QueueView<R> qv{ring_w + slot, ring_prim + slot};
+                QueueView<R, MESH> qv{ring_w + slot, ring_prim + slot};
                 sweep(qv, ring_n[slot]);
             }
             __syncwarp();
@@ -154,15 +162,13 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
             const int i = i0 + pass * 32;
             bool lit = false;
             int n = 0;
-            PathRecord<R> rec;
+            PathRecord<R, MESH> rec;
             if (lane_ok && i < spp) {
                 const uint64_t key = a.key0 + ((uint64_t)y * W + x) * (uint64_t)spp + (uint64_t)i;
                 const uint64_t base = key * kKeyMul;
                 V3<R> o = {sc.eye[0], sc.eye[1], sc.eye[2]};
                 V3<R> d = camera_ray(sc, x, y, base);
-                bool truncated;
-                n = trace_path(sc, bs, base, 2u, o, d, a.min_bounces, a.absorb, a.max_depth, rec, lit, n_seg, truncated);
-                n_trunc += truncated;
+                n = trace_path(sc, bs, mat, no_bvh, base, 2u, o, d, a.min_bounces, a.absorb, a.max_depth, rec, lit, cnt);
                 if (!QUEUE && lit) sweep(rec, n);
             }
             if (QUEUE) {
@@ -223,13 +229,23 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
         }
     }
     if (a.stats) {
-        n_seg = __reduce_add_sync(0xffffffffu, n_seg);
-        n_lit = __reduce_add_sync(0xffffffffu, n_lit);
-        n_trunc = __reduce_add_sync(0xffffffffu, n_trunc);
+        // 64-bit warp totals: a warp can see far more than 2^32 node visits on a large mesh
+        auto total = [](uint32_t v) {
+            unsigned long long t = v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            return t;
+        };
+        const unsigned long long seg = total(cnt.segments), litp = total(n_lit), tr = total(cnt.truncated),
+                                 nodes = total(cnt.bvh_nodes), tests = total(cnt.tri_tests);
         if (lane == 0) {
-            atomicAdd((unsigned long long*)&a.stats->segments, (unsigned long long)n_seg);
-            atomicAdd((unsigned long long*)&a.stats->lit_paths, (unsigned long long)n_lit);
-            if (n_trunc) atomicAdd((unsigned long long*)&a.stats->truncated_paths, (unsigned long long)n_trunc);
+            atomicAdd((unsigned long long*)&a.stats->segments, seg);
+            atomicAdd((unsigned long long*)&a.stats->lit_paths, litp);
+            if (tr) atomicAdd((unsigned long long*)&a.stats->truncated_paths, tr);
+            if (MESH) {
+                atomicAdd((unsigned long long*)&a.stats->bvh_nodes, nodes);
+                atomicAdd((unsigned long long*)&a.stats->tri_tests, tests);
+            }
         }
     }
 }
@@ -254,10 +270,10 @@ reduce_grad_kernel(const double* __restrict__ partial, int n_blocks, int P3, dou
 }
 
 // Pathtracer<T>::trace(scene, orig, dir) for user-supplied rays (pathtracer.hpp:121-136).
-template <typename R>
+template <typename R, bool MESH>
 __global__ void __launch_bounds__(kBlock)
-trace_rays_kernel(const __grid_constant__ DevScene<R> sc, const double* __restrict__ params,
-                  int min_bounces, double absorb, int max_depth, long long n,
+trace_rays_kernel(const __grid_constant__ DevScene<R> sc, const double* __restrict__ params, const MeshView mesh,
+                  uint32_t flags, int min_bounces, double absorb, int max_depth, long long n,
                   const double* __restrict__ orig, const double* __restrict__ dir,
                   const uint64_t* __restrict__ keys, double* __restrict__ radiance, double* jac)
 {
@@ -266,18 +282,22 @@ trace_rays_kernel(const __grid_constant__ DevScene<R> sc, const double* __restri
     __syncthreads();
     const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (i >= n) return;
+    Materials<R, MESH> mat;
+    mat.bs = &bs;
+    if constexpr (MESH) { mat.mesh = mesh; mat.params = params; }
     const R inv_p = absorb < 1.0 ? R(1.0 / (1.0 - absorb)) : R(0);
     V3<R> o = {R(orig[3 * i]), R(orig[3 * i + 1]), R(orig[3 * i + 2])};
     V3<R> d = {R(dir[3 * i]), R(dir[3 * i + 1]), R(dir[3 * i + 2])};
-    PathRecord<R> rec;
-    bool lit, truncated;
-    uint32_t seg = 0;
-    int nv = trace_path(sc, bs, keys[i] * kKeyMul, 2u, o, d, min_bounces, absorb, max_depth, rec, lit, seg, truncated);
+    PathRecord<R, MESH> rec;
+    bool lit;
+    TraceCounters cnt;
+    int nv = trace_path(sc, bs, mat, (flags & DRTB_FLAG_NO_BVH) != 0, keys[i] * kKeyMul, 2u, o, d, min_bounces, absorb,
+                        max_depth, rec, lit, cnt);
     R L0[3] = {R(0), R(0), R(0)};
     if (lit) {
         const R one[3] = {R(1), R(1), R(1)};
         JacSink sink{jac ? jac + (size_t)i * sc.n_params * 3 : nullptr};
-        radiance_and_adjoint(bs, rec, nv, min_bounces, inv_p, jac != nullptr, one, L0, sink);
+        radiance_and_adjoint(mat, rec, nv, min_bounces, inv_p, jac != nullptr, one, L0, sink);
     }
     radiance[3 * i] = double(L0[0]); radiance[3 * i + 1] = double(L0[1]); radiance[3 * i + 2] = double(L0[2]);
 }
@@ -325,6 +345,14 @@ struct drtb_ctx {
     double* d_grad = nullptr;     size_t grad_cap = 0;
     drtb_stats* d_stats = nullptr;
     unsigned long long launches = 0;
+    // triangle mesh + BVH (device)
+    int64_t n_tris = 0;
+    float4* d_nodes = nullptr;
+    double* d_tri64 = nullptr;
+    float4* d_tri32 = nullptr;
+    int32_t* d_tri_color = nullptr;
+    int32_t* d_tri_emis = nullptr;
+    double mesh_build_ms = 0.0;
 };
 
 namespace {
@@ -378,8 +406,8 @@ void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
         const drtb_prim& p = c.prims[i];
         d.n_planes += p.type == DRTB_PLANE;
         d.type[i] = int8_t(p.type);
-        d.color[i] = int8_t(p.material >= 0 ? c.materials[p.material].color : -1);
-        d.emis[i] = int8_t(p.emission);
+        d.color[i] = p.material >= 0 ? c.materials[p.material].color : -1;
+        d.emis[i] = p.emission;
     }
     const drtb_camera& cam = c.camera;
     for (int j = 0; j < 3; ++j) {
@@ -424,12 +452,12 @@ int occupancy(drtb_ctx* ctx, K kernel, size_t smem, int& out)
     return DRTB_OK;
 }
 
-template <typename R, bool SMALLP, bool QUEUE>
+template <typename R, bool SMALLP, bool QUEUE, bool MESH>
 int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t smem, long long need_blocks,
                    int P3, bool want_grad, cudaStream_t stream, int& grid_out)
 {
     int per_sm = 0;
-    int rc = occupancy(ctx, render_kernel<R, SMALLP, QUEUE>, smem, per_sm);
+    int rc = occupancy(ctx, render_kernel<R, SMALLP, QUEUE, MESH>, smem, per_sm);
     if (rc != DRTB_OK) return rc;
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > need_blocks) grid = need_blocks;
@@ -439,7 +467,7 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
         if (rc != DRTB_OK) return rc;
         a.grad_partial = ctx->d_partial;
     }
-    render_kernel<R, SMALLP, QUEUE><<<int(grid), kBlock, smem, stream>>>(sc, a);
+    render_kernel<R, SMALLP, QUEUE, MESH><<<int(grid), kBlock, smem, stream>>>(sc, a);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     grid_out = int(grid);
@@ -447,13 +475,36 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
 }
 
 template <typename R>
-int launch_precision(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, bool smallp, bool queue, size_t smem,
-                     long long need_blocks, int P3, bool want_grad, cudaStream_t stream, int& grid)
+int launch_precision(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, bool smallp, bool queue, bool mesh,
+                     size_t smem, long long need_blocks, int P3, bool want_grad, cudaStream_t stream, int& grid)
 {
-    if (smallp) return queue ? launch_variant<R, true, true>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid)
-                             : launch_variant<R, true, false>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid);
-    return queue ? launch_variant<R, false, true>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid)
-                 : launch_variant<R, false, false>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid);
+#define DRTB_LAUNCH(SP, Q, M) launch_variant<R, SP, Q, M>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid)
+    if (mesh) {
+        // mesh scenes: parameters live in global memory; small sets still use the smem gradient columns
+        if (smallp) return queue ? DRTB_LAUNCH(true, true, true) : DRTB_LAUNCH(true, false, true);
+        return queue ? DRTB_LAUNCH(false, true, true) : DRTB_LAUNCH(false, false, true);
+    }
+    if (smallp) return queue ? DRTB_LAUNCH(true, true, false) : DRTB_LAUNCH(true, false, false);
+    return queue ? DRTB_LAUNCH(false, true, false) : DRTB_LAUNCH(false, false, false);
+#undef DRTB_LAUNCH
+}
+
+MeshView mesh_view(const drtb_ctx* ctx)
+{
+    MeshView m{};
+    m.nodes = ctx->d_nodes; m.tri64 = ctx->d_tri64; m.tri32 = ctx->d_tri32;
+    m.color = ctx->d_tri_color; m.emis = ctx->d_tri_emis;
+    m.n_tris = int32_t(ctx->n_tris); m.n_prims = int32_t(ctx->prims.size());
+    return m;
+}
+
+void free_mesh(drtb_ctx* ctx)
+{
+    cudaFree(ctx->d_nodes); cudaFree(ctx->d_tri64); cudaFree(ctx->d_tri32);
+    cudaFree(ctx->d_tri_color); cudaFree(ctx->d_tri_emis);
+    ctx->d_nodes = nullptr; ctx->d_tri64 = nullptr; ctx->d_tri32 = nullptr;
+    ctx->d_tri_color = nullptr; ctx->d_tri_emis = nullptr;
+    ctx->n_tris = 0;
 }
 
 int validate_opts(drtb_ctx* ctx, const drtb_render_opts* o)
@@ -469,6 +520,8 @@ int validate_opts(drtb_ctx* ctx, const drtb_render_opts* o)
         return fail(ctx, DRTB_ERR_INVALID, "bad shard (index, count, band_rows)");
     if (o->max_depth < 0 || o->max_depth > kMaxDepth)
         return fail(ctx, DRTB_ERR_UNSUPPORTED, "max_depth must be in [0, 64]");
+    if (ctx->n_tris == 0 && ctx->params.size() > size_t(kMaxParams) * 3)
+        return fail(ctx, DRTB_ERR_UNSUPPORTED, "more than 64 RGB parameters needs a mesh scene (drtb_mesh_upload)");
     if (o->absorb == 1.0 && o->min_bounces > kMaxDepth)
         return fail(ctx, DRTB_ERR_UNSUPPORTED, "min_bounces > 64 with absorb == 1 exceeds the vertex record");
     return DRTB_OK;
@@ -505,8 +558,11 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     const bool f32 = o->precision == DRTB_F32;
     // lit-path compaction needs whole-pixel warp tasks and records that fit the ring
     const bool queue = o->spp >= 32 && a.max_depth <= kQueueDepth;
+    const bool mesh = ctx->n_tris > 0;
+    a.mesh = mesh_view(ctx);
     size_t smem = (smallp && want_grad) ? size_t(P3) * kBlock * sizeof(double) : 0;
-    if (queue) smem += kWarpsPerBlock * queue_bytes_per_warp(a.max_depth, f32 ? sizeof(float) : sizeof(double));
+    if (queue) smem += kWarpsPerBlock * queue_bytes_per_warp(a.max_depth, f32 ? sizeof(float) : sizeof(double),
+                                                             mesh ? sizeof(int32_t) : sizeof(uint8_t));
     smem = (smem + 15) & ~size_t(15);
     const long long npix = (long long)rows * W;
     const int ppw = o->spp >= 32 ? 1 : 32 / o->spp;
@@ -521,8 +577,8 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
         a.grad_atomic = d_grad;
     }
     int grid = 0;
-    int rc = f32 ? launch_precision<float>(ctx, ctx->sc32, a, smallp, queue, smem, need, P3, want_grad, stream, grid)
-                 : launch_precision<double>(ctx, ctx->sc64, a, smallp, queue, smem, need, P3, want_grad, stream, grid);
+    int rc = f32 ? launch_precision<float>(ctx, ctx->sc32, a, smallp, queue, mesh, smem, need, P3, want_grad, stream, grid)
+                 : launch_precision<double>(ctx, ctx->sc64, a, smallp, queue, mesh, smem, need, P3, want_grad, stream, grid);
     if (rc != DRTB_OK) return rc;
     if (want_grad && smallp) {
         reduce_grad_kernel<<<1, 256, 0, stream>>>(ctx->d_partial, int(grid), P3, d_grad);
@@ -576,6 +632,7 @@ size_t drtb_struct_size(int which)
         case 3: return sizeof(drtb_scene);
         case 4: return sizeof(drtb_render_opts);
         case 5: return sizeof(drtb_stats);
+        case 6: return sizeof(drtb_mesh);
         default: return 0;
     }
 }
@@ -624,6 +681,7 @@ void drtb_destroy(drtb_ctx* ctx)
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     cudaFree(ctx->d_params); cudaFree(ctx->d_partial); cudaFree(ctx->d_img);
     cudaFree(ctx->d_seed); cudaFree(ctx->d_grad); cudaFree(ctx->d_stats);
+    free_mesh(ctx);
     delete ctx;
 }
 
@@ -638,8 +696,6 @@ int drtb_scene_upload(drtb_ctx* ctx, const drtb_scene* s)
     if (s->camera.width < 1 || s->camera.height < 1) return fail(ctx, DRTB_ERR_INVALID, "camera width/height must be >= 1");
     if (s->n_prims > kMaxPrims)
         return fail(ctx, DRTB_ERR_UNSUPPORTED, "more than 32 analytic primitives is not supported by this build");
-    if (s->n_params > kMaxParams)
-        return fail(ctx, DRTB_ERR_UNSUPPORTED, "more than 64 RGB parameters is not supported by this build");
     for (int m = 0; m < s->n_materials; ++m) {
         if (s->materials[m].type != DRTB_DIFFUSE) return fail(ctx, DRTB_ERR_UNSUPPORTED, "only DRTB_DIFFUSE materials are supported");
         if (s->materials[m].color < 0 || s->materials[m].color >= s->n_params) return fail(ctx, DRTB_ERR_INVALID, "material colour index out of range");
@@ -651,6 +707,8 @@ int drtb_scene_upload(drtb_ctx* ctx, const drtb_scene* s)
         if (p.emission < -1 || p.emission >= s->n_params) return fail(ctx, DRTB_ERR_INVALID, "primitive emission index out of range");
     }
     CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    free_mesh(ctx);                                   // a mesh belongs to the scene it was attached to
     ctx->prims.assign(s->prims, s->prims + s->n_prims);
     ctx->materials.assign(s->materials, s->materials + s->n_materials);
     ctx->params.assign(s->params, s->params + size_t(s->n_params) * 3);
@@ -662,6 +720,92 @@ int drtb_scene_upload(drtb_ctx* ctx, const drtb_scene* s)
     if (!ctx->params.empty())
         CK(ctx, cudaMemcpy(ctx->d_params, ctx->params.data(), sizeof(double) * ctx->params.size(), cudaMemcpyHostToDevice));
     ctx->has_scene = true;
+    return DRTB_OK;
+}
+
+int drtb_mesh_upload(drtb_ctx* ctx, const drtb_mesh* mesh)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, DRTB_ERR_INVALID, "upload a scene before attaching a mesh");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    free_mesh(ctx);
+    if (!mesh || mesh->n_triangles == 0) return DRTB_OK;
+    const int64_t n = mesh->n_triangles, nv = mesh->n_vertices;
+    if (n < 0 || nv <= 0 || !mesh->vertices || !mesh->indices) return fail(ctx, DRTB_ERR_INVALID, "mesh has NULL arrays or bad counts");
+    if (n > (int64_t(1) << 30)) return fail(ctx, DRTB_ERR_UNSUPPORTED, "more than 2^30 triangles");
+    const int P = int(ctx->params.size() / 3);
+    for (int64_t i = 0; i < 3 * n; ++i)
+        if (mesh->indices[i] < 0 || mesh->indices[i] >= nv) return fail(ctx, DRTB_ERR_INVALID, "mesh vertex index out of range");
+    for (int64_t i = 0; i < n; ++i) {
+        if (mesh->color && (mesh->color[i] < -1 || mesh->color[i] >= P)) return fail(ctx, DRTB_ERR_INVALID, "triangle colour parameter index out of range");
+        if (mesh->emission && (mesh->emission[i] < -1 || mesh->emission[i] >= P)) return fail(ctx, DRTB_ERR_INVALID, "triangle emission parameter index out of range");
+    }
+    // ---- device buffers: persistent mesh data + build temporaries
+    double* d_vert = nullptr; int32_t* d_idx = nullptr;
+    float *d_lo = nullptr, *d_hi = nullptr; uint32_t* d_bounds = nullptr;
+    uint64_t *d_keys = nullptr, *d_keys2 = nullptr; uint32_t *d_vals = nullptr, *d_vals2 = nullptr;
+    int2* d_children = nullptr; int *d_pnode = nullptr, *d_pleaf = nullptr, *d_arrive = nullptr; void* d_tmp = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_vert); cudaFree(d_idx); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_bounds); cudaFree(d_keys);
+        cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_children); cudaFree(d_pnode);
+        cudaFree(d_pleaf); cudaFree(d_arrive); cudaFree(d_tmp);
+    };
+#define CKM(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); free_mesh(ctx); return fail(ctx, e_ == cudaErrorMemoryAllocation ? DRTB_ERR_NOMEM : DRTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    cudaStream_t st = ctx->stream;
+    const size_t nn = size_t(n), nodes = nn > 1 ? nn - 1 : 1;
+    CKM(cudaMalloc((void**)&ctx->d_tri64, nn * kTri64Stride * sizeof(double)));
+    CKM(cudaMalloc((void**)&ctx->d_tri32, nn * kTri32Stride * sizeof(float4)));
+    CKM(cudaMalloc((void**)&ctx->d_tri_color, nn * sizeof(int32_t)));
+    CKM(cudaMalloc((void**)&ctx->d_tri_emis, nn * sizeof(int32_t)));
+    CKM(cudaMalloc((void**)&ctx->d_nodes, nodes * 4 * sizeof(float4)));
+    CKM(cudaMalloc((void**)&d_vert, size_t(nv) * 3 * sizeof(double)));
+    CKM(cudaMalloc((void**)&d_idx, nn * 3 * sizeof(int32_t)));
+    CKM(cudaMalloc((void**)&d_lo, nn * 3 * sizeof(float)));
+    CKM(cudaMalloc((void**)&d_hi, nn * 3 * sizeof(float)));
+    CKM(cudaMalloc((void**)&d_bounds, 6 * sizeof(uint32_t)));
+    CKM(cudaMalloc((void**)&d_keys, nn * sizeof(uint64_t)));  CKM(cudaMalloc((void**)&d_keys2, nn * sizeof(uint64_t)));
+    CKM(cudaMalloc((void**)&d_vals, nn * sizeof(uint32_t)));  CKM(cudaMalloc((void**)&d_vals2, nn * sizeof(uint32_t)));
+    CKM(cudaMalloc((void**)&d_children, nodes * sizeof(int2)));
+    CKM(cudaMalloc((void**)&d_pnode, nodes * sizeof(int)));   CKM(cudaMalloc((void**)&d_pleaf, nn * sizeof(int)));
+    CKM(cudaMalloc((void**)&d_arrive, nodes * sizeof(int)));
+    CKM(cudaMemcpyAsync(d_vert, mesh->vertices, size_t(nv) * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CKM(cudaMemcpyAsync(d_idx, mesh->indices, nn * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (mesh->color) CKM(cudaMemcpyAsync(ctx->d_tri_color, mesh->color, nn * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    else CKM(cudaMemsetAsync(ctx->d_tri_color, 0xff, nn * sizeof(int32_t), st));
+    if (mesh->emission) CKM(cudaMemcpyAsync(ctx->d_tri_emis, mesh->emission, nn * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    else CKM(cudaMemsetAsync(ctx->d_tri_emis, 0xff, nn * sizeof(int32_t), st));
+    // scene bounds start at (+max, -max) in the ordered-uint encoding
+    const uint32_t init_bounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    CKM(cudaMemcpyAsync(d_bounds, init_bounds, sizeof init_bounds, cudaMemcpyHostToDevice, st));
+    CKM(cudaMemsetAsync(d_arrive, 0, nodes * sizeof(int), st));
+    CKM(cudaEventRecord(ctx->ev0, st));
+    const int T = 256, G = int((nn + T - 1) / T);
+    mesh_prepare_kernel<<<G, T, 0, st>>>(d_vert, d_idx, int(n), ctx->d_tri64, ctx->d_tri32, d_lo, d_hi, d_bounds);
+    CKM(cudaGetLastError());
+    ctx->launches++;
+    if (n > 1) {
+        mesh_morton_kernel<<<G, T, 0, st>>>(d_lo, d_hi, d_bounds, int(n), d_keys, d_vals);
+        CKM(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        CKM(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, int(n), 0, 63, st));
+        CKM(cudaMalloc(&d_tmp, tmp_bytes));
+        CKM(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, int(n), 0, 63, st));
+        lbvh_hierarchy_kernel<<<G, T, 0, st>>>(d_keys2, int(n), d_children, d_pnode, d_pleaf);
+        CKM(cudaGetLastError());
+        lbvh_refit_kernel<<<G, T, 0, st>>>(d_vals2, d_lo, d_hi, d_children, d_pnode, d_pleaf, d_bounds, int(n), d_arrive,
+                                           reinterpret_cast<float*>(ctx->d_nodes));
+        CKM(cudaGetLastError());
+        ctx->launches += 5;                                  // morton, sort (>= 2), hierarchy, refit
+    }
+    CKM(cudaEventRecord(ctx->ev1, st));
+    CKM(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CKM(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->mesh_build_ms = ms;
+#undef CKM
+    cleanup();
+    ctx->n_tris = n;
     return DRTB_OK;
 }
 
@@ -759,10 +903,15 @@ int drtb_trace_rays(drtb_ctx* ctx, const drtb_render_opts* o, int64_t n, const d
     CKF(cudaMemcpyAsync(d_k, keys, sizeof(uint64_t) * size_t(n), cudaMemcpyHostToDevice, ctx->stream));
     const int grid = int((n + kBlock - 1) / kBlock);
     const int md = effective_max_depth(o);
-    if (o->precision == DRTB_F32)
-        trace_rays_kernel<float><<<grid, kBlock, 0, ctx->stream>>>(ctx->sc32, ctx->d_params, o->min_bounces, o->absorb, md, n, d_o, d_d, d_k, d_r, d_j);
-    else
-        trace_rays_kernel<double><<<grid, kBlock, 0, ctx->stream>>>(ctx->sc64, ctx->d_params, o->min_bounces, o->absorb, md, n, d_o, d_d, d_k, d_r, d_j);
+    const MeshView mv = mesh_view(ctx);
+    const bool f32 = o->precision == DRTB_F32;
+    if (ctx->n_tris > 0) {
+        if (f32) trace_rays_kernel<float, true><<<grid, kBlock, 0, ctx->stream>>>(ctx->sc32, ctx->d_params, mv, o->flags, o->min_bounces, o->absorb, md, n, d_o, d_d, d_k, d_r, d_j);
+        else     trace_rays_kernel<double, true><<<grid, kBlock, 0, ctx->stream>>>(ctx->sc64, ctx->d_params, mv, o->flags, o->min_bounces, o->absorb, md, n, d_o, d_d, d_k, d_r, d_j);
+    } else {
+        if (f32) trace_rays_kernel<float, false><<<grid, kBlock, 0, ctx->stream>>>(ctx->sc32, ctx->d_params, mv, o->flags, o->min_bounces, o->absorb, md, n, d_o, d_d, d_k, d_r, d_j);
+        else     trace_rays_kernel<double, false><<<grid, kBlock, 0, ctx->stream>>>(ctx->sc64, ctx->d_params, mv, o->flags, o->min_bounces, o->absorb, md, n, d_o, d_d, d_k, d_r, d_j);
+    }
     CKF(cudaGetLastError());
     ctx->launches++;
     CKF(cudaMemcpyAsync(radiance, d_r, b3, cudaMemcpyDeviceToHost, ctx->stream));

@@ -30,8 +30,8 @@ struct DevScene {
     int8_t  id[kMaxPrims];               // scan slot -> scene index
     // Indexed by SCENE index:
     int8_t  type[kMaxPrims];             // DRTB_SPHERE | DRTB_PLANE
-    int8_t  color[kMaxPrims];            // param index of the albedo, -1 = null BxDF
-    int8_t  emis[kMaxPrims];             // param index of the emission, -1 = no emitter
+    int32_t color[kMaxPrims];            // param index of the albedo, -1 = null BxDF
+    int32_t emis[kMaxPrims];             // param index of the emission, -1 = no emitter
     int8_t  slot[kMaxPrims];             // scene index -> scan slot
     int32_t n_prims, n_planes;
     int32_t n_params;
@@ -43,20 +43,6 @@ struct DevScene {
     int32_t width, height;
 };
 
-struct RenderArgs {
-    int32_t  spp, min_bounces, max_depth;
-    uint32_t flags;
-    double   absorb;
-    uint64_t key0;                       // seed * kSeedMul
-    int32_t  shard_index, shard_count, band_rows, shard_rows;
-    double   seed_scale;
-    const double* params;                // n_params x 3 (device)
-    const double* seed_img;              // shard_rows x W x 3 or null
-    double*  img;                        // shard_rows x W x 3 or null
-    double*  grad_partial;               // gridDim.x x (n_params*3)  (small-P path)
-    double*  grad_atomic;                // n_params*3, pre-zeroed     (large-P path)
-    drtb_stats* stats;                   // or null
-};
 
 template <typename R> struct V3 { R x, y, z; };
 
@@ -76,13 +62,34 @@ template <typename R> __device__ __forceinline__ V3<R> normalize(V3<R> a)
     return a * Real<R>::rsqrt(dot(a, a));             // vector.hpp:580-590
 }
 
+} // namespace drtb
+#include "bvh.cuh"
+namespace drtb {
+
+struct RenderArgs {
+    int32_t  spp, min_bounces, max_depth;
+    uint32_t flags;
+    double   absorb;
+    uint64_t key0;                       // seed * kSeedMul
+    int32_t  shard_index, shard_count, band_rows, shard_rows;
+    double   seed_scale;
+    const double* params;                // n_params x 3 (device)
+    const double* seed_img;              // shard_rows x W x 3 or null
+    double*  img;                        // shard_rows x W x 3 or null
+    double*  grad_partial;               // gridDim.x x (n_params*3)  (small-P path)
+    double*  grad_atomic;                // n_params*3, pre-zeroed     (large-P path)
+    drtb_stats* stats;                   // or null
+    MeshView mesh;                       // n_tris == 0: analytic scene only
+};
+
 // Per-block shared copy of what is looked up with a PER-LANE index (the prim a
 // lane actually hit, the parameters of its material).
 template <typename R>
 struct BlockScene {
-    R      prim[kMaxPrims][4];
-    R      param[kMaxParams * 3];
-    int8_t type[kMaxPrims], color[kMaxPrims], emis[kMaxPrims];
+    R       prim[kMaxPrims][4];
+    R       param[kMaxParams * 3];       // staged only when n_params <= kMaxParams
+    int32_t color[kMaxPrims], emis[kMaxPrims];
+    int8_t  type[kMaxPrims];
 };
 
 template <typename R>
@@ -94,7 +101,8 @@ __device__ __forceinline__ void load_block_scene(BlockScene<R>& bs, const DevSce
     for (int i = threadIdx.x; i < sc.n_prims; i += blockDim.x) {
         bs.type[i] = sc.type[i]; bs.color[i] = sc.color[i]; bs.emis[i] = sc.emis[i];
     }
-    for (int i = threadIdx.x; i < sc.n_params * 3; i += blockDim.x) bs.param[i] = R(params[i]);
+    if (sc.n_params <= kMaxParams)
+        for (int i = threadIdx.x; i < sc.n_params * 3; i += blockDim.x) bs.param[i] = R(params[i]);
 }
 
 // ---------------------------------------------------------------------------
@@ -191,13 +199,18 @@ __device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, R u_theta, R u_phi, R& 
 
 // Per-path vertex record: what the reference keeps as ~17 heap-allocated tape
 // nodes per segment (vector.hpp:194-213) shrinks to (prim id, w) per vertex;
-// p_v is a function of the depth alone (pathtracer.hpp:130).
-template <typename R>
+// p_v is a function of the depth alone (pathtracer.hpp:130).  Scene indices fit
+// a byte for analytic scenes, 32 bits once a mesh is attached.
+template <bool MESH> struct PrimId { using type = uint8_t; };
+template <> struct PrimId<true> { using type = int32_t; };
+
+template <typename R, bool MESH>
 struct PathRecord {
-    R       w_[kMaxDepth];
-    uint8_t prim_[kMaxDepth];
+    using Id = typename PrimId<MESH>::type;
+    R  w_[kMaxDepth];
+    Id prim_[kMaxDepth];
     __device__ __forceinline__ R w(int v) const { return w_[v]; }
-    __device__ __forceinline__ int prim(int v) const { return prim_[v]; }
+    __device__ __forceinline__ int prim(int v) const { return int(prim_[v]); }
 };
 
 // Lit-path compaction.  Only ~16 % of the Cornell box's paths reach the light,
@@ -208,18 +221,42 @@ struct PathRecord {
 constexpr int kQueueSlots = 64;    // ring capacity per warp (power of two)
 constexpr int kQueueDepth = 16;    // deepest record the ring stores; deeper runs use the direct path
 
-template <typename R>
+template <typename R, bool MESH>
 struct QueueView {                 // one record of one warp's ring
+    using Id = typename PrimId<MESH>::type;
     const R* w_;                   // &ring_w[slot], stride kQueueSlots
-    const uint8_t* prim_;
+    const Id* prim_;
     __device__ __forceinline__ R w(int v) const { return w_[v * kQueueSlots]; }
-    __device__ __forceinline__ int prim(int v) const { return prim_[v * kQueueSlots]; }
+    __device__ __forceinline__ int prim(int v) const { return int(prim_[v * kQueueSlots]); }
 };
 
-__host__ __device__ constexpr size_t queue_bytes_per_warp(int depth, size_t real_size)
+__host__ __device__ constexpr size_t queue_bytes_per_warp(int depth, size_t real_size, size_t id_size)
 {
-    return size_t(depth) * kQueueSlots * real_size + size_t(depth) * kQueueSlots + kQueueSlots;
+    // w[depth][slots] | prim[depth][slots] | n[slots], each part 8-byte aligned
+    return size_t(depth) * kQueueSlots * real_size + size_t(depth) * kQueueSlots * id_size + kQueueSlots;
 }
+
+// Who emits, who scatters, and the parameter values, by scene index.  Analytic
+// primitives answer from the block's shared copy; triangles (scene index >=
+// n_prims) and large parameter sets answer from global memory through the
+// read-only path.
+template <typename R, bool MESH> struct Materials;
+template <typename R> struct Materials<R, false> {
+    const BlockScene<R>* bs;
+    __device__ __forceinline__ int em(int k) const { return bs->emis[k]; }
+    __device__ __forceinline__ int col(int k) const { return bs->color[k]; }
+    __device__ __forceinline__ R param(int i) const { return bs->param[i]; }
+};
+template <typename R> struct Materials<R, true> {
+    const BlockScene<R>* bs;
+    MeshView mesh;
+    const double* params;
+    __device__ __forceinline__ int em(int k) const { return k < mesh.n_prims ? bs->emis[k] : __ldg(mesh.emis + (k - mesh.n_prims)); }
+    __device__ __forceinline__ int col(int k) const { return k < mesh.n_prims ? bs->color[k] : __ldg(mesh.color + (k - mesh.n_prims)); }
+    __device__ __forceinline__ R param(int i) const { return R(__ldg(params + i)); }
+};
+
+struct TraceCounters { uint32_t segments = 0, truncated = 0, bvh_nodes = 0, tri_tests = 0; };
 
 // ---------------------------------------------------------------------------
 // Pathtracer::trace + scatter (pathtracer.hpp:91-136), recursion unrolled into
@@ -228,37 +265,55 @@ __host__ __device__ constexpr size_t queue_bytes_per_warp(int depth, size_t real
 // gradient of the path are exactly zero and the sweeps are skipped).
 // `slot` is the next stream slot (2 after the camera draws).
 // ---------------------------------------------------------------------------
-template <typename R>
+template <typename R, bool MESH>
 __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScene<R>& bs,
+                                          const Materials<R, MESH>& mat, bool no_bvh,
                                           uint64_t base, uint32_t slot, V3<R> o, V3<R> d,
                                           int min_bounces, double absorb, int max_depth,
-                                          PathRecord<R>& rec, bool& lit, uint32_t& segments,
-                                          bool& truncated)
+                                          PathRecord<R, MESH>& rec, bool& lit, TraceCounters& cnt)
 {
+    using Id = typename PrimId<MESH>::type;
     int n = 0;
     lit = false;
-    truncated = false;
     for (int depth = 0;; ++depth) {
         if (depth >= min_bounces) {                         // Russian roulette, :128-130
             double u = Real<double>::uniform(stream_draw_base(base, slot++));
             if (u < absorb) break;
         }
-        if (n >= max_depth) { truncated = true; break; }
+        if (n >= max_depth) { ++cnt.truncated; break; }
         R t;
-        int k = closest_hit(sc, o, d, t);
-        ++segments;
+        int k = closest_hit(sc, o, d, t);                   // analytic primitives
+        int tri = -1;
+        if constexpr (MESH) {                               // then the mesh; analytic wins exact ties
+            if (k < 0) t = Real<R>::inf();
+            if (no_bvh) brute_closest(mat.mesh, o, d, t, tri, cnt.tri_tests);
+            else        bvh_closest(mat.mesh, o, d, t, tri, cnt.bvh_nodes, cnt.tri_tests);
+            if (tri >= 0) k = mat.mesh.n_prims + tri;
+        }
+        ++cnt.segments;
         if (k < 0) break;                                   // miss, :134-135
         V3<R> pt = {o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
-        const int em = bs.emis[k], col = bs.color[k];
+        const int em = mat.em(k), col = mat.col(k);
         lit |= em >= 0;
-        rec.prim_[n] = uint8_t(k);
+        rec.prim_[n] = Id(k);
         if (col < 0) {                                      // null BxDF, :25-26, 38-39
             rec.w_[n++] = R(0);
             break;
         }
-        V3<R> nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]};
-        if (bs.type[k] == DRTB_SPHERE)                      // shape.hpp:105-106
-            nrm = normalize(V3<R>{pt.x - nrm.x, pt.y - nrm.y, pt.z - nrm.z});
+        V3<R> nrm;
+        bool on_mesh = false;
+        if constexpr (MESH) {
+            if (tri >= 0) {                                 // unit geometric normal, drtb.h
+                const TriData<R> T = load_tri<R>(mat.mesh, tri);
+                nrm = normalize(cross(T.e1, T.e2));
+                on_mesh = true;
+            }
+        }
+        if (!on_mesh) {
+            nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]};
+            if (bs.type[k] == DRTB_SPHERE)                  // shape.hpp:105-106
+                nrm = normalize(V3<R>{pt.x - nrm.x, pt.y - nrm.y, pt.z - nrm.z});
+        }
         R u_theta = Real<R>::uniform_fast(stream_draw_base(base, slot));
         R u_phi   = Real<R>::uniform_fast(stream_draw_base(base, slot + 1));
         slot += 2;
@@ -279,8 +334,8 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
 //   g_{v+1} = gp w_v rho_v / pi.           (per channel; channels never mix)
 // Sink::add(param_index, channel, value) receives the contributions.
 // ---------------------------------------------------------------------------
-template <typename R, typename Rec, typename Sink>
-__device__ __forceinline__ void radiance_and_adjoint(const BlockScene<R>& bs, const Rec& rec,
+template <typename R, typename Mat, typename Rec, typename Sink>
+__device__ __forceinline__ void radiance_and_adjoint(const Mat& mat, const Rec& rec,
                                                      int n, int min_bounces, R inv_p,
                                                      bool want_grad, const R g0[3], R L0[3], Sink& sink)
 {
@@ -288,14 +343,14 @@ __device__ __forceinline__ void radiance_and_adjoint(const BlockScene<R>& bs, co
     R L[3] = {R(0), R(0), R(0)};
     for (int v = n - 1; v >= 0; --v) {
         const int k = rec.prim(v);
-        const int em = bs.emis[k], col = bs.color[k];
+        const int em = mat.em(k), col = mat.col(k);
         const R ip = v >= min_bounces ? inv_p : R(1);
         const R f = rec.w(v) * Real<R>::kInvPi;
         if (want_grad) { Ls[v + 1][0] = L[0]; Ls[v + 1][1] = L[1]; Ls[v + 1][2] = L[2]; }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            R E = em >= 0 ? bs.param[3 * em + c] : R(0);
-            R rho = col >= 0 ? bs.param[3 * col + c] : R(0);
+            R E = em >= 0 ? mat.param(3 * em + c) : R(0);
+            R rho = col >= 0 ? mat.param(3 * col + c) : R(0);
             L[c] = (E + rho * f * L[c]) * ip;
         }
     }
@@ -304,7 +359,7 @@ __device__ __forceinline__ void radiance_and_adjoint(const BlockScene<R>& bs, co
     R g[3] = {g0[0], g0[1], g0[2]};
     for (int v = 0; v < n; ++v) {
         const int k = rec.prim(v);
-        const int em = bs.emis[k], col = bs.color[k];
+        const int em = mat.em(k), col = mat.col(k);
         const R ip = v >= min_bounces ? inv_p : R(1);
         const R f = rec.w(v) * Real<R>::kInvPi;
 #pragma unroll
@@ -313,7 +368,7 @@ __device__ __forceinline__ void radiance_and_adjoint(const BlockScene<R>& bs, co
             if (em >= 0) sink.add(em, c, gp);
             if (col >= 0) {
                 sink.add(col, c, gp * f * Ls[v + 1][c]);
-                g[c] = gp * f * bs.param[3 * col + c];
+                g[c] = gp * f * mat.param(3 * col + c);
             } else {
                 g[c] = R(0);
             }

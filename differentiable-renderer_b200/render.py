@@ -65,6 +65,9 @@ class Context:
         sc = scene.flatten()
         self._check(self._lib.drtb_scene_upload(self._h, C.byref(sc)))
         self.scene, self._abi_scene = scene, sc
+        mesh = scene.flatten_mesh()
+        if mesh is not None:                      # GPU LBVH build happens here
+            self._check(self._lib.drtb_mesh_upload(self._h, C.byref(mesh)))
         return self
 
     def set_params(self, values: np.ndarray):
@@ -80,7 +83,7 @@ class Context:
         rows = shard_rows(cam.height, opts.shard_index, max(1, opts.shard_count),
                           max(1, opts.band_rows))
         img = np.empty((rows, cam.width, 3), dtype=np.float64) if opts.flags & abi.FLAG_IMAGE else None
-        grad = np.empty((len(self.scene.params), 3), dtype=np.float64) if opts.flags & abi.FLAG_GRAD else None
+        grad = np.empty((self.scene.n_params, 3), dtype=np.float64) if opts.flags & abi.FLAG_GRAD else None
         if seed_img is not None:
             seed_img = np.ascontiguousarray(seed_img, dtype=np.float64)
             assert seed_img.shape == (rows, cam.width, 3)
@@ -116,7 +119,7 @@ class Context:
         keys = np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1)
         n = orig.shape[0]
         rad = np.empty((n, 3), dtype=np.float64)
-        J = np.empty((n, len(self.scene.params), 3), dtype=np.float64) if jac else None
+        J = np.empty((n, self.scene.n_params, 3), dtype=np.float64) if jac else None
         self._check(self._lib.drtb_trace_rays(self._h, C.byref(opts), n, _ptr(orig), _ptr(dirs),
                                               keys.ctypes.data_as(C.POINTER(C.c_uint64)),
                                               _ptr(rad), _ptr(J)))

@@ -80,6 +80,24 @@ typedef struct drtb_camera {
     double  eye[3], forward[3], right[3], up[3];
 } drtb_camera;
 
+/* Triangle mesh (NEW functionality: the reference has no triangle shape and no
+ * acceleration structure).  Semantics are defined to extend the
+ * reference's rules: Moller-Trumbore in the precision of the instantiation,
+ * both sides hit, acceptance t > 0 with no epsilon, barycentric bounds
+ * inclusive (u >= 0, v >= 0, u + v <= 1), det == 0 misses; the normal is the
+ * unit geometric normal normalize(cross(v1 - v0, v2 - v0)) used as given, like
+ * a plane's.  In scene order the triangles FOLLOW the analytic primitives
+ * (triangle i has scene index n_prims + i), so on an exact tie in t the
+ * analytic primitive, then the lower triangle index, wins. */
+typedef struct drtb_mesh {
+    const double*  vertices;   int64_t n_vertices;     /* n_vertices  x 3          */
+    const int32_t* indices;    int64_t n_triangles;    /* n_triangles x 3          */
+    const int32_t* color;      /* per triangle: params[] index of its DiffuseBxDF
+                                  albedo, -1 = null BxDF; NULL = all -1            */
+    const int32_t* emission;   /* per triangle: params[] index of its AreaEmitter
+                                  RGB, -1 = none; NULL = all -1                    */
+} drtb_mesh;
+
 typedef struct drtb_scene {
     const drtb_prim*     prims;      int32_t n_prims;
     const drtb_material* materials;  int32_t n_materials;
@@ -98,6 +116,8 @@ typedef struct drtb_scene {
 #define DRTB_FLAG_IMAGE   1u    /* write the image                              */
 #define DRTB_FLAG_GRAD    2u    /* run the adjoint and write the gradients      */
 #define DRTB_FLAG_STATS   4u    /* fill drtb_stats (segments, lit paths, ...)   */
+#define DRTB_FLAG_NO_BVH  8u    /* test aid: scan every triangle instead of
+                                   traversing the BVH (same results, O(N) per ray) */
 
 typedef struct drtb_render_opts {
     int32_t  spp;               /* samples per pixel  (args.hpp:32-37 `-n`)     */
@@ -128,6 +148,8 @@ typedef struct drtb_stats {
     uint64_t lit_paths;         /* paths with non-zero radiance                 */
     uint64_t truncated_paths;   /* paths cut at max_depth                       */
     uint64_t retraced_paths;    /* DRTB_MIXED: paths re-traced in double        */
+    uint64_t bvh_nodes;         /* mesh scenes: BVH nodes visited               */
+    uint64_t tri_tests;         /* mesh scenes: ray-triangle tests executed     */
     double   kernel_ms;         /* device time of the render kernels (events)   */
 } drtb_stats;
 
@@ -143,7 +165,7 @@ int drtb_device_count(void);
 
 /* sizeof() of the ABI structs as this library was compiled, so a binding can
  * verify its mirror: 0 drtb_prim, 1 drtb_material, 2 drtb_camera, 3 drtb_scene,
- * 4 drtb_render_opts, 5 drtb_stats; anything else returns 0. */
+ * 4 drtb_render_opts, 5 drtb_stats, 6 drtb_mesh; anything else returns 0. */
 size_t drtb_struct_size(int which);
 
 /* Create a context on CUDA device `device`.  Replaces nothing in the reference
@@ -159,6 +181,13 @@ const char* drtb_last_error(const drtb_ctx* ctx);
 /* Flatten-and-upload: replaces the object graph built at src/render.cpp:26-65
  * (parameters, materials, shapes, Scene<T>, Camera<T>).  Copies everything. */
 int drtb_scene_upload(drtb_ctx* ctx, const drtb_scene* scene);
+
+/* Attach a triangle mesh to the uploaded scene (call after drtb_scene_upload;
+ * parameter indices refer to that scene's params[]).  Copies the mesh, builds
+ * an LBVH on the GPU (Morton codes -> radix sort -> Karras hierarchy ->
+ * bottom-up refit).  mesh == NULL or n_triangles == 0 detaches the mesh.
+ * A later drtb_scene_upload detaches it as well. */
+int drtb_mesh_upload(drtb_ctx* ctx, const drtb_mesh* mesh);
 
 /* Overwrite parameter values only (n_params x 3 doubles); the cheap call an
  * optimisation loop makes between renders. */

@@ -40,7 +40,7 @@
 #include <omp.h>
 #endif
 
-#include "drtb.h"
+#include "../include/drtb.h"       // by path: this repo's include/ is NOT on the search path (see Makefile)
 
 namespace {
 
@@ -79,10 +79,48 @@ int oracle_rand()
 #include "drt/vector.hpp"
 #undef rand
 
+// Guard: these must be the REFERENCE's headers.  Its tape is a class tree with a
+// VariableNode (reference vector.hpp:165-192); this repo's drop-in headers have
+// no such type, so picking them up by mistake fails to compile right here.
+static_assert(sizeof(drt::internal::VariableNode<double, 3>) > 0, "not the reference's include/drt");
+
 using namespace drt;
 using T = double;                                    // src/render.cpp:22
 
 namespace {
+
+// Test-only extension: the reference has no triangle shape.
+// This subclass plugs triangles into the reference's OWN raycast / scatter /
+// tape machinery, with the semantics fixed in include/drtb.h, so that the
+// mesh extension of oracle/restate.c can be checked against reference code
+// rather than against itself.
+template <typename S>
+class Triangle : public Shape<S> {
+public:
+    Triangle(Vector<S, 3> v0, Vector<S, 3> v1, Vector<S, 3> v2, std::shared_ptr<BxDF<S>> bxdf = nullptr,
+             std::shared_ptr<Emitter<S>> emitter = nullptr)
+      : Shape<S>(bxdf, emitter), m_v0(v0), m_e1(v1 - v0), m_e2(v2 - v0), m_n(normalize(cross(v1 - v0, v2 - v0))) {}
+
+    bool intersect(Vector<S, 3> orig, Vector<S, 3> dir, double& t) const override
+    {
+        Vector<S, 3> p = cross(dir, m_e2);
+        double det = dot(m_e1, p);
+        if (det == 0.0) return false;
+        double inv = 1.0 / det;
+        Vector<S, 3> tv = orig - m_v0;
+        double u = dot(tv, p) * inv;
+        if (!(u >= 0.0 && u <= 1.0)) return false;
+        Vector<S, 3> q = cross(tv, m_e1);
+        double v = dot(dir, q) * inv;
+        if (!(v >= 0.0 && u + v <= 1.0)) return false;
+        t = dot(m_e2, q) * inv;
+        return t > 0;
+    }
+    Vector<S, 3> normal(Vector<S, 3>) const override { return m_n; }
+
+private:
+    Vector<S, 3> m_v0, m_e1, m_e2, m_n;
+};
 
 // One private copy of the src/render.cpp:26-65 object graph (the reference is
 // not thread-safe: VariableNode::m_grad is a plain +=, vector.hpp:187).
@@ -92,7 +130,7 @@ struct World {
     std::vector<std::unique_ptr<Shape<T>>> shapes;
     Scene<T> scene;
 
-    explicit World(const drtb_scene& s)
+    explicit World(const drtb_scene& s, const drtb_mesh* mesh = nullptr)
     {
         for (int k = 0; k < s.n_params; ++k) {
             Vector<T, 3> v{s.params[3*k], s.params[3*k+1], s.params[3*k+2]};
@@ -123,6 +161,24 @@ struct World {
                 throw std::runtime_error("bad prim type");
             scene.push_back(shapes.back().get());
         }
+        if (mesh) {                                   // triangles follow the analytic primitives
+            std::vector<std::shared_ptr<BxDF<T>>> by_param(size_t(s.n_params));
+            for (int64_t i = 0; i < mesh->n_triangles; ++i) {
+                auto vtx = [&](int c) {
+                    const double* q = mesh->vertices + 3 * int64_t(mesh->indices[3 * i + c]);
+                    return Vector<T, 3>{q[0], q[1], q[2]};
+                };
+                const int col = mesh->color ? mesh->color[i] : -1, em = mesh->emission ? mesh->emission[i] : -1;
+                std::shared_ptr<BxDF<T>> bx;
+                if (col >= 0) {
+                    if (!by_param.at(col)) by_param[col] = std::make_shared<DiffuseBxDF<T>>(params.at(col));
+                    bx = by_param[col];
+                }
+                std::shared_ptr<Emitter<T>> e = em >= 0 ? std::make_shared<AreaEmitter<T>>(params.at(em)) : nullptr;
+                shapes.emplace_back(new Triangle<T>(vtx(0), vtx(1), vtx(2), bx, e));
+                scene.push_back(shapes.back().get());
+            }
+        }
     }
 };
 
@@ -147,10 +203,11 @@ extern "C" {
 // Rows are written compactly in increasing y, exactly as drtb_render does.
 // rand_mode 0: counter stream (drtb.h); 1: as-shipped sequential glibc rand()
 // (single thread, loop order of src/render.cpp:72-76).  Returns 0 or -1.
-int drt_ref_render(const drtb_scene* s, const drtb_render_opts* o,
-                   const double* seed_img, double* img, double* grad,
-                   int n_threads, int rand_mode, uint64_t* draws_out)
+int drt_ref_render_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drtb_render_opts* o,
+                        const double* seed_img, double* img, double* grad,
+                        int n_threads, int rand_mode, uint64_t* draws_out)
 {
+    if (mesh && mesh->n_triangles == 0) mesh = nullptr;
     try {
         const int W = s->camera.width, H = s->camera.height, spp = o->spp;
         std::vector<int> rows;
@@ -173,7 +230,7 @@ int drt_ref_render(const drtb_scene* s, const drtb_render_opts* o,
 #ifdef _OPENMP
             tid = omp_get_thread_num();
 #endif
-            World w(*s);
+            World w(*s, mesh);
             Camera<T> cam = make_camera(s->camera);
             Pathtracer<T> tracer(o->absorb, size_t(o->min_bounces));
             g_libc = rand_mode;
@@ -221,6 +278,13 @@ int drt_ref_render(const drtb_scene* s, const drtb_render_opts* o,
     } catch (...) {
         return -1;
     }
+}
+
+int drt_ref_render(const drtb_scene* s, const drtb_render_opts* o,
+                   const double* seed_img, double* img, double* grad,
+                   int n_threads, int rand_mode, uint64_t* draws_out)
+{
+    return drt_ref_render_mesh(s, nullptr, o, seed_img, img, grad, n_threads, rand_mode, draws_out);
 }
 
 // Single explicit ray through the reference's Pathtracer::trace, for the

@@ -99,12 +99,46 @@ static int sphere_intersect(const drtb_prim* p, v3 o, v3 d, double* t)
     return 0;
 }
 
+/* Triangle (NEW, no reference counterpart; semantics fixed in drtb.h):
+ * Moller-Trumbore, both sides, inclusive barycentric bounds, t > 0. */
+static v3 mesh_vertex(const drtb_mesh* m, int64_t tri, int corner)
+{
+    const double* p = m->vertices + 3 * (int64_t)m->indices[3 * tri + corner];
+    v3 r = {p[0], p[1], p[2]};
+    return r;
+}
+
+static int triangle_intersect(const drtb_mesh* m, int64_t tri, v3 o, v3 d, double* t)
+{
+    v3 v0 = mesh_vertex(m, tri, 0);
+    v3 e1 = sub3(mesh_vertex(m, tri, 1), v0), e2 = sub3(mesh_vertex(m, tri, 2), v0);
+    v3 p = cross3(d, e2);
+    double det = dot3(e1, p);
+    if (det == 0.0) return 0;
+    double inv = 1.0 / det;
+    v3 tv = sub3(o, v0);
+    double u = dot3(tv, p) * inv;
+    if (!(u >= 0.0 && u <= 1.0)) return 0;
+    v3 q = cross3(tv, e1);
+    double v = dot3(d, q) * inv;
+    if (!(v >= 0.0 && u + v <= 1.0)) return 0;
+    *t = dot3(e2, q) * inv;
+    return *t > 0;
+}
+
+static v3 triangle_normal(const drtb_mesh* m, int64_t tri)
+{
+    v3 v0 = mesh_vertex(m, tri, 0);
+    return normalize3(cross3(sub3(mesh_vertex(m, tri, 1), v0), sub3(mesh_vertex(m, tri, 2), v0)));
+}
+
 /* Pathtracer::raycast, pathtracer.hpp:72-89: linear scan in scene order,
- * `!hit || t >= tmin -> continue`, so the first shape wins ties. */
-static int raycast(const drtb_scene* s, v3 o, v3 d, v3* point, v3* normal)
+ * `!hit || t >= tmin -> continue`, so the first shape wins ties.  Triangles
+ * follow the analytic primitives in scene order (index n_prims + i). */
+static int64_t raycast(const drtb_scene* s, const drtb_mesh* mesh, v3 o, v3 d, v3* point, v3* normal)
 {
     double tmin = INFINITY;
-    int best = -1;
+    int64_t best = -1;
     for (int i = 0; i < s->n_prims; ++i) {
         const drtb_prim* p = &s->prims[i];
         double t;
@@ -122,7 +156,28 @@ static int raycast(const drtb_scene* s, v3 o, v3 d, v3* point, v3* normal)
             *normal = normalize3(sub3(*point, c));
         }
     }
+    if (mesh)
+        for (int64_t i = 0; i < mesh->n_triangles; ++i) {
+            double t;
+            if (!triangle_intersect(mesh, i, o, d, &t) || t >= tmin) continue;
+            tmin = t;
+            best = s->n_prims + i;
+            *point = add3(o, mul3(d, t));
+            *normal = triangle_normal(mesh, i);
+        }
     return isinf(tmin) ? -1 : best;
+}
+
+/* material lookup by scene index: analytic prims through materials[], triangles direct */
+static int prim_color(const drtb_scene* s, const drtb_mesh* m, int64_t k)
+{
+    if (k < s->n_prims) return s->prims[k].material >= 0 ? s->materials[s->prims[k].material].color : -1;
+    return m->color ? m->color[k - s->n_prims] : -1;
+}
+static int prim_emission(const drtb_scene* s, const drtb_mesh* m, int64_t k)
+{
+    if (k < s->n_prims) return s->prims[k].emission;
+    return m->emission ? m->emission[k - s->n_prims] : -1;
 }
 
 /* ---- DiffuseBxDF::sample, bxdf.hpp:69-79 with make_frame :29-41 and
@@ -149,7 +204,7 @@ static v3 diffuse_sample(stream_t* rng, v3 n, double* pdf)
  *      from recursion into a vertex list, then the tape's backward
  *      (vector.hpp:418-486) as two sweeps -------------- */
 
-typedef struct { int prim; double p, cosn, pdf; } vertex_t;
+typedef struct { int64_t prim; double p, cosn, pdf; } vertex_t;
 
 typedef struct {
     vertex_t* v; int n, cap;
@@ -170,7 +225,7 @@ typedef struct { uint64_t segments, lit; } counters_t;
 
 /* Traces from (o, d) with the stream positioned after the camera draws;
  * returns L_0 in out[3]; if g0 != NULL accumulates g0 . dL/dparam into grad. */
-static void trace_path(const drtb_scene* s, const drtb_render_opts* opt,
+static void trace_path(const drtb_scene* s, const drtb_mesh* mesh, const drtb_render_opts* opt,
                        stream_t* rng, v3 o, v3 d, path_buf* b,
                        double out[3], const double* g0, double* grad,
                        counters_t* cnt)
@@ -185,12 +240,11 @@ static void trace_path(const drtb_scene* s, const drtb_render_opts* opt,
             p = 1 - absorb;
         }
         v3 pt, n;
-        int k = raycast(s, o, d, &pt, &n);
+        int64_t k = raycast(s, mesh, o, d, &pt, &n);
         cnt->segments++;
         if (k < 0) break;                                /* :134-135 */
-        const drtb_prim* pr = &s->prims[k];
         vertex_t vx = {k, p, 0.0, 1.0};
-        if (pr->material < 0) {
+        if (prim_color(s, mesh, k) < 0) {
             /* null BxDF: dir_out = 0, pdf = 1, brdf = 0 (pathtracer.hpp:25-26,
              * 38-39): every deeper term is multiplied by 0, so the path ends
              * here for all observable purposes. */
@@ -218,12 +272,12 @@ static void trace_path(const drtb_scene* s, const drtb_render_opts* opt,
     L[3*n] = L[3*n+1] = L[3*n+2] = 0.0;
     for (int v = n - 1; v >= 0; --v) {
         const vertex_t* vx = &b->v[v];
-        const drtb_prim* pr = &s->prims[vx->prim];
+        const int em = prim_emission(s, mesh, vx->prim), colp = prim_color(s, mesh, vx->prim);
         for (int c = 0; c < 3; ++c) {
-            double E = pr->emission >= 0 ? s->params[3*pr->emission + c] : 0.0;
+            double E = em >= 0 ? s->params[3*em + c] : 0.0;
             double diffuse = 0.0;
-            if (pr->material >= 0) {
-                double rho = s->params[3*s->materials[pr->material].color + c];
+            if (colp >= 0) {
+                double rho = s->params[3*colp + c];
                 diffuse = 0.0 + (((rho / PI) * L[3*(v+1)+c]) * vx->cosn) / vx->pdf;
             }
             L[3*v+c] = (E + diffuse) / vx->p;
@@ -237,13 +291,13 @@ static void trace_path(const drtb_scene* s, const drtb_render_opts* opt,
     double g[3] = {g0[0], g0[1], g0[2]};
     for (int v = 0; v < n; ++v) {
         const vertex_t* vx = &b->v[v];
-        const drtb_prim* pr = &s->prims[vx->prim];
+        const int em = prim_emission(s, mesh, vx->prim), colp = prim_color(s, mesh, vx->prim);
         for (int c = 0; c < 3; ++c) {
             double gp = g[c] / vx->p;                    /* ScalarDivBackward (/p) */
-            if (pr->emission >= 0)                       /* AddBackward -> VariableNode */
-                grad[3*pr->emission + c] += gp;
-            if (pr->material >= 0) {
-                int col = s->materials[pr->material].color;
+            if (em >= 0)                                 /* AddBackward -> VariableNode */
+                grad[3*em + c] += gp;
+            if (colp >= 0) {
+                int col = colp;
                 double g2 = gp / vx->pdf;                /* ScalarDivBackward (/pdf) */
                 double g3 = vx->cosn * g2;               /* ScalarMulBackward (*cos) */
                 /* MulBackward lhs: brdf.backward(radiance * g3); brdf = color/pi */
@@ -282,10 +336,11 @@ static int row_in_shard(int y, const drtb_render_opts* o)
 
 /* The pixel loop, src/render.cpp:72-86, gradient seed per SAMPLE, not divided
  * by spp or pdf.  Same contract as drtb_render. */
-int drt_oracle_render(const drtb_scene* s, const drtb_render_opts* o,
-                      const double* seed_img, double* img, double* grad,
-                      int n_threads, drtb_stats* stats)
+int drt_oracle_render_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drtb_render_opts* o,
+                           const double* seed_img, double* img, double* grad,
+                           int n_threads, drtb_stats* stats)
 {
+    if (mesh && mesh->n_triangles == 0) mesh = NULL;
     const int W = s->camera.width, H = s->camera.height, spp = o->spp;
     const int P = s->n_params;
     int* rows = (int*)malloc(sizeof(int) * (size_t)(H > 0 ? H : 1));
@@ -324,7 +379,7 @@ int drt_oracle_render(const drtb_scene* s, const drtb_render_opts* o,
                     v3 eye = {s->camera.eye[0], s->camera.eye[1], s->camera.eye[2]};
                     v3 dir = camera_sample(&s->camera, x, y, &rng);
                     double L[3];
-                    trace_path(s, o, &rng, eye, dir, &buf, L,
+                    trace_path(s, mesh, o, &rng, eye, dir, &buf, L,
                                want_grad ? seed : NULL, g, &cnt);
                     for (int c = 0; c < 3; ++c) acc[c] += L[c] / 1.0;   /* /pdf, pdf = 1 */
                 }
@@ -352,11 +407,19 @@ int drt_oracle_render(const drtb_scene* s, const drtb_render_opts* o,
     return 0;
 }
 
-/* Pathtracer::trace on explicit rays (same contract as drtb_trace_rays). */
-int drt_oracle_trace_rays(const drtb_scene* s, const drtb_render_opts* o,
-                          int64_t n, const double* orig, const double* dir,
-                          const uint64_t* keys, double* radiance, double* jac)
+int drt_oracle_render(const drtb_scene* s, const drtb_render_opts* o,
+                      const double* seed_img, double* img, double* grad,
+                      int n_threads, drtb_stats* stats)
 {
+    return drt_oracle_render_mesh(s, NULL, o, seed_img, img, grad, n_threads, stats);
+}
+
+/* Pathtracer::trace on explicit rays (same contract as drtb_trace_rays). */
+int drt_oracle_trace_rays_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drtb_render_opts* o,
+                               int64_t n, const double* orig, const double* dir,
+                               const uint64_t* keys, double* radiance, double* jac)
+{
+    if (mesh && mesh->n_triangles == 0) mesh = NULL;
     const int P = s->n_params;
     path_buf buf; memset(&buf, 0, sizeof buf);
     counters_t cnt = {0, 0};
@@ -368,11 +431,18 @@ int drt_oracle_trace_rays(const drtb_scene* s, const drtb_render_opts* o,
         stream_t rng = {keys[i], 2};
         memset(g, 0, sizeof(double) * (size_t)P * 3);
         /* channels never mix, so one all-ones seed yields the whole diagonal */
-        trace_path(s, o, &rng, og, d, &buf, radiance + 3*i, jac ? one : NULL, g, &cnt);
+        trace_path(s, mesh, o, &rng, og, d, &buf, radiance + 3*i, jac ? one : NULL, g, &cnt);
         if (jac) memcpy(jac + (size_t)i * P * 3, g, sizeof(double) * (size_t)P * 3);
     }
     free(g); free(buf.v); free(buf.L);
     return 0;
+}
+
+int drt_oracle_trace_rays(const drtb_scene* s, const drtb_render_opts* o,
+                          int64_t n, const double* orig, const double* dir,
+                          const uint64_t* keys, double* radiance, double* jac)
+{
+    return drt_oracle_trace_rays_mesh(s, NULL, o, n, orig, dir, keys, radiance, jac);
 }
 
 uint32_t drt_oracle_stream_draw(uint64_t key, uint32_t slot)

@@ -67,6 +67,11 @@ def main():
         assert rc == 0
     np.savez_compressed(HERE / "rays_64_b3_p03.npz", orig=orig, dirs=dirs, keys=keys, radiance=rad, jac=jac)
     print("rays lit:", int((rad.sum(1) > 0).sum()), "of", n)
+    # triangle mesh through the reference's raycast/scatter/tape (test-only Triangle<T> shape)
+    scene = drt.tessellated_room(2, 4, width=32, height=24)
+    img, grad = oracle_lib.ref_render(scene, drt.make_opts(4, 4, 1.0))
+    np.savez_compressed(HERE / "mesh_room_98tri_32x24_4spp_b4.npz", img=img, grad=grad)
+    print("mesh", img.reshape(-1, 3).mean(0), np.count_nonzero(grad))
 
 
 if __name__ == "__main__":

@@ -35,6 +35,12 @@ def load_restate() -> C.CDLL:
     lib.drt_oracle_render.restype = C.c_int
     lib.drt_oracle_render.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.RenderOpts), _dp, _dp, _dp,
                                       C.c_int, C.POINTER(abi.Stats)]
+    lib.drt_oracle_render_mesh.restype = C.c_int
+    lib.drt_oracle_render_mesh.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Mesh), C.POINTER(abi.RenderOpts), _dp, _dp,
+                                           _dp, C.c_int, C.POINTER(abi.Stats)]
+    lib.drt_oracle_trace_rays_mesh.restype = C.c_int
+    lib.drt_oracle_trace_rays_mesh.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Mesh), C.POINTER(abi.RenderOpts),
+                                               C.c_int64, _dp, _dp, C.POINTER(C.c_uint64), _dp, _dp]
     lib.drt_oracle_trace_rays.restype = C.c_int
     lib.drt_oracle_trace_rays.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.RenderOpts), C.c_int64,
                                           _dp, _dp, C.POINTER(C.c_uint64), _dp, _dp]
@@ -59,6 +65,9 @@ def load_ref() -> C.CDLL:
     lib.drt_ref_render.restype = C.c_int
     lib.drt_ref_render.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.RenderOpts), _dp, _dp, _dp,
                                    C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    lib.drt_ref_render_mesh.restype = C.c_int
+    lib.drt_ref_render_mesh.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Mesh), C.POINTER(abi.RenderOpts), _dp, _dp,
+                                        _dp, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     lib.drt_ref_trace_ray.restype = C.c_int
     lib.drt_ref_trace_ray.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.RenderOpts), _dp, _dp,
                                       C.c_uint64, _dp, _dp]
@@ -81,14 +90,15 @@ def _rows(scene, opts):
 def restate_render(scene, opts, seed_img=None, threads=1, want_stats=False):
     lib = load_restate()
     sc = scene.flatten()
+    mesh = scene.flatten_mesh()
     rows = _rows(scene, opts)
     img = np.zeros((rows, scene.camera.width, 3))
-    grad = np.zeros((len(scene.params), 3))
+    grad = np.zeros((scene.n_params, 3))
     st = abi.Stats()
     if seed_img is not None:
         seed_img = np.ascontiguousarray(seed_img, dtype=np.float64)
-    rc = lib.drt_oracle_render(C.byref(sc), C.byref(opts), _ptr(seed_img), _ptr(img), _ptr(grad),
-                               threads, C.byref(st))
+    rc = lib.drt_oracle_render_mesh(C.byref(sc), C.byref(mesh) if mesh is not None else None, C.byref(opts),
+                                    _ptr(seed_img), _ptr(img), _ptr(grad), threads, C.byref(st))
     assert rc == 0
     return (img, grad, st) if want_stats else (img, grad)
 
@@ -96,14 +106,15 @@ def restate_render(scene, opts, seed_img=None, threads=1, want_stats=False):
 def ref_render(scene, opts, seed_img=None, threads=1, rand_mode=0, want_draws=False):
     lib = load_ref()
     sc = scene.flatten()
+    mesh = scene.flatten_mesh()
     rows = _rows(scene, opts)
     img = np.zeros((rows, scene.camera.width, 3))
-    grad = np.zeros((len(scene.params), 3))
+    grad = np.zeros((scene.n_params, 3))
     draws = C.c_uint64()
     if seed_img is not None:
         seed_img = np.ascontiguousarray(seed_img, dtype=np.float64)
-    rc = lib.drt_ref_render(C.byref(sc), C.byref(opts), _ptr(seed_img), _ptr(img), _ptr(grad),
-                            threads, rand_mode, C.byref(draws))
+    rc = lib.drt_ref_render_mesh(C.byref(sc), C.byref(mesh) if mesh is not None else None, C.byref(opts),
+                                 _ptr(seed_img), _ptr(img), _ptr(grad), threads, rand_mode, C.byref(draws))
     assert rc == 0
     return (img, grad, draws.value) if want_draws else (img, grad)
 

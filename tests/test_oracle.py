@@ -179,3 +179,33 @@ def test_stream_is_the_documented_hash_and_stays_below_rand_max():
             assert want <= 2147483646
             assert lib.drt_oracle_stream_draw(key, slot) == want
             assert prod.drtb_stream_draw(key, slot) == want
+
+
+# ---- triangle meshes (new functionality; semantics in include/drtb.h) ---------------
+def mixed_mesh_scene(W=32, H=24):
+    """A tessellated room WITH analytic primitives in front of it: exercises the
+    analytic-then-triangle scene order."""
+    sc = drt.tessellated_room(2, 4, width=W, height=H)
+    ball = drt.DiffuseBxDF(drt.Param(np.array([0.7, 0.6, 0.2]), "ball"))
+    sc.push_back(drt.Sphere((-1.2, -2.0, 2.5), 1.0, ball))
+    sc.push_back(drt.Plane((0.0, 1.0, 0.0), -2.5, drt.DiffuseBxDF(drt.Param(np.array([0.3, 0.4, 0.5]), "floor"))))
+    return sc
+
+
+@needs_ref
+@pytest.mark.parametrize("mb,ab", [(4, 1.0), (1, 0.4)])
+def test_mesh_restatement_equals_reference_with_triangle_shape(mb, ab):
+    """The reference's own raycast/scatter/tape over a test-only Triangle<T> shape
+    (oracle/ref_oracle.cpp) against the flat mesh extension of oracle/restate.c."""
+    for scene in (drt.tessellated_room(2, 4, width=28, height=20), mixed_mesh_scene()):
+        a_img, a_grad = ref_render(scene, drt.make_opts(3, mb, ab, seed=3))
+        b_img, b_grad = restate_render(scene, drt.make_opts(3, mb, ab, seed=3))
+        assert np.array_equal(a_img, b_img)
+        assert rel_err(b_grad, a_grad).max() < 1e-13
+        assert a_img.max() > 0
+
+
+def test_mesh_restatement_matches_golden():
+    z = np.load(GOLDEN / "mesh_room_98tri_32x24_4spp_b4.npz")
+    img, grad = restate_render(drt.tessellated_room(2, 4, width=32, height=24), drt.make_opts(4, 4, 1.0))
+    assert np.array_equal(img, z["img"]) and rel_err(grad, z["grad"]).max() < 1e-13
