@@ -77,6 +77,7 @@ SYMBOLS = [
     ("drtb_last_error", C.c_char_p, [C.c_void_p]),
     ("drtb_scene_upload", C.c_int, [C.c_void_p, C.POINTER(Scene)]),
     ("drtb_mesh_upload", C.c_int, [C.c_void_p, C.POINTER(Mesh)]),
+    ("drtb_mesh_build_ms", C.c_double, [C.c_void_p]),
     ("drtb_set_params", C.c_int, [C.c_void_p, _dp, C.c_int32]),
     ("drtb_shard_rows", C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("drtb_render", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), _dp, _dp, _dp, C.POINTER(Stats)]),

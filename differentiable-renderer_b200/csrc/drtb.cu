@@ -809,6 +809,8 @@ int drtb_mesh_upload(drtb_ctx* ctx, const drtb_mesh* mesh)
     return DRTB_OK;
 }
 
+double drtb_mesh_build_ms(const drtb_ctx* ctx) { return ctx && ctx->n_tris > 0 ? ctx->mesh_build_ms : 0.0; }
+
 int drtb_set_params(drtb_ctx* ctx, const double* params, int32_t n_params)
 {
     if (!ctx) return DRTB_ERR_INVALID;

@@ -131,6 +131,10 @@ class Context:
         return out.value
 
     @property
+    def mesh_build_ms(self) -> float:
+        return float(self._lib.drtb_mesh_build_ms(self._h))
+
+    @property
     def launch_count(self) -> int:
         return int(self._lib.drtb_launch_count(self._h))
 

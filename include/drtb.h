@@ -189,6 +189,10 @@ int drtb_scene_upload(drtb_ctx* ctx, const drtb_scene* scene);
  * A later drtb_scene_upload detaches it as well. */
 int drtb_mesh_upload(drtb_ctx* ctx, const drtb_mesh* mesh);
 
+/* Device time of the last drtb_mesh_upload's BVH build (all build kernels +
+ * the radix sort), in milliseconds; 0 if no mesh is attached. */
+double drtb_mesh_build_ms(const drtb_ctx* ctx);
+
 /* Overwrite parameter values only (n_params x 3 doubles); the cheap call an
  * optimisation loop makes between renders. */
 int drtb_set_params(drtb_ctx* ctx, const double* params, int32_t n_params);
