@@ -162,7 +162,7 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
             const int i = i0 + pass * 32;
             bool lit = false;
             int n = 0;
-            PathRecord<R, MESH> rec;
+            PathRecord<R, MESH, QUEUE ? kQueueDepth : kMaxDepth> rec;
             if (lane_ok && i < spp) {
                 const uint64_t key = a.key0 + ((uint64_t)y * W + x) * (uint64_t)spp + (uint64_t)i;
                 const uint64_t base = key * kKeyMul;
@@ -288,7 +288,7 @@ trace_rays_kernel(const __grid_constant__ DevScene<R> sc, const double* __restri
     const R inv_p = absorb < 1.0 ? R(1.0 / (1.0 - absorb)) : R(0);
     V3<R> o = {R(orig[3 * i]), R(orig[3 * i + 1]), R(orig[3 * i + 2])};
     V3<R> d = {R(dir[3 * i]), R(dir[3 * i + 1]), R(dir[3 * i + 2])};
-    PathRecord<R, MESH> rec;
+    PathRecord<R, MESH, kMaxDepth> rec;
     bool lit;
     TraceCounters cnt;
     int nv = trace_path(sc, bs, mat, (flags & DRTB_FLAG_NO_BVH) != 0, keys[i] * kKeyMul, 2u, o, d, min_bounces, absorb,
@@ -390,24 +390,43 @@ void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
     memset(&d, 0, sizeof d);
     d.n_prims = int(c.prims.size());
     d.n_params = int(c.params.size() / 3);
-    // scan slots: planes first, then spheres, each group in scene order
-    int slot = 0;
-    for (int pass = 0; pass < 2; ++pass)
-        for (int i = 0; i < d.n_prims; ++i) {
-            const drtb_prim& p = c.prims[i];
-            if ((pass == 0) != (p.type == DRTB_PLANE)) continue;
-            for (int j = 0; j < 4; ++j) d.prim[slot][j] = R(p.v[j]);
-            d.id[slot] = int8_t(i);
-            d.slot[i] = int8_t(slot);
-            ++slot;
-        }
-    d.n_planes = 0;
+    // scan slots (see DevScene): the first kFast planes / spheres right-aligned in
+    // the straight-line windows, the rest appended in scene order
+    std::vector<int> planes, spheres;
+    for (int i = 0; i < d.n_prims; ++i) (c.prims[i].type == DRTB_PLANE ? planes : spheres).push_back(i);
+    d.n_fast_planes = std::min<int>(kFast, int(planes.size()));
+    d.n_fast_spheres = std::min<int>(kFast, int(spheres.size()));
+    d.n_over_planes = int(planes.size()) - d.n_fast_planes;
+    d.n_over_spheres = int(spheres.size()) - d.n_fast_spheres;
+    auto put = [&](int slot, int i) {
+        for (int j = 0; j < 4; ++j) d.prim[slot][j] = R(c.prims[i].v[j]);
+        d.id[slot] = i;
+        d.slot[i] = int8_t(slot);
+    };
+    for (int j = 0; j < int(planes.size()); ++j)
+        put(j < d.n_fast_planes ? kFast - d.n_fast_planes + j : 2 * kFast + (j - d.n_fast_planes), planes[j]);
+    for (int j = 0; j < int(spheres.size()); ++j)
+        put(j < d.n_fast_spheres ? 2 * kFast - d.n_fast_spheres + j
+                                 : 2 * kFast + d.n_over_planes + (j - d.n_fast_spheres), spheres[j]);
     for (int i = 0; i < d.n_prims; ++i) {
         const drtb_prim& p = c.prims[i];
-        d.n_planes += p.type == DRTB_PLANE;
         d.type[i] = int8_t(p.type);
         d.color[i] = p.material >= 0 ? c.materials[p.material].color : -1;
         d.emis[i] = p.emission;
+        if (p.type == DRTB_PLANE) {
+            // make_frame(normal), bxdf.hpp:29-41, in double with the reference's own operation order
+            const double n[3] = {p.v[0], p.v[1], p.v[2]};
+            const bool ex = std::fabs(n[0]) < std::fabs(n[1]);
+            const double e[3] = {ex ? 1.0 : 0.0, ex ? 0.0 : 1.0, 0.0};
+            const double en = ex ? n[0] : n[1];
+            double t[3], b[3];
+            for (int j = 0; j < 3; ++j) t[j] = e[j] - n[j] * en;
+            double len = std::sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+            for (int j = 0; j < 3; ++j) t[j] /= len;
+            b[0] = n[1] * t[2] - n[2] * t[1]; b[1] = n[2] * t[0] - n[0] * t[2]; b[2] = n[0] * t[1] - n[1] * t[0];
+            len = std::sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+            for (int j = 0; j < 3; ++j) { d.frame[i][j] = R(t[j]); d.frame[i][3 + j] = R(b[j] / len); }
+        }
     }
     const drtb_camera& cam = c.camera;
     for (int j = 0; j < 3; ++j) {

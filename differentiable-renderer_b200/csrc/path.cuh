@@ -17,23 +17,32 @@ constexpr int kMaxDepth   = 64;    // vertex-record capacity per path
 constexpr int kSmallP     = 8;     // <= this many parameters: per-thread smem gradient columns
 constexpr int kBlock      = 128;
 constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr int kFast       = 8;     // planes / spheres scanned by straight-line code (compile-time slots)
+constexpr int kSlots      = 2 * kFast + kMaxPrims;
 
 // Scene as the kernels see it.  Passed BY VALUE as a __grid_constant__ kernel
 // parameter: the closest-hit scan indexes prim[] with a warp-uniform i, so
 // every operand comes straight out of the constant bank with no load
 // instruction.  (Flattened Scene<T>/Shape<T>/Camera<T>, src/render.cpp:26-65.)
 template <typename R>
-struct DevScene {
-    // Scan order: all planes, then all spheres (two branch-free loops); id[] is
+struct alignas(16) DevScene {
+    // Scan slots.  [0, kFast): the first planes of the scene, RIGHT-aligned, and
+    // [kFast, 2 kFast): the first spheres, right-aligned -- the closest-hit scan
+    // enters straight-line code at slot kFast - n, so every operand of those
+    // tests is a compile-time constant-bank address (no LDC, no loop).  From
+    // 2 kFast on: the planes, then the spheres, that did not fit (rolled loops).
+    // Planes are scanned before spheres, each group in Scene<T> order; id[] is
     // the position in Scene<T>, which decides exact ties (pathtracer.hpp:80).
-    R       prim[kMaxPrims][4];          // plane: n.xyz (RAW), offset ; sphere: c.xyz, r
-    int8_t  id[kMaxPrims];               // scan slot -> scene index
+    R       prim[kSlots][4];             // plane: n.xyz (RAW), offset ; sphere: c.xyz, r
+    int32_t id[kSlots];                  // scan slot -> scene index
+    int32_t n_fast_planes, n_fast_spheres, n_over_planes, n_over_spheres;
     // Indexed by SCENE index:
+    R       frame[kMaxPrims][6];         // planes: make_frame(n) tangent, bitangent (bxdf.hpp:29-41), host double
     int8_t  type[kMaxPrims];             // DRTB_SPHERE | DRTB_PLANE
     int32_t color[kMaxPrims];            // param index of the albedo, -1 = null BxDF
     int32_t emis[kMaxPrims];             // param index of the emission, -1 = no emitter
     int8_t  slot[kMaxPrims];             // scene index -> scan slot
-    int32_t n_prims, n_planes;
+    int32_t n_prims;
     int32_t n_params;
     // Camera (camera.hpp:51-60), constants folded on the host in double with the
     // host libm (the same tan() the reference calls):
@@ -87,6 +96,7 @@ struct RenderArgs {
 template <typename R>
 struct BlockScene {
     R       prim[kMaxPrims][4];
+    R       frame[kMaxPrims][6];         // plane tangent + bitangent
     R       param[kMaxParams * 3];       // staged only when n_params <= kMaxParams
     int32_t color[kMaxPrims], emis[kMaxPrims];
     int8_t  type[kMaxPrims];
@@ -98,6 +108,8 @@ __device__ __forceinline__ void load_block_scene(BlockScene<R>& bs, const DevSce
 {
     for (int i = threadIdx.x; i < sc.n_prims * 4; i += blockDim.x)      // bs.prim is by SCENE index
         bs.prim[i >> 2][i & 3] = sc.prim[sc.slot[i >> 2]][i & 3];
+    for (int i = threadIdx.x; i < sc.n_prims * 6; i += blockDim.x)
+        bs.frame[i / 6][i % 6] = sc.frame[i / 6][i % 6];
     for (int i = threadIdx.x; i < sc.n_prims; i += blockDim.x) {
         bs.type[i] = sc.type[i]; bs.color[i] = sc.color[i]; bs.emis[i] = sc.emis[i];
     }
@@ -123,6 +135,37 @@ __device__ __forceinline__ V3<R> camera_ray(const DevScene<R>& sc, int x, int y,
     return normalize(d);
 }
 
+// One plane / sphere against the running best (bn / bd, best).  SLOT is either
+// a compile-time constant (straight-line scan) or a warp-uniform register.
+template <typename R>
+__device__ __forceinline__ void plane_test(const DevScene<R>& sc, int slot, V3<R> o, V3<R> d, R& bn, R& bd, int& best)
+{
+    const R a0 = sc.prim[slot][0], a1 = sc.prim[slot][1], a2 = sc.prim[slot][2], a3 = sc.prim[slot][3];
+    const R h = Real<R>::fma(o.x, a0, Real<R>::fma(o.y, a1, Real<R>::fma(o.z, a2, -a3)));   // o.n - offset
+    const R g = Real<R>::fma(d.x, a0, Real<R>::fma(d.y, a1, d.z * a2));                     // d.n ; t = h / -g
+    const R num = Real<R>::flip_if_pos(h, g);
+    const R den = Real<R>::abs(g);
+    // t > 0  <=>  num > 0 (den > 0);  den == 0 gives t = +-inf / NaN: rejected as in the reference
+    if (Real<R>::is_pos(num) && Real<R>::is_nonzero(g) && num * bd < bn * den) { bn = num; bd = den; best = sc.id[slot]; }
+}
+
+template <typename R>
+__device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<R> o, V3<R> d, R& bn, R& bd, int& best)
+{
+    const R a0 = sc.prim[slot][0], a1 = sc.prim[slot][1], a2 = sc.prim[slot][2], a3 = sc.prim[slot][3];
+    const V3<R> oc = {o.x - a0, o.y - a1, o.z - a2};
+    const R hb = dot(oc, d);                       // b/2
+    const R c = Real<R>::fma(-a3, a3, dot(oc, oc));
+    const R disc = Real<R>::fma(hb, hb, -c);       // (b^2 - 4c)/4, an exact rescaling
+    const R sq = Real<R>::sqrt(disc);              // NaN when disc < 0: every compare below fails
+    const R t1 = -hb - sq, t2 = sq - hb;           // t1 <= t2
+    const R t = Real<R>::select(Real<R>::is_pos(t1), t1, t2);
+    const int id = sc.id[slot];
+    const R lhs = t * bd;
+    const bool closer = (lhs < bn) | ((lhs == bn) & (id < best));       // bitwise: no branch
+    if (Real<R>::is_pos(t) & closer) { bn = t; bd = R(1); best = id; }
+}
+
 // ---------------------------------------------------------------------------
 // Pathtracer::raycast, pathtracer.hpp:72-89 with Plane::intersect
 // (shape.hpp:49-56) and Sphere::intersect (shape.hpp:78-103, a == 1).
@@ -132,51 +175,73 @@ __device__ __forceinline__ V3<R> camera_ray(const DevScene<R>& sc, int x, int y,
 // cross-multiplication, so a segment costs ONE division (for the winner)
 // instead of one per plane.  Acceptance is the reference's: t > 0, strictly
 // closer than the best so far, the lower scene index winning exact ties.
-// The slot index is warp-uniform: operands come from the constant bank.
+// The first kFast planes and kFast spheres are tested by straight-line code
+// entered through a jump table (their operands are immediate constant-bank
+// addresses); larger scenes continue in rolled loops with a warp-uniform slot.
 // ---------------------------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R> d, R& tmin)
 {
     R bn = Real<R>::inf(), bd = R(1);                  // best t = bn / bd
     int best = -1;
-    const int np = sc.n_planes;
-#pragma unroll 2
-    for (int i = 0; i < np; ++i) {
-        const R a0 = sc.prim[i][0], a1 = sc.prim[i][1], a2 = sc.prim[i][2], a3 = sc.prim[i][3];
-        const R h = Real<R>::fma(o.x, a0, Real<R>::fma(o.y, a1, Real<R>::fma(o.z, a2, -a3)));   // o.n - offset
-        const R g = Real<R>::fma(d.x, a0, Real<R>::fma(d.y, a1, d.z * a2));                     // d.n ; t = h / -g
-        const R num = Real<R>::flip_if_pos(h, g);
-        const R den = Real<R>::abs(g);
-        // t > 0  <=>  num > 0 (den > 0);  den == 0 gives t = +-inf / NaN: rejected as in the reference
-        if (Real<R>::is_pos(num) && Real<R>::is_nonzero(g) && num * bd < bn * den) { bn = num; bd = den; best = sc.id[i]; }
+    switch (kFast - sc.n_fast_planes) {
+        case 0: plane_test(sc, 0, o, d, bn, bd, best); [[fallthrough]];
+        case 1: plane_test(sc, 1, o, d, bn, bd, best); [[fallthrough]];
+        case 2: plane_test(sc, 2, o, d, bn, bd, best); [[fallthrough]];
+        case 3: plane_test(sc, 3, o, d, bn, bd, best); [[fallthrough]];
+        case 4: plane_test(sc, 4, o, d, bn, bd, best); [[fallthrough]];
+        case 5: plane_test(sc, 5, o, d, bn, bd, best); [[fallthrough]];
+        case 6: plane_test(sc, 6, o, d, bn, bd, best); [[fallthrough]];
+        case 7: plane_test(sc, 7, o, d, bn, bd, best); [[fallthrough]];
+        default: break;
     }
-    for (int i = np; i < sc.n_prims; ++i) {
-        const R a0 = sc.prim[i][0], a1 = sc.prim[i][1], a2 = sc.prim[i][2], a3 = sc.prim[i][3];
-        const V3<R> oc = {o.x - a0, o.y - a1, o.z - a2};
-        const R hb = dot(oc, d);                       // b/2
-        const R c = Real<R>::fma(-a3, a3, dot(oc, oc));
-        const R disc = Real<R>::fma(hb, hb, -c);       // (b^2 - 4c)/4, an exact rescaling
-        const R sq = Real<R>::sqrt(disc);              // NaN when disc < 0: every compare below fails
-        const R t1 = -hb - sq, t2 = sq - hb;           // t1 <= t2
-        const R t = Real<R>::select(Real<R>::is_pos(t1), t1, t2);
-        const int id = sc.id[i];
-        const R lhs = t * bd;
-        const bool closer = lhs < bn || (lhs == bn && id < best);
-        if (Real<R>::is_pos(t) && closer) { bn = t; bd = R(1); best = id; }
+    for (int i = 0; i < sc.n_over_planes; ++i) plane_test(sc, 2 * kFast + i, o, d, bn, bd, best);
+    switch (kFast - sc.n_fast_spheres) {
+        case 0: sphere_test(sc, kFast + 0, o, d, bn, bd, best); [[fallthrough]];
+        case 1: sphere_test(sc, kFast + 1, o, d, bn, bd, best); [[fallthrough]];
+        case 2: sphere_test(sc, kFast + 2, o, d, bn, bd, best); [[fallthrough]];
+        case 3: sphere_test(sc, kFast + 3, o, d, bn, bd, best); [[fallthrough]];
+        case 4: sphere_test(sc, kFast + 4, o, d, bn, bd, best); [[fallthrough]];
+        case 5: sphere_test(sc, kFast + 5, o, d, bn, bd, best); [[fallthrough]];
+        case 6: sphere_test(sc, kFast + 6, o, d, bn, bd, best); [[fallthrough]];
+        case 7: sphere_test(sc, kFast + 7, o, d, bn, bd, best); [[fallthrough]];
+        default: break;
     }
+    for (int i = 0; i < sc.n_over_spheres; ++i)
+        sphere_test(sc, 2 * kFast + sc.n_over_planes + i, o, d, bn, bd, best);
     tmin = Real<R>::div(bn, bd);
     return best;
 }
 
+// make_frame (bxdf.hpp:29-41) for a UNIT normal (spheres, triangles): with
+// e the axis the reference picks, tangent = (e - n (e.n)) / sqrt(1 - (e.n)^2)
+// because |e - n (e.n)|^2 = 1 - (e.n)^2 when |n| = 1, and n x tangent is then
+// already a unit vector, so the reference's second normalize() is the
+// identity up to rounding.  (e.n)^2 <= 1/2 by the axis choice: well conditioned.
+// Plane normals may be non-unit (src/render.cpp:42); their frames come from
+// the host, computed with the reference's own formula.
+template <typename R>
+__device__ __forceinline__ void unit_frame(V3<R> n, V3<R>& tg, V3<R>& bt)
+{
+    const bool ex = Real<R>::abs(n.x) < Real<R>::abs(n.y);      // e = (1,0,0) : (0,1,0)
+    const R a = Real<R>::select(ex, n.x, n.y);                  // e.n
+    const R s = Real<R>::fma(-a, a, R(1));                      // |e - n a|^2 = pivot component of e - n a
+    const R r = Real<R>::rsqrt(s);
+    const R m = -a * r;
+    const R piv = s * r;
+    tg = {Real<R>::select(ex, piv, n.x * m), Real<R>::select(ex, n.y * m, piv), n.z * m};
+    bt = cross(n, tg);
+}
+
 // ---------------------------------------------------------------------------
-// DiffuseBxDF::sample (bxdf.hpp:69-79) + make_frame (:29-41) + angle_to_dir
-// (:43-52), then cos = dot(n, dir_out) (pathtracer.hpp:103).  Returns
+// DiffuseBxDF::sample (bxdf.hpp:69-79) + angle_to_dir (:43-52) on the frame
+// (tg, bt, n), then cos = dot(n, dir_out) (pathtracer.hpp:103).  Returns
 // w = cos / pdf.  n is used RAW (the non-unit green-wall normal stays non-unit).
 // sin(asin(sqrt u)) = sqrt u, cos(asin(sqrt u)) = sqrt(1 - u); u < 1 always, so
 // one rsqrt(1 - u) yields both cos(theta) and the 1/cos(theta) that pdf needs.
 // ---------------------------------------------------------------------------
 template <typename R>
-__device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, R u_theta, R u_phi, R& w)
+__device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, V3<R> tg, V3<R> bt, R u_theta, R u_phi, R& w)
 {
     const R st = Real<R>::sqrt(u_theta);
     const R om = R(1) - u_theta;
@@ -184,16 +249,11 @@ __device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, R u_theta, R u_phi, R& 
     const R ct = om * inv_ct;
     R sp, cp;
     Real<R>::sincos2pi(u_phi, &sp, &cp);
-    V3<R> tg;
-    if (Real<R>::abs(n.x) < Real<R>::abs(n.y)) tg = {Real<R>::fma(-n.x, n.x, R(1)), -n.y * n.x, -n.z * n.x};
-    else                                       tg = {-n.x * n.y, Real<R>::fma(-n.y, n.y, R(1)), -n.z * n.y};
-    tg = normalize(tg);
-    const V3<R> bt = normalize(cross(n, tg));
     const R x = cp * st, y = sp * st;
     const V3<R> dout = {x * tg.x + y * bt.x + ct * n.x,
                         x * tg.y + y * bt.y + ct * n.y,
                         x * tg.z + y * bt.z + ct * n.z};
-    w = dot(n, dout) * Real<R>::kPi * inv_ct;          // dot(n, dout) / (cos(theta) / pi)
+    w = dot(n, dout) * (Real<R>::pi() * inv_ct);       // dot(n, dout) / (cos(theta) / pi)
     return dout;
 }
 
@@ -204,11 +264,12 @@ __device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, R u_theta, R u_phi, R& 
 template <bool MESH> struct PrimId { using type = uint8_t; };
 template <> struct PrimId<true> { using type = int32_t; };
 
-template <typename R, bool MESH>
+template <typename R, bool MESH, int CAP>
 struct PathRecord {
     using Id = typename PrimId<MESH>::type;
-    R  w_[kMaxDepth];
-    Id prim_[kMaxDepth];
+    static constexpr int kCap = CAP;     // kQueueDepth for the compacting kernels, kMaxDepth otherwise: the
+    R  w_[CAP];                          // per-thread local-memory footprint has to stay inside L2
+    Id prim_[CAP];
     __device__ __forceinline__ R w(int v) const { return w_[v]; }
     __device__ __forceinline__ int prim(int v) const { return int(prim_[v]); }
 };
@@ -224,6 +285,7 @@ constexpr int kQueueDepth = 16;    // deepest record the ring stores; deeper run
 template <typename R, bool MESH>
 struct QueueView {                 // one record of one warp's ring
     using Id = typename PrimId<MESH>::type;
+    static constexpr int kCap = kQueueDepth;
     const R* w_;                   // &ring_w[slot], stride kQueueSlots
     const Id* prim_;
     __device__ __forceinline__ R w(int v) const { return w_[v * kQueueSlots]; }
@@ -265,12 +327,12 @@ struct TraceCounters { uint32_t segments = 0, truncated = 0, bvh_nodes = 0, tri_
 // gradient of the path are exactly zero and the sweeps are skipped).
 // `slot` is the next stream slot (2 after the camera draws).
 // ---------------------------------------------------------------------------
-template <typename R, bool MESH>
+template <typename R, bool MESH, int CAP>
 __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScene<R>& bs,
                                           const Materials<R, MESH>& mat, bool no_bvh,
                                           uint64_t base, uint32_t slot, V3<R> o, V3<R> d,
                                           int min_bounces, double absorb, int max_depth,
-                                          PathRecord<R, MESH>& rec, bool& lit, TraceCounters& cnt)
+                                          PathRecord<R, MESH, CAP>& rec, bool& lit, TraceCounters& cnt)
 {
     using Id = typename PrimId<MESH>::type;
     int n = 0;
@@ -300,27 +362,34 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
             rec.w_[n++] = R(0);
             break;
         }
-        V3<R> nrm;
+        V3<R> nrm, tg, bt;
         bool on_mesh = false;
         if constexpr (MESH) {
             if (tri >= 0) {                                 // unit geometric normal, drtb.h
                 const TriData<R> T = load_tri<R>(mat.mesh, tri);
                 nrm = normalize(cross(T.e1, T.e2));
+                unit_frame(nrm, tg, bt);
                 on_mesh = true;
             }
         }
         if (!on_mesh) {
             nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]};
-            if (bs.type[k] == DRTB_SPHERE)                  // shape.hpp:105-106
+            if (bs.type[k] == DRTB_SPHERE) {                // shape.hpp:105-106
                 nrm = normalize(V3<R>{pt.x - nrm.x, pt.y - nrm.y, pt.z - nrm.z});
+                unit_frame(nrm, tg, bt);
+            } else {                                        // plane: constant frame, bxdf.hpp:29-41 on the host
+                tg = {bs.frame[k][0], bs.frame[k][1], bs.frame[k][2]};
+                bt = {bs.frame[k][3], bs.frame[k][4], bs.frame[k][5]};
+            }
         }
         R u_theta = Real<R>::uniform_fast(stream_draw_base(base, slot));
         R u_phi   = Real<R>::uniform_fast(stream_draw_base(base, slot + 1));
         slot += 2;
         R w;
-        V3<R> dout = diffuse_sample(nrm, u_theta, u_phi, w);
+        V3<R> dout = diffuse_sample(nrm, tg, bt, u_theta, u_phi, w);
         rec.w_[n++] = w;
-        o = {pt.x + R(1e-3) * dout.x, pt.y + R(1e-3) * dout.y, pt.z + R(1e-3) * dout.z};   // :99
+        const R eps = Real<R>::origin_eps();                // 1e-3, pathtracer.hpp:99
+        o = {Real<R>::fma(eps, dout.x, pt.x), Real<R>::fma(eps, dout.y, pt.y), Real<R>::fma(eps, dout.z, pt.z)};
         d = dout;
     }
     return n;
@@ -339,13 +408,13 @@ __device__ __forceinline__ void radiance_and_adjoint(const Mat& mat, const Rec& 
                                                      int n, int min_bounces, R inv_p,
                                                      bool want_grad, const R g0[3], R L0[3], Sink& sink)
 {
-    R Ls[kMaxDepth + 1][3];
+    R Ls[Rec::kCap + 1][3];
     R L[3] = {R(0), R(0), R(0)};
     for (int v = n - 1; v >= 0; --v) {
         const int k = rec.prim(v);
         const int em = mat.em(k), col = mat.col(k);
         const R ip = v >= min_bounces ? inv_p : R(1);
-        const R f = rec.w(v) * Real<R>::kInvPi;
+        const R f = rec.w(v) * Real<R>::inv_pi();
         if (want_grad) { Ls[v + 1][0] = L[0]; Ls[v + 1][1] = L[1]; Ls[v + 1][2] = L[2]; }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -361,7 +430,7 @@ __device__ __forceinline__ void radiance_and_adjoint(const Mat& mat, const Rec& 
         const int k = rec.prim(v);
         const int em = mat.em(k), col = mat.col(k);
         const R ip = v >= min_bounces ? inv_p : R(1);
-        const R f = rec.w(v) * Real<R>::kInvPi;
+        const R f = rec.w(v) * Real<R>::inv_pi();
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             R gp = g[c] * ip;

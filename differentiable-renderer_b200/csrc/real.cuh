@@ -15,9 +15,25 @@ namespace drtb {
 
 template <typename R> struct Real;
 
+// Double constants that are not encodable as a 32-bit immediate live in the
+// constant bank: an FP64 instruction can take c[bank][offset] as an operand
+// directly, whereas a literal costs two UMOVs each time it is rematerialised
+// (34 per ray segment for the sincos polynomials alone in the first builds).
+struct ConstF64 {
+    double sin_c[8], cos_c[8];
+    double half_pi, pi, inv_pi, inv_m, m, origin_eps;
+};
+__constant__ ConstF64 kC64 = {
+    {2.8114572543455206e-15, -7.6471637318198164e-13, 1.6059043836821613e-10, -2.5052108385441720e-08,
+     2.7557319223985893e-06, -1.9841269841269841e-04, 8.3333333333333332e-03, -1.6666666666666666e-01},
+    {-1.5619206968586225e-16, 4.7794773323873853e-14, -1.1470745597729725e-11, 2.0876756987868100e-09,
+     -2.7557319223985888e-07, 2.4801587301587302e-05, -1.3888888888888889e-03, 4.1666666666666664e-02},
+    1.5707963267948966, 3.14159265358979323846, 0.31830988618379067154, 1.0 / 2147483647.0, 2147483647.0, 1e-3};
+
 template <> struct Real<double> {
-    static constexpr double kPi    = 3.14159265358979323846;   // constants.hpp:9
-    static constexpr double kInvPi = 0.31830988618379067154;
+    static __device__ __forceinline__ double pi() { return kC64.pi; }           // constants.hpp:9
+    static __device__ __forceinline__ double inv_pi() { return kC64.inv_pi; }
+    static __device__ __forceinline__ double origin_eps() { return kC64.origin_eps; }
     static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000ll); }
     static __device__ __forceinline__ double abs(double a) { return ::fabs(a); }
     static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
@@ -77,25 +93,15 @@ template <> struct Real<double> {
         const double x = 4.0 * u;
         const int q = __double2int_rn(x);
         const double r = x - double(q);                          // exact, |r| <= 0.5
-        const double t = r * 1.5707963267948966;                 // r * pi/2, |t| <= pi/4
+        const double t = r * kC64.half_pi;                       // r * pi/2, |t| <= pi/4
         const double t2 = t * t;
-        double ps = 2.8114572543455206e-15;                      //  1/17!
-        ps = ::fma(ps, t2, -7.6471637318198164e-13);             // -1/15!
-        ps = ::fma(ps, t2, 1.6059043836821613e-10);              //  1/13!
-        ps = ::fma(ps, t2, -2.5052108385441720e-08);             // -1/11!
-        ps = ::fma(ps, t2, 2.7557319223985893e-06);              //  1/9!
-        ps = ::fma(ps, t2, -1.9841269841269841e-04);             // -1/7!
-        ps = ::fma(ps, t2, 8.3333333333333332e-03);              //  1/5!
-        ps = ::fma(ps, t2, -1.6666666666666666e-01);             // -1/3!
+        double ps = kC64.sin_c[0];                               //  1/17!, -1/15!, ... -1/3!
+#pragma unroll
+        for (int i = 1; i < 8; ++i) ps = ::fma(ps, t2, kC64.sin_c[i]);
         const double sn = ::fma(ps * t2, t, t);
-        double pc = -1.5619206968586225e-16;                     // -1/18!
-        pc = ::fma(pc, t2, 4.7794773323873853e-14);              //  1/16!
-        pc = ::fma(pc, t2, -1.1470745597729725e-11);             // -1/14!
-        pc = ::fma(pc, t2, 2.0876756987868100e-09);              //  1/12!
-        pc = ::fma(pc, t2, -2.7557319223985888e-07);             // -1/10!
-        pc = ::fma(pc, t2, 2.4801587301587302e-05);              //  1/8!
-        pc = ::fma(pc, t2, -1.3888888888888889e-03);             // -1/6!
-        pc = ::fma(pc, t2, 4.1666666666666664e-02);              //  1/4!
+        double pc = kC64.cos_c[0];                               // -1/18!, 1/16!, ... 1/4!
+#pragma unroll
+        for (int i = 1; i < 8; ++i) pc = ::fma(pc, t2, kC64.cos_c[i]);
         pc = ::fma(pc, t2, -0.5);
         const double cs = ::fma(pc, t2, 1.0);
         // rotate by q quarter turns: (sin, cos)(a + q pi/2)
@@ -110,7 +116,7 @@ template <> struct Real<double> {
     // q0 = RN(k/M) up to 1 ulp, one FMA residual step makes it exact (Markstein).
     static __device__ __forceinline__ double uniform(uint32_t k)
     {
-        const double M = 2147483647.0, inv = 1.0 / 2147483647.0;
+        const double M = kC64.m, inv = kC64.inv_m;
         double a = double(k);
         double q = a * inv;
         double r = ::fma(-q, M, a);
@@ -118,12 +124,13 @@ template <> struct Real<double> {
     }
     // The same to 1 ulp (k * RN(1/M)) for draws that feed continuous quantities
     // (pixel jitter, theta, phi); Russian roulette keeps the exact one.
-    static __device__ __forceinline__ double uniform_fast(uint32_t k) { return double(k) * (1.0 / 2147483647.0); }
+    static __device__ __forceinline__ double uniform_fast(uint32_t k) { return double(k) * kC64.inv_m; }
 };
 
 template <> struct Real<float> {
-    static constexpr float kPi    = 3.14159265358979323846f;
-    static constexpr float kInvPi = 0.31830988618379067154f;
+    static __device__ __forceinline__ float pi() { return 3.14159265358979323846f; }
+    static __device__ __forceinline__ float inv_pi() { return 0.31830988618379067154f; }
+    static __device__ __forceinline__ float origin_eps() { return 1e-3f; }
     static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
     static __device__ __forceinline__ float abs(float a) { return ::fabsf(a); }
     static __device__ __forceinline__ float fma(float a, float b, float c) { return ::fmaf(a, b, c); }
