@@ -1,4 +1,4 @@
-// bvh.cuh — triangle meshes: GPU-built LBVH and its traversal.
+// bvh.cuh — triangle meshes: GPU-built 4-wide BVH and its traversal.
 //
 // NEW functionality (the reference has planes and spheres only, scanned
 // linearly: pathtracer.hpp:72-89).  Semantics are fixed in include/drtb.h so
@@ -6,14 +6,24 @@
 // return if it had a Triangle shape: closest t > 0, exact ties to the lower
 // scene index.
 //
-// Build (all on the device, Karras 2012): per-triangle bounds + centroid ->
-// 63-bit Morton code -> cub radix sort -> binary radix tree over the sorted
-// codes -> bottom-up refit with one atomic counter per internal node.
-// Node = 64 B: the AABBs of BOTH children + two child links, so one 64-byte
-// read (4 x float4 through the read-only path) decides both subtrees.
-// Boxes are float, rounded outward and padded, and the slab test is
-// conservative, so float culling can never reject a triangle the double
-// intersection test would accept.
+// Build, all on the device:
+//   1. per-triangle bounds + centroid -> 63-bit Morton code -> cub radix sort
+//   2. binary tree over the sorted leaves, either
+//        PLOC  (parallel locally-ordered clustering, Meister & Bittner 2018):
+//              every cluster looks kPlocRadius neighbours left and right along
+//              the Morton order for the partner with the smallest merged
+//              surface area, mutual nearest neighbours merge, repeat -- an
+//              agglomerative build whose SAH cost is far below LBVH's; or
+//        LBVH  (Karras 2012): binary radix tree over the codes + bottom-up refit
+//              (kept as the fast-build option, DRTB_BVH=lbvh)
+//   3. collapse to a 4-wide BVH, top-down and level-synchronous: a wide node
+//      adopts the grandchildren with the largest surface area first; subtrees
+//      of <= kLeafMax triangles become leaves and their triangles are stored
+//      contiguously in leaf order.
+// Wide node = 128 B (one cache line): the 4 child boxes as SoA float4 rows
+// (lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4]) + 4 child links.  Boxes
+// are float, rounded outward and padded, and the slab test is conservative, so
+// float culling can never reject a triangle the exact test would accept.
 #pragma once
 #include <cfloat>
 #include <cstdint>
@@ -23,16 +33,20 @@
 
 namespace drtb {
 
-constexpr int kBvhStack = 96;            // >= 63 Morton bits + 32 index bits of LBVH depth
+constexpr int kBvhStack   = 64;           // traversal stack entries per lane (overflow falls back to a linear scan)
+constexpr int kLeafMax    = 4;            // triangles per leaf (2 bits of the leaf link)
+constexpr int kPlocRadius = 16;           // PLOC neighbour search radius along the Morton order
 constexpr int kTri64Stride = 10;          // doubles per triangle: v0, e1, e2, pad (16-byte aligned rows)
 constexpr int kTri32Stride = 3;           // float4 per triangle
+constexpr int kNodeStride  = 8;           // float4 per wide node
+constexpr int kEmptyLink   = 0x7fffffff;
 
 struct MeshView {
-    const float4*  nodes;                 // 4 float4 per node (n_tris - 1 nodes)
-    const double*  tri64;                 // v0.xyz e1.xyz e2.xyz pad
-    const float4*  tri32;                 // (v0.xyz,e1.x) (e1.yz,e2.xy) (e2.z,0,0,0)
-    const int32_t* color;                 // per triangle: param index of the albedo, -1 = null BxDF
-    const int32_t* emis;                  // per triangle: param index of the emission, -1 = none
+    const float4*  nodes;                 // kNodeStride float4 per wide node; node 0 is the root
+    const double*  tri64;                 // ORIGINAL order: v0.xyz e1.xyz e2.xyz pad
+    const float4*  tri32;                 // LEAF order: (v0.xyz,e1.x) (e1.yz,e2.xy) (e2.z, max|e1|, max|e2|, original index)
+    const int32_t* color;                 // per triangle (original order): param index of the albedo, -1 = null BxDF
+    const int32_t* emis;                  // per triangle (original order): param index of the emission, -1 = none
     int32_t n_tris;
     int32_t n_prims;                      // scene index of triangle 0
 };
@@ -52,10 +66,9 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u)
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// per triangle: edge form in double and float, outward-rounded float AABB, centroid; scene bounds
+// per triangle: edge form in double, outward-rounded float AABB; scene bounds
 __global__ void mesh_prepare_kernel(const double* __restrict__ vertices, const int32_t* __restrict__ indices, int n,
-                                    double* __restrict__ tri64, float4* __restrict__ tri32,
-                                    float* __restrict__ leaf_lo, float* __restrict__ leaf_hi,
+                                    double* __restrict__ tri64, float4* __restrict__ leaf_lo, float4* __restrict__ leaf_hi,
                                     uint32_t* __restrict__ bounds /* [6] ordered: lo xyz, hi xyz */)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,12 +84,10 @@ __global__ void mesh_prepare_kernel(const double* __restrict__ vertices, const i
             t[a] = v[0][a]; t[3 + a] = v[1][a] - v[0][a]; t[6 + a] = v[2][a] - v[0][a];
             const double mn = fmin(v[0][a], fmin(v[1][a], v[2][a])), mx = fmax(v[0][a], fmax(v[1][a], v[2][a]));
             lo[a] = __double2float_rd(mn); hi[a] = __double2float_ru(mx);
-            leaf_lo[3ll * i + a] = lo[a]; leaf_hi[3ll * i + a] = hi[a];
         }
         t[9] = 0.0;
-        tri32[(size_t)i * 3 + 0] = make_float4(float(t[0]), float(t[1]), float(t[2]), float(t[3]));
-        tri32[(size_t)i * 3 + 1] = make_float4(float(t[4]), float(t[5]), float(t[6]), float(t[7]));
-        tri32[(size_t)i * 3 + 2] = make_float4(float(t[8]), 0.f, 0.f, 0.f);
+        leaf_lo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        leaf_hi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
     }
     for (int a = 0; a < 3; ++a) {
         float l = lo[a], h = hi[a];
@@ -102,16 +113,18 @@ __device__ __forceinline__ uint64_t spread21(uint32_t v)      // 21 bits -> ever
     return x;
 }
 
-__global__ void mesh_morton_kernel(const float* __restrict__ leaf_lo, const float* __restrict__ leaf_hi,
+__global__ void mesh_morton_kernel(const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                                    const uint32_t* __restrict__ bounds, int n, uint64_t* __restrict__ keys,
                                    uint32_t* __restrict__ vals)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const float4 l = leaf_lo[i], h = leaf_hi[i];
+    const float cl[3] = {l.x, l.y, l.z}, ch[3] = {h.x, h.y, h.z};
     uint64_t code = 0;
     for (int a = 0; a < 3; ++a) {
         const float lo = ordered_to_float(bounds[a]), hi = ordered_to_float(bounds[3 + a]);
-        const float c = 0.5f * (leaf_lo[3ll * i + a] + leaf_hi[3ll * i + a]);
+        const float c = 0.5f * (cl[a] + ch[a]);
         const float ext = hi - lo;
         float u = ext > 0.f ? (c - lo) / ext : 0.f;
         u = fminf(fmaxf(u, 0.f), 1.f);
@@ -122,7 +135,39 @@ __global__ void mesh_morton_kernel(const float* __restrict__ leaf_lo, const floa
     vals[i] = uint32_t(i);
 }
 
-// longest common prefix of sorted keys i and j; equal keys fall back to the index (Karras 2012, §4)
+// Binary-tree node ids shared by both builders: id < n is the leaf at SORTED
+// position id, id >= n is internal node id - n.  Per node: box (lo.xyz | hi.xyz),
+// lo.w = triangle count (as int bits).
+struct BinTree {
+    float4* lo;                           // [2n - 1]
+    float4* hi;                           // [2n - 1]
+    int2*   children;                     // [n - 1], indexed by id - n
+};
+
+__device__ __forceinline__ float box_area(float4 lo, float4 hi)
+{
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// leaves of the binary tree, in Morton order, boxes padded for the float slab test
+__global__ void bin_leaves_kernel(const uint32_t* __restrict__ sorted_tri, const float4* __restrict__ leaf_lo,
+                                  const float4* __restrict__ leaf_hi, const uint32_t* __restrict__ bounds, int n,
+                                  BinTree t)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    float ext = 0.f;
+    for (int a = 0; a < 3; ++a) ext = fmaxf(ext, ordered_to_float(bounds[3 + a]) - ordered_to_float(bounds[a]));
+    const float pad = 4e-6f * ext + FLT_MIN;          // covers float rounding of the ray and of the slab test
+    const uint32_t tri = sorted_tri[p];
+    const float4 l = leaf_lo[tri], h = leaf_hi[tri];
+    t.lo[p] = make_float4(l.x - pad, l.y - pad, l.z - pad, __int_as_float(1));
+    t.hi[p] = make_float4(h.x + pad, h.y + pad, h.z + pad, 0.f);
+}
+
+// ---- LBVH (Karras 2012) ----------------------------------------------------
+// longest common prefix of sorted keys i and j; equal keys fall back to the index
 __device__ __forceinline__ int lbvh_delta(const uint64_t* __restrict__ keys, int n, int i, int j)
 {
     if (j < 0 || j >= n) return -1;
@@ -130,9 +175,8 @@ __device__ __forceinline__ int lbvh_delta(const uint64_t* __restrict__ keys, int
     return a == b ? 64 + __clz(uint32_t(i) ^ uint32_t(j)) : __clzll((long long)(a ^ b));
 }
 
-// child link encoding while building: >= 0 internal node, < 0 leaf at SORTED position ~c
 __global__ void lbvh_hierarchy_kernel(const uint64_t* __restrict__ keys, int n, int2* __restrict__ children,
-                                      int* __restrict__ parent_of_node, int* __restrict__ parent_of_leaf)
+                                      int* __restrict__ parent /* [2n-1] by node id */)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -152,61 +196,188 @@ __global__ void lbvh_hierarchy_kernel(const uint64_t* __restrict__ keys, int n, 
     } while (t > 1);
     const int gamma = i + s * d + min(d, 0);
     const int lo = min(i, j), hi = max(i, j);
-    const int left = lo == gamma ? ~gamma : gamma;
-    const int right = hi == gamma + 1 ? ~(gamma + 1) : gamma + 1;
+    const int left = lo == gamma ? gamma : n + gamma;              // leaf id : internal id
+    const int right = hi == gamma + 1 ? gamma + 1 : n + gamma + 1;
     children[i] = make_int2(left, right);
-    if (left < 0) parent_of_leaf[~left] = i; else parent_of_node[left] = i;
-    if (right < 0) parent_of_leaf[~right] = i; else parent_of_node[right] = i;
-    if (i == 0) parent_of_node[0] = -1;
-}
-
-struct Box { float lo[3], hi[3]; };
-
-__device__ __forceinline__ Box node_union(const volatile float* nd)   // union of a finished node's two child boxes
-{
-    Box b;
-    for (int a = 0; a < 3; ++a) {
-        b.lo[a] = fminf(nd[a], nd[6 + a]);
-        b.hi[a] = fmaxf(nd[3 + a], nd[9 + a]);
-    }
-    return b;
+    parent[left] = n + i;
+    parent[right] = n + i;
+    if (i == 0) parent[n] = -1;
 }
 
 // one thread per leaf climbs; the second arrival at a node owns it
-__global__ void lbvh_refit_kernel(const uint32_t* __restrict__ sorted_tri, const float* __restrict__ leaf_lo,
-                                  const float* __restrict__ leaf_hi, const int2* __restrict__ children,
-                                  const int* __restrict__ parent_of_node, const int* __restrict__ parent_of_leaf,
-                                  const uint32_t* __restrict__ bounds, int n, int* __restrict__ arrivals,
-                                  float* __restrict__ nodes /* 16 floats per node */)
+__global__ void lbvh_refit_kernel(int n, const int* __restrict__ parent, int* __restrict__ arrivals, BinTree t)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    float ext = 0.f;
-    for (int a = 0; a < 3; ++a) ext = fmaxf(ext, ordered_to_float(bounds[3 + a]) - ordered_to_float(bounds[a]));
-    const float pad = 4e-6f * ext + FLT_MIN;          // covers float rounding of the ray and of the slab test
-    int node = parent_of_leaf[p];
+    int node = parent[p];
     while (node >= 0) {
         __threadfence();
-        if (atomicAdd(arrivals + node, 1) == 0) return;
-        const int2 ch = children[node];
-        float* out = nodes + (size_t)node * 16;
-        const int link[2] = {ch.x, ch.y};
-        int enc[2];
-        for (int k = 0; k < 2; ++k) {
-            Box b;
-            if (link[k] < 0) {
-                const uint32_t tri = sorted_tri[~link[k]];
-                for (int a = 0; a < 3; ++a) { b.lo[a] = leaf_lo[3ll * tri + a] - pad; b.hi[a] = leaf_hi[3ll * tri + a] + pad; }
-                enc[k] = ~int(tri);                   // leaves point at the ORIGINAL triangle index
-            } else {
-                b = node_union(nodes + (size_t)link[k] * 16);
-                enc[k] = link[k];
-            }
-            for (int a = 0; a < 3; ++a) { out[6 * k + a] = b.lo[a]; out[6 * k + 3 + a] = b.hi[a]; }
-        }
-        out[12] = __int_as_float(enc[0]); out[13] = __int_as_float(enc[1]); out[14] = 0.f; out[15] = 0.f;
-        node = parent_of_node[node];
+        if (atomicAdd(arrivals + (node - n), 1) == 0) return;
+        const int2 ch = t.children[node - n];
+        const volatile float4* vlo = t.lo; const volatile float4* vhi = t.hi;
+        const float4 al = {vlo[ch.x].x, vlo[ch.x].y, vlo[ch.x].z, vlo[ch.x].w};
+        const float4 bl = {vlo[ch.y].x, vlo[ch.y].y, vlo[ch.y].z, vlo[ch.y].w};
+        const float4 ah = {vhi[ch.x].x, vhi[ch.x].y, vhi[ch.x].z, 0.f};
+        const float4 bh = {vhi[ch.y].x, vhi[ch.y].y, vhi[ch.y].z, 0.f};
+        t.lo[node] = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z),
+                                 __int_as_float(__float_as_int(al.w) + __float_as_int(bl.w)));
+        t.hi[node] = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f);
+        node = parent[node];
     }
+}
+
+// ---- PLOC -------------------------------------------------------------------
+// clusters[i] = node id of the i-th live cluster, in Morton order.
+// nearest[i] = the j in [i - R, i + R] \ {i} minimising area(box_i U box_j); ties -> smaller j.
+__global__ void __launch_bounds__(256)
+ploc_nearest_kernel(const int* __restrict__ clusters, int m, BinTree t, int* __restrict__ nearest)
+{
+    constexpr int R = kPlocRadius, T = 256;
+    __shared__ float4 s_lo[T + 2 * R], s_hi[T + 2 * R];
+    const int base = blockIdx.x * T - R;
+    for (int k = threadIdx.x; k < T + 2 * R; k += T) {
+        const int g = base + k;
+        if (g >= 0 && g < m) { const int id = clusters[g]; s_lo[k] = t.lo[id]; s_hi[k] = t.hi[id]; }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * T + threadIdx.x;
+    if (i >= m) return;
+    const float4 al = s_lo[threadIdx.x + R], ah = s_hi[threadIdx.x + R];
+    float best = FLT_MAX; int bj = -1;
+    for (int k = 0; k <= 2 * R; ++k) {
+        const int j = base + threadIdx.x + k;                     // i - R + k
+        if (k == R || j < 0 || j >= m) continue;
+        const float4 bl = s_lo[threadIdx.x + k], bh = s_hi[threadIdx.x + k];
+        const float4 ul = {fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.f};
+        const float4 uh = {fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f};
+        const float a = box_area(ul, uh);
+        if (a < best) { best = a; bj = j; }
+    }
+    nearest[i] = bj;
+}
+
+// flags[i]: low 32 bits = 1 if cluster i survives (alone or as the merged pair's
+// left member), high 32 bits = 1 if i leads a merge (allocates a node)
+__global__ void ploc_flag_kernel(const int* __restrict__ nearest, int m, uint64_t* __restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int j = nearest[i];
+    const bool mutual = j >= 0 && nearest[j] == i;
+    const uint64_t keep = !(mutual && j < i);
+    const uint64_t lead = mutual && i < j;
+    flags[i] = keep | (lead << 32);
+}
+
+// scan[i] = exclusive prefix sums of flags; merged leaders create node n + first_node + (#leaders before i)
+__global__ void ploc_merge_kernel(const int* __restrict__ clusters, const int* __restrict__ nearest,
+                                  const uint64_t* __restrict__ flags, const uint64_t* __restrict__ scan, int m, int n,
+                                  int first_node, BinTree t, int* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint64_t f = flags[i];
+    if (!(f & 1u)) return;
+    const int pos = int(scan[i] & 0xffffffffu);
+    int id = clusters[i];
+    if (f >> 32) {
+        const int other = clusters[nearest[i]];
+        const int k = first_node + int(scan[i] >> 32);            // internal index
+        t.children[k] = make_int2(id, other);
+        const float4 al = t.lo[id], ah = t.hi[id], bl = t.lo[other], bh = t.hi[other];
+        t.lo[n + k] = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z),
+                                  __int_as_float(__float_as_int(al.w) + __float_as_int(bl.w)));
+        t.hi[n + k] = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f);
+        id = n + k;
+    }
+    out[pos] = id;
+}
+
+// ---- collapse to the 4-wide BVH ----------------------------------------------
+struct CollapseCounters { int nodes, tris, next; int pad; };
+
+__device__ __forceinline__ int bin_count(const BinTree& t, int id) { return __float_as_int(t.lo[id].w); }
+
+// One thread per (binary node -> wide node slot) task of this level.
+__global__ void collapse_kernel(const int2* __restrict__ tasks, int n_tasks, int n, BinTree t,
+                                const uint32_t* __restrict__ sorted_tri, float4* __restrict__ nodes,
+                                int32_t* __restrict__ leaf_order, CollapseCounters* __restrict__ cnt,
+                                int2* __restrict__ next_tasks)
+{
+    const int ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= n_tasks) return;
+    const int b = tasks[ti].x, slot = tasks[ti].y;
+    int cand[4]; int nc;
+    if (b < n || bin_count(t, b) <= kLeafMax) { cand[0] = b; nc = 1; }        // tiny mesh: the root is a leaf
+    else {
+        const int2 ch = t.children[b - n];
+        cand[0] = ch.x; cand[1] = ch.y; nc = 2;
+        while (nc < 4) {                                  // open the largest child that is not a leaf yet
+            int pick = -1; float pa = -1.f;
+            for (int k = 0; k < nc; ++k) {
+                const int id = cand[k];
+                if (id < n || bin_count(t, id) <= kLeafMax) continue;
+                const float a = box_area(t.lo[id], t.hi[id]);
+                if (a > pa) { pa = a; pick = k; }
+            }
+            if (pick < 0) break;
+            const int2 c2 = t.children[cand[pick] - n];
+            cand[pick] = c2.x; cand[nc++] = c2.y;
+        }
+    }
+    float lo[3][4], hi[3][4]; int link[4];
+    for (int k = 0; k < 4; ++k) {
+        if (k >= nc) {
+            // NaN planes: every slab compare fails, the empty slot can never be entered
+            for (int a = 0; a < 3; ++a) { lo[a][k] = __int_as_float(0x7fc00000); hi[a][k] = __int_as_float(0x7fc00000); }
+            link[k] = kEmptyLink;
+            continue;
+        }
+        const int id = cand[k];
+        const float4 l = t.lo[id], h = t.hi[id];
+        lo[0][k] = l.x; lo[1][k] = l.y; lo[2][k] = l.z; hi[0][k] = h.x; hi[1][k] = h.y; hi[2][k] = h.z;
+        const int c = __float_as_int(l.w);
+        if (c <= kLeafMax) {                              // leaf: triangles stored contiguously in leaf order
+            const int first = atomicAdd(&cnt->tris, c);
+            int st[kLeafMax], sp = 0, w = 0;
+            st[sp++] = id;
+            while (sp > 0) {
+                const int x = st[--sp];
+                if (x < n) leaf_order[first + w++] = int32_t(sorted_tri[x]);
+                else { const int2 c2 = t.children[x - n]; st[sp++] = c2.y; st[sp++] = c2.x; }
+            }
+            link[k] = ~((first << 2) | (c - 1));
+        } else {
+            const int s = atomicAdd(&cnt->nodes, 1);
+            next_tasks[atomicAdd(&cnt->next, 1)] = make_int2(id, s);
+            link[k] = s;
+        }
+    }
+    float4* out = nodes + (size_t)slot * kNodeStride;
+    for (int a = 0; a < 3; ++a) {
+        out[a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
+        out[3 + a] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
+    }
+    out[6] = make_float4(__int_as_float(link[0]), __int_as_float(link[1]), __int_as_float(link[2]), __int_as_float(link[3]));
+    out[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// leaf-ordered float triangles: (v0.xyz, e1.x) (e1.yz, e2.xy) (e2.z, max|e1|, max|e2|, original index)
+__global__ void leaf_triangles_kernel(const int32_t* __restrict__ leaf_order, const double* __restrict__ tri64, int n,
+                                      float4* __restrict__ tri32)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int tri = leaf_order[s];
+    const double* t = tri64 + (size_t)tri * kTri64Stride;
+    float f[9];
+    for (int k = 0; k < 9; ++k) f[k] = float(t[k]);
+    // max-norms rounded up: they scale the float cull's error bound
+    const float c1 = fmaxf(fabsf(f[3]), fmaxf(fabsf(f[4]), fabsf(f[5]))) * 1.0000002f;
+    const float c2 = fmaxf(fabsf(f[6]), fmaxf(fabsf(f[7]), fabsf(f[8]))) * 1.0000002f;
+    tri32[(size_t)s * 3 + 0] = make_float4(f[0], f[1], f[2], f[3]);
+    tri32[(size_t)s * 3 + 1] = make_float4(f[4], f[5], f[6], f[7]);
+    tri32[(size_t)s * 3 + 2] = make_float4(f[8], c1, c2, __int_as_float(tri));
 }
 
 // ---------------------------------------------------------------------------
@@ -214,26 +385,27 @@ __global__ void lbvh_refit_kernel(const uint32_t* __restrict__ sorted_tri, const
 // ---------------------------------------------------------------------------
 template <typename R> struct TriData { V3<R> v0, e1, e2; };
 
-template <typename R> __device__ __forceinline__ TriData<R> load_tri(const MeshView& m, int tri);
-template <> __device__ __forceinline__ TriData<double> load_tri<double>(const MeshView& m, int tri)
+// geometry of triangle `tri` (ORIGINAL index) in the precision of the instantiation
+template <typename R> __device__ __forceinline__ TriData<R> load_tri(const MeshView& m, int tri)
 {
     const double2* p = reinterpret_cast<const double2*>(m.tri64 + (size_t)tri * kTri64Stride);
     const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4);
-    return {{a.x, a.y, b.x}, {b.y, c.x, c.y}, {d.x, d.y, e.x}};
+    return {{R(a.x), R(a.y), R(b.x)}, {R(b.y), R(c.x), R(c.y)}, {R(d.x), R(d.y), R(e.x)}};
 }
-template <> __device__ __forceinline__ TriData<float> load_tri<float>(const MeshView& m, int tri)
+
+struct TriF { float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z, c1, c2; int id; };
+__device__ __forceinline__ TriF load_trif(const MeshView& m, int slot)
 {
-    const float4 a = __ldg(m.tri32 + (size_t)tri * 3), b = __ldg(m.tri32 + (size_t)tri * 3 + 1),
-                 c = __ldg(m.tri32 + (size_t)tri * 3 + 2);
-    return {{a.x, a.y, a.z}, {a.w, b.x, b.y}, {b.z, b.w, c.x}};
+    const float4 a = __ldg(m.tri32 + (size_t)slot * 3), b = __ldg(m.tri32 + (size_t)slot * 3 + 1),
+                 c = __ldg(m.tri32 + (size_t)slot * 3 + 2);
+    return {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, __float_as_int(c.w)};
 }
 
 // Moller-Trumbore with the acceptance rules of drtb.h.  `tmin`/`best` are the
 // closest hit so far (best < 0: an analytic primitive or nothing, which wins ties).
 template <typename R>
-__device__ __forceinline__ void tri_test(const MeshView& m, int tri, V3<R> o, V3<R> d, R& tmin, int& best)
+__device__ __forceinline__ void tri_test_exact(const TriData<R>& T, int tri, V3<R> o, V3<R> d, R& tmin, int& best)
 {
-    const TriData<R> T = load_tri<R>(m, tri);
     const V3<R> p = cross(d, T.e2);
     const R inv = Real<R>::rcp(dot(T.e1, p));          // det == 0 -> inf -> NaN below -> miss
     const V3<R> tv = {o.x - T.v0.x, o.y - T.v0.y, o.z - T.v0.z};
@@ -245,64 +417,162 @@ __device__ __forceinline__ void tri_test(const MeshView& m, int tri, V3<R> o, V3
     if (inside && (t < tmin || (t == tmin && best >= 0 && tri < best))) { tmin = t; best = tri; }
 }
 
+// The ray as the float stages see it.
+struct RayF {
+    float ox, oy, oz, dx, dy, dz;
+    float ix, iy, iz, oix, oiy, oiz;      // 1/d and o/d for the slab test  t = plane * (1/d) - o/d
+    float om, dm;                         // max-norms of o and d (error bound of the float cull)
+};
+
+template <typename R>
+__device__ __forceinline__ RayF make_rayf(V3<R> o, V3<R> d)
+{
+    RayF r;
+    r.ox = float(o.x); r.oy = float(o.y); r.oz = float(o.z);
+    r.dx = float(d.x); r.dy = float(d.y); r.dz = float(d.z);
+    // a zero component would give inf * 0 = NaN in the slab test; 1e-30 keeps it finite and conservative
+    const float sx = fabsf(r.dx) < 1e-30f ? copysignf(1e-30f, r.dx) : r.dx;
+    const float sy = fabsf(r.dy) < 1e-30f ? copysignf(1e-30f, r.dy) : r.dy;
+    const float sz = fabsf(r.dz) < 1e-30f ? copysignf(1e-30f, r.dz) : r.dz;
+    r.ix = 1.0f / sx; r.iy = 1.0f / sy; r.iz = 1.0f / sz;
+    r.oix = r.ox * r.ix; r.oiy = r.oy * r.iy; r.oiz = r.oz * r.iz;
+    r.om = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
+    r.dm = fmaxf(fabsf(r.dx), fmaxf(fabsf(r.dy), fabsf(r.dz)));
+    return r;
+}
+
+// Conservative float cull for the double instantiation: true = the exact test
+// CANNOT accept this triangle.  Every Moller-Trumbore numerator is evaluated in
+// float; its distance from the exact (double) value is bounded by
+//   K (|o|+|tv|) |d| |e2|  (u),  K (|o|+|tv|) |d| |e1|  (v),
+//   K (|o|+|tv|) |e1| |e2| (t),  K |d| |e1| |e2|        (det)      (max-norms)
+// with K = 128 * 2^-24, which covers the rounding of o, d, v0, e1, e2 to float
+// (cancellation in o - v0 included) and every float operation (worst case 72
+// units).  A triangle is culled only if some acceptance condition fails by
+// more than its bound; otherwise the exact double test decides.
+__device__ __forceinline__ bool tri_cull_f(const TriF& T, const RayF& r, float tmaxf)
+{
+    const float px = r.dy * T.e2z - r.dz * T.e2y, py = r.dz * T.e2x - r.dx * T.e2z, pz = r.dx * T.e2y - r.dy * T.e2x;
+    const float det = T.e1x * px + T.e1y * py + T.e1z * pz;
+    const float tx = r.ox - T.v0x, ty = r.oy - T.v0y, tz = r.oz - T.v0z;
+    const float up = tx * px + ty * py + tz * pz;
+    const float qx = ty * T.e1z - tz * T.e1y, qy = tz * T.e1x - tx * T.e1z, qz = tx * T.e1y - ty * T.e1x;
+    const float vp = r.dx * qx + r.dy * qy + r.dz * qz;
+    const float tp = T.e2x * qx + T.e2y * qy + T.e2z * qz;
+    const float K = 128.0f / 16777216.0f;
+    const float a = K * (r.om + fmaxf(fabsf(tx), fmaxf(fabsf(ty), fabsf(tz))));
+    const float ab = a * r.dm, c12 = T.c1 * T.c2;
+    const float Eu = ab * T.c2, Ev = ab * T.c1, Et = a * c12, Ed = K * r.dm * c12;
+    const float ad = fabsf(det);
+    const uint32_t s = __float_as_uint(det) & 0x80000000u;
+    const float us = __uint_as_float(__float_as_uint(up) ^ s), vs = __uint_as_float(__float_as_uint(vp) ^ s),
+                ts = __uint_as_float(__float_as_uint(tp) ^ s);
+    const bool out = us < -Eu || vs < -Ev || us + vs > ad + (Eu + Ev + Ed) || ts < -Et ||
+                     ts > fmaf(tmaxf, ad + Ed, Et) * 1.000001f;
+    return ad > Ed && out;
+}
+
 template <typename R> __device__ __forceinline__ float upper_float(R t);
 template <> __device__ __forceinline__ float upper_float<double>(double t) { return __double2float_ru(t); }
 template <> __device__ __forceinline__ float upper_float<float>(float t) { return t; }
 
-// Closest triangle along (o, d) that beats `tmin`; ordered traversal, near child first.
+// one triangle of a leaf (LEAF-order slot) against the running closest hit
+template <typename R>
+__device__ __forceinline__ void leaf_tri_test(const MeshView& m, int slot, const RayF& rf, V3<R> o, V3<R> d, R& tmin,
+                                              int& best);
+template <>
+__device__ __forceinline__ void leaf_tri_test<float>(const MeshView& m, int slot, const RayF&, V3<float> o, V3<float> d,
+                                                     float& tmin, int& best)
+{
+    const TriF T = load_trif(m, slot);
+    const TriData<float> D = {{T.v0x, T.v0y, T.v0z}, {T.e1x, T.e1y, T.e1z}, {T.e2x, T.e2y, T.e2z}};
+    tri_test_exact<float>(D, T.id, o, d, tmin, best);
+}
+template <>
+__device__ __forceinline__ void leaf_tri_test<double>(const MeshView& m, int slot, const RayF& rf, V3<double> o,
+                                                      V3<double> d, double& tmin, int& best)
+{
+    const TriF T = load_trif(m, slot);
+    if (tri_cull_f(T, rf, upper_float<double>(tmin))) return;
+    tri_test_exact<double>(load_tri<double>(m, T.id), T.id, o, d, tmin, best);
+}
+
+// test aid (DRTB_FLAG_NO_BVH) and stack-overflow fallback: the linear scan the BVH must agree with
+template <typename R>
+__device__ __forceinline__ void brute_closest(const MeshView& m, V3<R> o, V3<R> d, R& tmin, int& best, uint32_t& n_tests)
+{
+    for (int i = 0; i < m.n_tris; ++i) { ++n_tests; tri_test_exact<R>(load_tri<R>(m, i), i, o, d, tmin, best); }
+}
+
+// sort key of a slab hit: entry distance (non-negative float, so its bits order
+// like an int) with the child slot in the two low mantissa bits; clearing them
+// only lowers the distance, which keeps the pop-time cull conservative
+__device__ __forceinline__ int hit_key(float tn, float tf, float tmax, int j)
+{
+    return (tn <= tf && tn <= tmax) ? ((__float_as_int(tn) & ~3) | j) : 0x7fffffff;
+}
+__device__ __forceinline__ void cswap(int& a, int& b) { const int lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
+__device__ __forceinline__ int pick_link(float4 lk, int j)
+{
+    const float a = (j & 1) ? lk.y : lk.x, b = (j & 1) ? lk.w : lk.z;
+    return __float_as_int((j & 2) ? b : a);
+}
+
+// Closest triangle along (o, d) that beats `tmin`; ordered traversal, nearest child first.
 template <typename R>
 __device__ __forceinline__ void bvh_closest(const MeshView& m, V3<R> o, V3<R> d, R& tmin, int& best,
                                             uint32_t& n_nodes, uint32_t& n_tests)
 {
-    if (m.n_tris == 1) { ++n_tests; tri_test(m, 0, o, d, tmin, best); return; }
-    const float ox = float(o.x), oy = float(o.y), oz = float(o.z);
-    const float ix = 1.0f / float(d.x), iy = 1.0f / float(d.y), iz = 1.0f / float(d.z);
+    const RayF r = make_rayf(o, d);
     float tmax = upper_float<R>(tmin);
-    int stack[kBvhStack];
-    float stack_t[kBvhStack];
+    int2 stack[kBvhStack];                               // (key, link)
     int sp = 0, cur = 0;
+    bool overflow = false;
     for (;;) {
-        ++n_nodes;
-        const float4 n0 = __ldg(m.nodes + 4ll * cur), n1 = __ldg(m.nodes + 4ll * cur + 1),
-                     n2 = __ldg(m.nodes + 4ll * cur + 2), n3 = __ldg(m.nodes + 4ll * cur + 3);
-        // child 0: lo = n0.xyz, hi = (n0.w, n1.x, n1.y); child 1: lo = (n1.z, n1.w, n2.x), hi = n2.yzw
-        float a, b;
-        a = (n0.x - ox) * ix; b = (n0.w - ox) * ix; float tn0 = fminf(a, b), tf0 = fmaxf(a, b);
-        a = (n0.y - oy) * iy; b = (n1.x - oy) * iy; tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
-        a = (n0.z - oz) * iz; b = (n1.y - oz) * iz; tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
-        a = (n1.z - ox) * ix; b = (n2.y - ox) * ix; float tn1 = fminf(a, b), tf1 = fmaxf(a, b);
-        a = (n1.w - oy) * iy; b = (n2.z - oy) * iy; tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
-        a = (n2.x - oz) * iz; b = (n2.w - oz) * iz; tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
-        // conservative: widen [tn, tf] by a few ulp before comparing
-        tn0 = fmaxf(tn0 - fabsf(tn0) * 4e-7f, 0.0f); tn1 = fmaxf(tn1 - fabsf(tn1) * 4e-7f, 0.0f);
-        tf0 += fabsf(tf0) * 4e-7f; tf1 += fabsf(tf1) * 4e-7f;
-        bool h0 = tn0 <= tf0 && tn0 <= tmax, h1 = tn1 <= tf1 && tn1 <= tmax;
-        const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-        if (h0 && c0 < 0) { ++n_tests; tri_test(m, ~c0, o, d, tmin, best); h0 = false; }
-        if (h1 && c1 < 0) { ++n_tests; tri_test(m, ~c1, o, d, tmin, best); h1 = false; }
-        tmax = upper_float<R>(tmin);
-        if (h0 && h1) {
-            const bool zero_first = tn0 <= tn1;
-            if (sp < kBvhStack) { stack[sp] = zero_first ? c1 : c0; stack_t[sp] = zero_first ? tn1 : tn0; ++sp; }
-            cur = zero_first ? c0 : c1;
-            continue;
+        if (cur >= 0) {                                  // wide node
+            ++n_nodes;
+            const float4* nd = m.nodes + (size_t)cur * kNodeStride;
+            const float4 lx = __ldg(nd), ly = __ldg(nd + 1), lz = __ldg(nd + 2), hx = __ldg(nd + 3), hy = __ldg(nd + 4),
+                         hz = __ldg(nd + 5), lk = __ldg(nd + 6);
+            int key[4];
+#define DRTB_SLAB(J, C)                                                                                   \
+            {                                                                                             \
+                const float ax = fmaf(lx.C, r.ix, -r.oix), bx = fmaf(hx.C, r.ix, -r.oix);                 \
+                const float ay = fmaf(ly.C, r.iy, -r.oiy), by = fmaf(hy.C, r.iy, -r.oiy);                 \
+                const float az = fmaf(lz.C, r.iz, -r.oiz), bz = fmaf(hz.C, r.iz, -r.oiz);                 \
+                float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));                     \
+                float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));                     \
+                tn = fmaxf(tn - fabsf(tn) * 4e-7f, 0.0f);           /* conservative: widen by a few ulp */ \
+                tf += fabsf(tf) * 4e-7f;                                                                  \
+                key[J] = hit_key(tn, tf, tmax, J);                                                        \
+            }
+            DRTB_SLAB(0, x) DRTB_SLAB(1, y) DRTB_SLAB(2, z) DRTB_SLAB(3, w)
+#undef DRTB_SLAB
+            cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+            if (key[0] == 0x7fffffff) cur = kEmptyLink;  // nothing hit: pop
+            else {
+#pragma unroll
+                for (int k = 3; k >= 1; --k) {           // far ones first, so the nearest is popped first
+                    if (key[k] != 0x7fffffff) {
+                        if (sp < kBvhStack) stack[sp++] = make_int2(key[k], pick_link(lk, key[k] & 3)); else overflow = true;
+                    }
+                }
+                cur = pick_link(lk, key[0] & 3);
+                continue;
+            }
+        } else {                                         // leaf: ~((first << 2) | (count - 1))
+            const int code = ~cur, first = code >> 2, count = (code & 3) + 1;
+            for (int k = 0; k < count; ++k) { ++n_tests; leaf_tri_test<R>(m, first + k, r, o, d, tmin, best); }
+            tmax = upper_float<R>(tmin);
         }
-        if (h0) { cur = c0; continue; }
-        if (h1) { cur = c1; continue; }
         bool found = false;
         while (sp > 0) {
-            --sp;
-            if (stack_t[sp] <= tmax) { cur = stack[sp]; found = true; break; }
+            const int2 e = stack[--sp];
+            if (__int_as_float(e.x & ~3) <= tmax) { cur = e.y; found = true; break; }
         }
         if (!found) break;
     }
-}
-
-// test aid (DRTB_FLAG_NO_BVH): the linear scan the BVH must agree with
-template <typename R>
-__device__ __forceinline__ void brute_closest(const MeshView& m, V3<R> o, V3<R> d, R& tmin, int& best, uint32_t& n_tests)
-{
-    for (int i = 0; i < m.n_tris; ++i) { ++n_tests; tri_test(m, i, o, d, tmin, best); }
+    if (overflow) brute_closest<R>(m, o, d, tmin, best, n_tests);   // never seen on a PLOC tree; correctness first
 }
 
 } // namespace drtb

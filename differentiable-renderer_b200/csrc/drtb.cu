@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -19,6 +20,7 @@
 
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "path.cuh"
 
@@ -70,9 +72,12 @@ struct JacSink {
 #ifndef DRTB_MIN_BLOCKS
 #define DRTB_MIN_BLOCKS 1
 #endif
+#ifndef DRTB_MESH_MIN_BLOCKS
+#define DRTB_MESH_MIN_BLOCKS DRTB_MIN_BLOCKS
+#endif
 //   MESH  : a triangle mesh + BVH is attached (ids are 32-bit, parameters in global memory)
 template <typename R, bool SMALLP, bool QUEUE, bool MESH>
-__global__ void __launch_bounds__(kBlock, DRTB_MIN_BLOCKS)
+__global__ void __launch_bounds__(kBlock, MESH ? DRTB_MESH_MIN_BLOCKS : DRTB_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ RenderArgs a)
 {
     using Id = typename PrimId<MESH>::type;
@@ -250,6 +255,12 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     }
 }
 
+__global__ void iota_kernel(int* __restrict__ v, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+
 // grad[j] = sum_b partial[b][j], b ascending inside each thread, then a fixed tree.
 __global__ void __launch_bounds__(256)
 reduce_grad_kernel(const double* __restrict__ partial, int n_blocks, int P3, double* __restrict__ grad)
@@ -353,6 +364,7 @@ struct drtb_ctx {
     int32_t* d_tri_color = nullptr;
     int32_t* d_tri_emis = nullptr;
     double mesh_build_ms = 0.0;
+    int mesh_nodes = 0;
 };
 
 namespace {
@@ -752,7 +764,7 @@ int drtb_mesh_upload(drtb_ctx* ctx, const drtb_mesh* mesh)
     if (!mesh || mesh->n_triangles == 0) return DRTB_OK;
     const int64_t n = mesh->n_triangles, nv = mesh->n_vertices;
     if (n < 0 || nv <= 0 || !mesh->vertices || !mesh->indices) return fail(ctx, DRTB_ERR_INVALID, "mesh has NULL arrays or bad counts");
-    if (n > (int64_t(1) << 30)) return fail(ctx, DRTB_ERR_UNSUPPORTED, "more than 2^30 triangles");
+    if (n > (int64_t(1) << 28)) return fail(ctx, DRTB_ERR_UNSUPPORTED, "more than 2^28 triangles");
     const int P = int(ctx->params.size() / 3);
     for (int64_t i = 0; i < 3 * n; ++i)
         if (mesh->indices[i] < 0 || mesh->indices[i] >= nv) return fail(ctx, DRTB_ERR_INVALID, "mesh vertex index out of range");
@@ -761,33 +773,40 @@ int drtb_mesh_upload(drtb_ctx* ctx, const drtb_mesh* mesh)
         if (mesh->emission && (mesh->emission[i] < -1 || mesh->emission[i] >= P)) return fail(ctx, DRTB_ERR_INVALID, "triangle emission parameter index out of range");
     }
     // ---- device buffers: persistent mesh data + build temporaries
+    const bool use_lbvh = [] { const char* e = std::getenv("DRTB_BVH"); return e && std::string(e) == "lbvh"; }();
     double* d_vert = nullptr; int32_t* d_idx = nullptr;
-    float *d_lo = nullptr, *d_hi = nullptr; uint32_t* d_bounds = nullptr;
-    uint64_t *d_keys = nullptr, *d_keys2 = nullptr; uint32_t *d_vals = nullptr, *d_vals2 = nullptr;
-    int2* d_children = nullptr; int *d_pnode = nullptr, *d_pleaf = nullptr, *d_arrive = nullptr; void* d_tmp = nullptr;
+    float4 *d_lo = nullptr, *d_hi = nullptr, *d_blo = nullptr, *d_bhi = nullptr, *d_wide = nullptr; uint32_t* d_bounds = nullptr;
+    uint64_t *d_keys = nullptr, *d_keys2 = nullptr, *d_flags = nullptr, *d_scan = nullptr;
+    uint32_t *d_vals = nullptr, *d_vals2 = nullptr;
+    int2 *d_children = nullptr, *d_tasks = nullptr, *d_tasks2 = nullptr;
+    int *d_parent = nullptr, *d_arrive = nullptr, *d_clusters = nullptr, *d_clusters2 = nullptr, *d_nearest = nullptr;
+    int32_t* d_leaf_order = nullptr; CollapseCounters* d_cnt = nullptr; void *d_tmp = nullptr, *d_tmp2 = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_vert); cudaFree(d_idx); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_bounds); cudaFree(d_keys);
-        cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_children); cudaFree(d_pnode);
-        cudaFree(d_pleaf); cudaFree(d_arrive); cudaFree(d_tmp);
+        cudaFree(d_vert); cudaFree(d_idx); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_blo); cudaFree(d_bhi); cudaFree(d_wide);
+        cudaFree(d_bounds); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_flags); cudaFree(d_scan); cudaFree(d_vals);
+        cudaFree(d_vals2); cudaFree(d_children); cudaFree(d_tasks); cudaFree(d_tasks2); cudaFree(d_parent); cudaFree(d_arrive);
+        cudaFree(d_clusters); cudaFree(d_clusters2); cudaFree(d_nearest); cudaFree(d_leaf_order); cudaFree(d_cnt);
+        cudaFree(d_tmp); cudaFree(d_tmp2);
     };
 #define CKM(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); free_mesh(ctx); return fail(ctx, e_ == cudaErrorMemoryAllocation ? DRTB_ERR_NOMEM : DRTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
     cudaStream_t st = ctx->stream;
-    const size_t nn = size_t(n), nodes = nn > 1 ? nn - 1 : 1;
+    const size_t nn = size_t(n), n_int = nn > 1 ? nn - 1 : 1;
     CKM(cudaMalloc((void**)&ctx->d_tri64, nn * kTri64Stride * sizeof(double)));
     CKM(cudaMalloc((void**)&ctx->d_tri32, nn * kTri32Stride * sizeof(float4)));
     CKM(cudaMalloc((void**)&ctx->d_tri_color, nn * sizeof(int32_t)));
     CKM(cudaMalloc((void**)&ctx->d_tri_emis, nn * sizeof(int32_t)));
-    CKM(cudaMalloc((void**)&ctx->d_nodes, nodes * 4 * sizeof(float4)));
     CKM(cudaMalloc((void**)&d_vert, size_t(nv) * 3 * sizeof(double)));
     CKM(cudaMalloc((void**)&d_idx, nn * 3 * sizeof(int32_t)));
-    CKM(cudaMalloc((void**)&d_lo, nn * 3 * sizeof(float)));
-    CKM(cudaMalloc((void**)&d_hi, nn * 3 * sizeof(float)));
+    CKM(cudaMalloc((void**)&d_lo, nn * sizeof(float4)));      CKM(cudaMalloc((void**)&d_hi, nn * sizeof(float4)));
+    CKM(cudaMalloc((void**)&d_blo, 2 * nn * sizeof(float4))); CKM(cudaMalloc((void**)&d_bhi, 2 * nn * sizeof(float4)));
+    CKM(cudaMalloc((void**)&d_wide, nn * kNodeStride * sizeof(float4)));      // a wide node has >= 2 children: < n nodes
     CKM(cudaMalloc((void**)&d_bounds, 6 * sizeof(uint32_t)));
     CKM(cudaMalloc((void**)&d_keys, nn * sizeof(uint64_t)));  CKM(cudaMalloc((void**)&d_keys2, nn * sizeof(uint64_t)));
     CKM(cudaMalloc((void**)&d_vals, nn * sizeof(uint32_t)));  CKM(cudaMalloc((void**)&d_vals2, nn * sizeof(uint32_t)));
-    CKM(cudaMalloc((void**)&d_children, nodes * sizeof(int2)));
-    CKM(cudaMalloc((void**)&d_pnode, nodes * sizeof(int)));   CKM(cudaMalloc((void**)&d_pleaf, nn * sizeof(int)));
-    CKM(cudaMalloc((void**)&d_arrive, nodes * sizeof(int)));
+    CKM(cudaMalloc((void**)&d_children, n_int * sizeof(int2)));
+    CKM(cudaMalloc((void**)&d_tasks, nn * sizeof(int2)));     CKM(cudaMalloc((void**)&d_tasks2, nn * sizeof(int2)));
+    CKM(cudaMalloc((void**)&d_leaf_order, nn * sizeof(int32_t)));
+    CKM(cudaMalloc((void**)&d_cnt, sizeof(CollapseCounters)));
     CKM(cudaMemcpyAsync(d_vert, mesh->vertices, size_t(nv) * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     CKM(cudaMemcpyAsync(d_idx, mesh->indices, nn * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (mesh->color) CKM(cudaMemcpyAsync(ctx->d_tri_color, mesh->color, nn * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -797,31 +816,91 @@ int drtb_mesh_upload(drtb_ctx* ctx, const drtb_mesh* mesh)
     // scene bounds start at (+max, -max) in the ordered-uint encoding
     const uint32_t init_bounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     CKM(cudaMemcpyAsync(d_bounds, init_bounds, sizeof init_bounds, cudaMemcpyHostToDevice, st));
-    CKM(cudaMemsetAsync(d_arrive, 0, nodes * sizeof(int), st));
     CKM(cudaEventRecord(ctx->ev0, st));
     const int T = 256, G = int((nn + T - 1) / T);
-    mesh_prepare_kernel<<<G, T, 0, st>>>(d_vert, d_idx, int(n), ctx->d_tri64, ctx->d_tri32, d_lo, d_hi, d_bounds);
+    const BinTree bt{d_blo, d_bhi, d_children};
+    // 1. bounds, Morton codes, sort
+    mesh_prepare_kernel<<<G, T, 0, st>>>(d_vert, d_idx, int(n), ctx->d_tri64, d_lo, d_hi, d_bounds);
+    CKM(cudaGetLastError());
+    mesh_morton_kernel<<<G, T, 0, st>>>(d_lo, d_hi, d_bounds, int(n), d_keys, d_vals);
+    CKM(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CKM(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, int(n), 0, 63, st));
+    CKM(cudaMalloc(&d_tmp, tmp_bytes));
+    CKM(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, int(n), 0, 63, st));
+    bin_leaves_kernel<<<G, T, 0, st>>>(d_vals2, d_lo, d_hi, d_bounds, int(n), bt);
+    CKM(cudaGetLastError());
+    ctx->launches += 5;                                      // prepare, morton, sort (>= 2), leaves
+    // 2. binary tree
+    int root = 0;
+    if (n > 1 && use_lbvh) {
+        CKM(cudaMalloc((void**)&d_parent, 2 * nn * sizeof(int)));
+        CKM(cudaMalloc((void**)&d_arrive, n_int * sizeof(int)));
+        CKM(cudaMemsetAsync(d_arrive, 0, n_int * sizeof(int), st));
+        lbvh_hierarchy_kernel<<<G, T, 0, st>>>(d_keys2, int(n), d_children, d_parent);
+        CKM(cudaGetLastError());
+        lbvh_refit_kernel<<<G, T, 0, st>>>(int(n), d_parent, d_arrive, bt);
+        CKM(cudaGetLastError());
+        ctx->launches += 2;
+        root = int(n);                                       // Karras: internal node 0 is the root
+    } else if (n > 1) {
+        CKM(cudaMalloc((void**)&d_clusters, nn * sizeof(int)));  CKM(cudaMalloc((void**)&d_clusters2, nn * sizeof(int)));
+        CKM(cudaMalloc((void**)&d_nearest, nn * sizeof(int)));
+        CKM(cudaMalloc((void**)&d_flags, (nn + 1) * sizeof(uint64_t)));
+        CKM(cudaMalloc((void**)&d_scan, (nn + 1) * sizeof(uint64_t)));
+        size_t scan_bytes = 0;
+        CKM(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flags, d_scan, int(n) + 1, st));
+        CKM(cudaMalloc(&d_tmp2, scan_bytes));
+        iota_kernel<<<G, T, 0, st>>>(d_clusters, int(n));
+        CKM(cudaGetLastError());
+        int m = int(n), made = 0;
+        while (m > 1) {
+            const int g = (m + T - 1) / T;
+            ploc_nearest_kernel<<<g, 256, 0, st>>>(d_clusters, m, bt, d_nearest);
+            ploc_flag_kernel<<<g, T, 0, st>>>(d_nearest, m, d_flags);
+            CKM(cudaMemsetAsync(d_flags + m, 0, sizeof(uint64_t), st));
+            CKM(cub::DeviceScan::ExclusiveSum(d_tmp2, scan_bytes, d_flags, d_scan, m + 1, st));   // scan[m] = totals
+            ploc_merge_kernel<<<g, T, 0, st>>>(d_clusters, d_nearest, d_flags, d_scan, m, int(n), made, bt, d_clusters2);
+            CKM(cudaGetLastError());
+            uint64_t tot = 0;
+            CKM(cudaMemcpyAsync(&tot, d_scan + m, sizeof tot, cudaMemcpyDeviceToHost, st));
+            CKM(cudaStreamSynchronize(st));
+            const int kept = int(tot & 0xffffffffu), merged = int(tot >> 32);
+            if (merged < 1 || kept != m - merged) { cleanup(); free_mesh(ctx); return fail(ctx, DRTB_ERR_CUDA, "PLOC iteration made no progress"); }
+            made += merged; m = kept;
+            std::swap(d_clusters, d_clusters2);
+            ctx->launches += 4;
+        }
+        root = int(n) + made - 1;                            // the last node created
+    }
+    // 3. collapse to the 4-wide BVH, one level per launch
+    const CollapseCounters init_cnt{1, 0, 0, 0};
+    const int2 root_task = make_int2(root, 0);
+    CKM(cudaMemcpyAsync(d_cnt, &init_cnt, sizeof init_cnt, cudaMemcpyHostToDevice, st));
+    CKM(cudaMemcpyAsync(d_tasks, &root_task, sizeof root_task, cudaMemcpyHostToDevice, st));
+    CollapseCounters h_cnt = init_cnt;
+    for (int n_tasks = 1; n_tasks > 0;) {
+        collapse_kernel<<<(n_tasks + T - 1) / T, T, 0, st>>>(d_tasks, n_tasks, int(n), bt, d_vals2, d_wide, d_leaf_order, d_cnt, d_tasks2);
+        CKM(cudaGetLastError());
+        CKM(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+        CKM(cudaStreamSynchronize(st));
+        n_tasks = h_cnt.next;
+        CKM(cudaMemsetAsync(&d_cnt->next, 0, sizeof(int), st));
+        std::swap(d_tasks, d_tasks2);
+        ctx->launches++;
+    }
+    if (h_cnt.tris != int(n)) { cleanup(); free_mesh(ctx); return fail(ctx, DRTB_ERR_CUDA, "BVH collapse lost triangles"); }
+    CKM(cudaMalloc((void**)&ctx->d_nodes, size_t(h_cnt.nodes) * kNodeStride * sizeof(float4)));
+    CKM(cudaMemcpyAsync(ctx->d_nodes, d_wide, size_t(h_cnt.nodes) * kNodeStride * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    leaf_triangles_kernel<<<G, T, 0, st>>>(d_leaf_order, ctx->d_tri64, int(n), ctx->d_tri32);
     CKM(cudaGetLastError());
     ctx->launches++;
-    if (n > 1) {
-        mesh_morton_kernel<<<G, T, 0, st>>>(d_lo, d_hi, d_bounds, int(n), d_keys, d_vals);
-        CKM(cudaGetLastError());
-        size_t tmp_bytes = 0;
-        CKM(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, int(n), 0, 63, st));
-        CKM(cudaMalloc(&d_tmp, tmp_bytes));
-        CKM(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, int(n), 0, 63, st));
-        lbvh_hierarchy_kernel<<<G, T, 0, st>>>(d_keys2, int(n), d_children, d_pnode, d_pleaf);
-        CKM(cudaGetLastError());
-        lbvh_refit_kernel<<<G, T, 0, st>>>(d_vals2, d_lo, d_hi, d_children, d_pnode, d_pleaf, d_bounds, int(n), d_arrive,
-                                           reinterpret_cast<float*>(ctx->d_nodes));
-        CKM(cudaGetLastError());
-        ctx->launches += 5;                                  // morton, sort (>= 2), hierarchy, refit
-    }
     CKM(cudaEventRecord(ctx->ev1, st));
     CKM(cudaStreamSynchronize(st));
     float ms = 0.f;
     CKM(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->mesh_build_ms = ms;
+    ctx->mesh_nodes = h_cnt.nodes;
 #undef CKM
     cleanup();
     ctx->n_tris = n;

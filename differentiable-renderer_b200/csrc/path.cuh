@@ -176,7 +176,7 @@ __device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<
 // instead of one per plane.  Acceptance is the reference's: t > 0, strictly
 // closer than the best so far, the lower scene index winning exact ties.
 // The first kFast planes and kFast spheres are tested by straight-line code
-// entered through a jump table (their operands are immediate constant-bank
+// entered at the first live slot (their operands are immediate constant-bank
 // addresses); larger scenes continue in rolled loops with a warp-uniform slot.
 // ---------------------------------------------------------------------------
 template <typename R>
@@ -184,29 +184,42 @@ __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R>
 {
     R bn = Real<R>::inf(), bd = R(1);                  // best t = bn / bd
     int best = -1;
-    switch (kFast - sc.n_fast_planes) {
-        case 0: plane_test(sc, 0, o, d, bn, bd, best); [[fallthrough]];
-        case 1: plane_test(sc, 1, o, d, bn, bd, best); [[fallthrough]];
-        case 2: plane_test(sc, 2, o, d, bn, bd, best); [[fallthrough]];
-        case 3: plane_test(sc, 3, o, d, bn, bd, best); [[fallthrough]];
-        case 4: plane_test(sc, 4, o, d, bn, bd, best); [[fallthrough]];
-        case 5: plane_test(sc, 5, o, d, bn, bd, best); [[fallthrough]];
-        case 6: plane_test(sc, 6, o, d, bn, bd, best); [[fallthrough]];
-        case 7: plane_test(sc, 7, o, d, bn, bd, best); [[fallthrough]];
-        default: break;
+    // Entry into the straight-line tests by a 3-level compare tree on the (warp-uniform)
+    // first live slot: ~6 instructions, where the compiler's jump table for the
+    // equivalent switch cost ~20 per entry.
+#define DRTB_ENTER(first, L)                                                                   \
+    if (first >= 4) { if (first >= 6) { if (first >= 7) { if (first == 7) goto L##7; goto L##8; } goto L##6; } \
+                      if (first == 5) goto L##5; goto L##4; }                                   \
+    if (first >= 2) { if (first == 3) goto L##3; goto L##2; }                                   \
+    if (first == 1) goto L##1;
+    {
+        const int first = kFast - sc.n_fast_planes;
+        DRTB_ENTER(first, P)
+        plane_test(sc, 0, o, d, bn, bd, best);
+    P1: plane_test(sc, 1, o, d, bn, bd, best);
+    P2: plane_test(sc, 2, o, d, bn, bd, best);
+    P3: plane_test(sc, 3, o, d, bn, bd, best);
+    P4: plane_test(sc, 4, o, d, bn, bd, best);
+    P5: plane_test(sc, 5, o, d, bn, bd, best);
+    P6: plane_test(sc, 6, o, d, bn, bd, best);
+    P7: plane_test(sc, 7, o, d, bn, bd, best);
+    P8:;
     }
     for (int i = 0; i < sc.n_over_planes; ++i) plane_test(sc, 2 * kFast + i, o, d, bn, bd, best);
-    switch (kFast - sc.n_fast_spheres) {
-        case 0: sphere_test(sc, kFast + 0, o, d, bn, bd, best); [[fallthrough]];
-        case 1: sphere_test(sc, kFast + 1, o, d, bn, bd, best); [[fallthrough]];
-        case 2: sphere_test(sc, kFast + 2, o, d, bn, bd, best); [[fallthrough]];
-        case 3: sphere_test(sc, kFast + 3, o, d, bn, bd, best); [[fallthrough]];
-        case 4: sphere_test(sc, kFast + 4, o, d, bn, bd, best); [[fallthrough]];
-        case 5: sphere_test(sc, kFast + 5, o, d, bn, bd, best); [[fallthrough]];
-        case 6: sphere_test(sc, kFast + 6, o, d, bn, bd, best); [[fallthrough]];
-        case 7: sphere_test(sc, kFast + 7, o, d, bn, bd, best); [[fallthrough]];
-        default: break;
+    {
+        const int first = kFast - sc.n_fast_spheres;
+        DRTB_ENTER(first, S)
+        sphere_test(sc, kFast + 0, o, d, bn, bd, best);
+    S1: sphere_test(sc, kFast + 1, o, d, bn, bd, best);
+    S2: sphere_test(sc, kFast + 2, o, d, bn, bd, best);
+    S3: sphere_test(sc, kFast + 3, o, d, bn, bd, best);
+    S4: sphere_test(sc, kFast + 4, o, d, bn, bd, best);
+    S5: sphere_test(sc, kFast + 5, o, d, bn, bd, best);
+    S6: sphere_test(sc, kFast + 6, o, d, bn, bd, best);
+    S7: sphere_test(sc, kFast + 7, o, d, bn, bd, best);
+    S8:;
     }
+#undef DRTB_ENTER
     for (int i = 0; i < sc.n_over_spheres; ++i)
         sphere_test(sc, 2 * kFast + sc.n_over_planes + i, o, d, bn, bd, best);
     tmin = Real<R>::div(bn, bd);

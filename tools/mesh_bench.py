@@ -49,7 +49,7 @@ with drt.Context(0) as ctx:
                      "bvh_nodes_per_segment": best.bvh_nodes / best.segments, "tri_tests_per_segment": best.tri_tests / best.segments,
                      "algorithmic_bytes_per_segment": bytes_per_seg, "algorithmic_GBps": gbs, "hbm_peak_GBps": hbm,
                      "frac_of_hbm_peak": gbs / hbm,
-                     "actual_bytes_per_segment_est": best.bvh_nodes / best.segments * 64 + best.tri_tests / best.segments * (80 if name == "f64" else 48),
+                     "actual_bytes_per_segment_est": best.bvh_nodes / best.segments * 128 + best.tri_tests / best.segments * 48,
                      "image_mean": float(img.mean()), "nonzero_triangle_grads": int((abs(grad[scene.mesh.param_base:]).sum(1) > 0).sum())}
         print(name, json.dumps(res[name]))
 print(json.dumps({k: v for k, v in res.items() if k not in ("f64", "f32")}))
