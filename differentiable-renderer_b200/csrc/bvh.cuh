@@ -34,7 +34,10 @@
 namespace drtb {
 
 constexpr int kBvhStack   = 64;           // traversal stack entries per lane (overflow falls back to a linear scan)
-constexpr int kLeafMax    = 4;            // triangles per leaf (2 bits of the leaf link)
+#ifndef DRTB_LEAF_MAX
+#define DRTB_LEAF_MAX 4
+#endif
+constexpr int kLeafMax    = DRTB_LEAF_MAX; // triangles per leaf, <= 4 (2 bits of the leaf link)
 constexpr int kPlocRadius = 16;           // PLOC neighbour search radius along the Morton order
 constexpr int kTri64Stride = 10;          // doubles per triangle: v0, e1, e2, pad (16-byte aligned rows)
 constexpr int kTri32Stride = 3;           // float4 per triangle
@@ -527,50 +530,69 @@ __device__ __forceinline__ void bvh_closest(const MeshView& m, V3<R> o, V3<R> d,
     float tmax = upper_float<R>(tmin);
     int2 stack[kBvhStack];                               // (key, link)
     int sp = 0, cur = 0;
-    bool overflow = false;
+    bool overflow = false, alive = true;
+    // Warp-synchronous stepping with a majority vote.  Left to the compiler's own
+    // reconvergence this loop ran with 4.3 of 32 lanes active; converged but executing
+    // the node code and the leaf code in every iteration, the leaf code still ran at
+    // 2.9 of 32 (profiles/r01_mesh_f64_v2_bvh4_summary.txt, ..._v3_sync_summary.txt).
+    // So each iteration issues ONE kind of step -- the one more lanes are waiting for --
+    // and the minority keeps its state: lanes that reached a leaf wait until the leaf
+    // lanes outnumber the lanes still descending, then all leaves are tested together.
+    const unsigned live = __activemask();
+#ifndef DRTB_LEAF_WEIGHT
+#define DRTB_LEAF_WEIGHT 1
+#endif
     for (;;) {
-        if (cur >= 0) {                                  // wide node
-            ++n_nodes;
-            const float4* nd = m.nodes + (size_t)cur * kNodeStride;
-            const float4 lx = __ldg(nd), ly = __ldg(nd + 1), lz = __ldg(nd + 2), hx = __ldg(nd + 3), hy = __ldg(nd + 4),
-                         hz = __ldg(nd + 5), lk = __ldg(nd + 6);
-            int key[4];
+        const bool at_node = alive && cur >= 0, at_leaf = alive && cur < 0;
+        const unsigned node_m = __ballot_sync(live, at_node), leaf_m = __ballot_sync(live, at_leaf);
+        if ((node_m | leaf_m) == 0u) break;
+        const bool leaf_step = node_m == 0u || DRTB_LEAF_WEIGHT * __popc(leaf_m) >= __popc(node_m);
+        bool pop = false;
+        if (!leaf_step) {
+            if (at_node) {                               // wide node
+                ++n_nodes;
+                const float4* nd = m.nodes + (size_t)cur * kNodeStride;
+                const float4 lx = __ldg(nd), ly = __ldg(nd + 1), lz = __ldg(nd + 2), hx = __ldg(nd + 3), hy = __ldg(nd + 4),
+                             hz = __ldg(nd + 5), lk = __ldg(nd + 6);
+                int key[4];
 #define DRTB_SLAB(J, C)                                                                                   \
-            {                                                                                             \
-                const float ax = fmaf(lx.C, r.ix, -r.oix), bx = fmaf(hx.C, r.ix, -r.oix);                 \
-                const float ay = fmaf(ly.C, r.iy, -r.oiy), by = fmaf(hy.C, r.iy, -r.oiy);                 \
-                const float az = fmaf(lz.C, r.iz, -r.oiz), bz = fmaf(hz.C, r.iz, -r.oiz);                 \
-                float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));                     \
-                float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));                     \
-                tn = fmaxf(tn - fabsf(tn) * 4e-7f, 0.0f);           /* conservative: widen by a few ulp */ \
-                tf += fabsf(tf) * 4e-7f;                                                                  \
-                key[J] = hit_key(tn, tf, tmax, J);                                                        \
-            }
-            DRTB_SLAB(0, x) DRTB_SLAB(1, y) DRTB_SLAB(2, z) DRTB_SLAB(3, w)
-#undef DRTB_SLAB
-            cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
-            if (key[0] == 0x7fffffff) cur = kEmptyLink;  // nothing hit: pop
-            else {
-#pragma unroll
-                for (int k = 3; k >= 1; --k) {           // far ones first, so the nearest is popped first
-                    if (key[k] != 0x7fffffff) {
-                        if (sp < kBvhStack) stack[sp++] = make_int2(key[k], pick_link(lk, key[k] & 3)); else overflow = true;
-                    }
+                {                                                                                         \
+                    const float ax = fmaf(lx.C, r.ix, -r.oix), bx = fmaf(hx.C, r.ix, -r.oix);             \
+                    const float ay = fmaf(ly.C, r.iy, -r.oiy), by = fmaf(hy.C, r.iy, -r.oiy);             \
+                    const float az = fmaf(lz.C, r.iz, -r.oiz), bz = fmaf(hz.C, r.iz, -r.oiz);             \
+                    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));                 \
+                    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));                 \
+                    tn = fmaxf(tn - fabsf(tn) * 4e-7f, 0.0f);       /* conservative: widen by a few ulp */ \
+                    tf += fabsf(tf) * 4e-7f;                                                              \
+                    key[J] = hit_key(tn, tf, tmax, J);                                                    \
                 }
+                DRTB_SLAB(0, x) DRTB_SLAB(1, y) DRTB_SLAB(2, z) DRTB_SLAB(3, w)
+#undef DRTB_SLAB
+                cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+                // far ones first, so the nearest is popped first; the stores are predicated, not branched
+#pragma unroll
+                for (int k = 3; k >= 1; --k) {
+                    const bool hit = key[k] != 0x7fffffff;
+                    if (hit && sp < kBvhStack) stack[sp] = make_int2(key[k], pick_link(lk, key[k] & 3));
+                    overflow |= hit && sp >= kBvhStack;
+                    sp += (hit && sp < kBvhStack) ? 1 : 0;
+                }
+                pop = key[0] == 0x7fffffff;              // nothing hit
                 cur = pick_link(lk, key[0] & 3);
-                continue;
             }
-        } else {                                         // leaf: ~((first << 2) | (count - 1))
+        } else if (at_leaf) {                            // leaf: ~((first << 2) | (count - 1))
             const int code = ~cur, first = code >> 2, count = (code & 3) + 1;
             for (int k = 0; k < count; ++k) { ++n_tests; leaf_tri_test<R>(m, first + k, r, o, d, tmin, best); }
             tmax = upper_float<R>(tmin);
+            pop = true;
         }
-        bool found = false;
-        while (sp > 0) {
-            const int2 e = stack[--sp];
-            if (__int_as_float(e.x & ~3) <= tmax) { cur = e.y; found = true; break; }
+        if (pop) {
+            alive = false;
+            while (sp > 0) {
+                const int2 e = stack[--sp];
+                if (__int_as_float(e.x & ~3) <= tmax) { cur = e.y; alive = true; break; }
+            }
         }
-        if (!found) break;
     }
     if (overflow) brute_closest<R>(m, o, d, tmin, best, n_tests);   // never seen on a PLOC tree; correctness first
 }

@@ -350,12 +350,20 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
     using Id = typename PrimId<MESH>::type;
     int n = 0;
     lit = false;
+#ifndef DRTB_SYNC_DEPTH
+#define DRTB_SYNC_DEPTH 0                                   // 1: re-converge the analytic kernels per segment as well
+#endif
+    constexpr bool kSync = MESH || DRTB_SYNC_DEPTH;         // mesh kernels: the lanes must enter the BVH traversal together
+    unsigned live = kSync ? __activemask() : 0u;
+    bool alive = true;
     for (int depth = 0;; ++depth) {
+        if constexpr (kSync) live = __ballot_sync(live, alive);
+        if (!alive) break;
         if (depth >= min_bounces) {                         // Russian roulette, :128-130
             double u = Real<double>::uniform(stream_draw_base(base, slot++));
-            if (u < absorb) break;
+            if (u < absorb) { alive = false; continue; }
         }
-        if (n >= max_depth) { ++cnt.truncated; break; }
+        if (n >= max_depth) { ++cnt.truncated; alive = false; continue; }
         R t;
         int k = closest_hit(sc, o, d, t);                   // analytic primitives
         int tri = -1;
@@ -366,14 +374,15 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
             if (tri >= 0) k = mat.mesh.n_prims + tri;
         }
         ++cnt.segments;
-        if (k < 0) break;                                   // miss, :134-135
+        if (k < 0) { alive = false; continue; }             // miss, :134-135
         V3<R> pt = {o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
         const int em = mat.em(k), col = mat.col(k);
         lit |= em >= 0;
         rec.prim_[n] = Id(k);
         if (col < 0) {                                      // null BxDF, :25-26, 38-39
             rec.w_[n++] = R(0);
-            break;
+            alive = false;
+            continue;
         }
         V3<R> nrm, tg, bt;
         bool on_mesh = false;
