@@ -521,6 +521,42 @@ __device__ __forceinline__ int pick_link(float4 lk, int j)
     return __float_as_int((j & 2) ? b : a);
 }
 
+// One wide-node step of a lane: slab-test the 4 children, sort the hits by entry
+// distance, push the far ones (far first, so the nearest is popped first), descend
+// into the nearest.  Returns true when nothing was hit (the caller pops).
+__device__ __forceinline__ bool bvh_node_step(const MeshView& m, const RayF& r, float tmax, int& cur, int2* stack, int& sp,
+                                              bool& overflow)
+{
+    const float4* nd = m.nodes + (size_t)cur * kNodeStride;
+    const float4 lx = __ldg(nd), ly = __ldg(nd + 1), lz = __ldg(nd + 2), hx = __ldg(nd + 3), hy = __ldg(nd + 4),
+                 hz = __ldg(nd + 5), lk = __ldg(nd + 6);
+    int key[4];
+#define DRTB_SLAB(J, C)                                                                           \
+    {                                                                                             \
+        const float ax = fmaf(lx.C, r.ix, -r.oix), bx = fmaf(hx.C, r.ix, -r.oix);                 \
+        const float ay = fmaf(ly.C, r.iy, -r.oiy), by = fmaf(hy.C, r.iy, -r.oiy);                 \
+        const float az = fmaf(lz.C, r.iz, -r.oiz), bz = fmaf(hz.C, r.iz, -r.oiz);                 \
+        float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));                     \
+        float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));                     \
+        tn = fmaxf(tn - fabsf(tn) * 4e-7f, 0.0f);           /* conservative: widen by a few ulp */ \
+        tf += fabsf(tf) * 4e-7f;                                                                  \
+        key[J] = hit_key(tn, tf, tmax, J);                                                        \
+    }
+    DRTB_SLAB(0, x) DRTB_SLAB(1, y) DRTB_SLAB(2, z) DRTB_SLAB(3, w)
+#undef DRTB_SLAB
+    cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+    // the stores are predicated, not branched
+#pragma unroll
+    for (int k = 3; k >= 1; --k) {
+        const bool hit = key[k] != 0x7fffffff;
+        if (hit && sp < kBvhStack) stack[sp] = make_int2(key[k], pick_link(lk, key[k] & 3));
+        overflow |= hit && sp >= kBvhStack;
+        sp += (hit && sp < kBvhStack) ? 1 : 0;
+    }
+    cur = pick_link(lk, key[0] & 3);
+    return key[0] == 0x7fffffff;
+}
+
 // Closest triangle along (o, d) that beats `tmin`; ordered traversal, nearest child first.
 template <typename R>
 __device__ __forceinline__ void bvh_closest(const MeshView& m, V3<R> o, V3<R> d, R& tmin, int& best,
@@ -551,34 +587,7 @@ __device__ __forceinline__ void bvh_closest(const MeshView& m, V3<R> o, V3<R> d,
         if (!leaf_step) {
             if (at_node) {                               // wide node
                 ++n_nodes;
-                const float4* nd = m.nodes + (size_t)cur * kNodeStride;
-                const float4 lx = __ldg(nd), ly = __ldg(nd + 1), lz = __ldg(nd + 2), hx = __ldg(nd + 3), hy = __ldg(nd + 4),
-                             hz = __ldg(nd + 5), lk = __ldg(nd + 6);
-                int key[4];
-#define DRTB_SLAB(J, C)                                                                                   \
-                {                                                                                         \
-                    const float ax = fmaf(lx.C, r.ix, -r.oix), bx = fmaf(hx.C, r.ix, -r.oix);             \
-                    const float ay = fmaf(ly.C, r.iy, -r.oiy), by = fmaf(hy.C, r.iy, -r.oiy);             \
-                    const float az = fmaf(lz.C, r.iz, -r.oiz), bz = fmaf(hz.C, r.iz, -r.oiz);             \
-                    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));                 \
-                    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));                 \
-                    tn = fmaxf(tn - fabsf(tn) * 4e-7f, 0.0f);       /* conservative: widen by a few ulp */ \
-                    tf += fabsf(tf) * 4e-7f;                                                              \
-                    key[J] = hit_key(tn, tf, tmax, J);                                                    \
-                }
-                DRTB_SLAB(0, x) DRTB_SLAB(1, y) DRTB_SLAB(2, z) DRTB_SLAB(3, w)
-#undef DRTB_SLAB
-                cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
-                // far ones first, so the nearest is popped first; the stores are predicated, not branched
-#pragma unroll
-                for (int k = 3; k >= 1; --k) {
-                    const bool hit = key[k] != 0x7fffffff;
-                    if (hit && sp < kBvhStack) stack[sp] = make_int2(key[k], pick_link(lk, key[k] & 3));
-                    overflow |= hit && sp >= kBvhStack;
-                    sp += (hit && sp < kBvhStack) ? 1 : 0;
-                }
-                pop = key[0] == 0x7fffffff;              // nothing hit
-                cur = pick_link(lk, key[0] & 3);
+                pop = bvh_node_step(m, r, tmax, cur, stack, sp, overflow);
             }
         } else if (at_leaf) {                            // leaf: ~((first << 2) | (count - 1))
             const int code = ~cur, first = code >> 2, count = (code & 3) + 1;

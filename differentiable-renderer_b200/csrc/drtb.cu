@@ -23,6 +23,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "path.cuh"
+#include "wavefront.cuh"
 
 using namespace drtb;
 
@@ -280,6 +281,108 @@ reduce_grad_kernel(const double* __restrict__ partial, int n_blocks, int P3, dou
     }
 }
 
+// Wavefront stage 4: radiance recurrence + adjoint over the records one batch
+// left in HBM, the per-pixel sums of src/render.cpp:78-82 and the gradient sums.
+// Same warp-task shape as render_kernel (a warp owns whole pixels, lanes own
+// samples), so the image is summed in a fixed order.
+template <typename R, bool SMALLP, int CAP>
+__global__ void __launch_bounds__(kBlock)
+wf_adjoint(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArgs a, const WfBuffers<R> b, int partial_row0)
+{
+    extern __shared__ double s_dyn[];
+    __shared__ BlockScene<R> bs;
+    __shared__ double s_red[kSmallP * 3][kWarpsPerBlock];
+    const bool want_grad = (a.flags & DRTB_FLAG_GRAD) != 0;
+    const int P3 = sc.n_params * 3;
+    double* s_acc = s_dyn;
+    const int acc_doubles = (SMALLP && want_grad) ? P3 * kBlock : 0;
+    load_block_scene(bs, sc, a.params);
+    for (int i = threadIdx.x; i < acc_doubles; i += kBlock) s_acc[i] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int spp = a.spp;
+    const long long npix = a.n_paths / spp, pix0 = a.first_path / spp;
+    const int ppw = spp >= 32 ? 1 : 32 / spp;
+    const int passes = spp >= 32 ? (spp + 31) / 32 : 1;
+    const long long n_tasks = (npix + ppw - 1) / ppw;
+    const long long n_warps = (long long)gridDim.x * kWarpsPerBlock;
+    const R inv_p = a.absorb < 1.0 ? R(1.0 / (1.0 - a.absorb)) : R(0);
+    SmemSink ssink{s_acc + threadIdx.x};
+    AtomicSink asink{a.grad_atomic};
+    Materials<R, true> mat;
+    mat.bs = &bs; mat.mesh = a.mesh; mat.params = a.params;
+    uint32_t n_lit = 0;
+    for (long long task = (long long)blockIdx.x * kWarpsPerBlock + warp; task < n_tasks; task += n_warps) {
+        const int sub = spp >= 32 ? 0 : lane / spp;
+        const int i0 = spp >= 32 ? lane : lane % spp;
+        const long long lp = task * ppw + sub;                // pixel within the batch
+        const bool lane_ok = sub < ppw && lp < npix;
+        const long long pix = pix0 + lp;                      // pixel within the shard
+        R g0[3] = {R(0), R(0), R(0)};
+        if (lane_ok && want_grad) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) g0[c] = R(a.seed_scale * (a.seed_img ? a.seed_img[pix * 3 + c] : 1.0));
+        }
+        double acc[3] = {0.0, 0.0, 0.0};
+        for (int pass = 0; pass < passes; ++pass) {
+            const int i = i0 + pass * 32;
+            if (!(lane_ok && i < spp)) continue;
+            const long long p = lp * spp + i;
+            const uint32_t st = b.state[p];
+            if (!(st & kStLit)) continue;
+            const int n = int((st >> 16) & 0xffu);
+            const WfRecordView<R, CAP> rec{b.rec_w + p, b.rec_prim + p, a.batch};
+            R L0[3];
+            if (SMALLP) radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ssink);
+            else        radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, asink);
+            acc[0] += double(L0[0]); acc[1] += double(L0[1]); acc[2] += double(L0[2]);
+            n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
+        }
+        if (a.img) {
+            if (spp >= 32) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[c] = warp_sum(acc[c]);
+                if (lane == 0 && lane_ok) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) a.img[pix * 3 + c] = acc[c] / double(spp);
+                }
+            } else {
+                double tot[3] = {acc[0], acc[1], acc[2]};
+                for (int j = 1; j < spp; ++j) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        double o = __shfl_down_sync(0xffffffffu, acc[c], j);
+                        if (i0 + j < spp) tot[c] += o;
+                    }
+                }
+                if (lane_ok && i0 == 0) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) a.img[pix * 3 + c] = tot[c] / double(spp);
+                }
+            }
+        }
+    }
+    if (SMALLP && want_grad) {
+        for (int j = 0; j < P3; ++j) {
+            double v = warp_sum(s_acc[j * kBlock + threadIdx.x]);
+            if (lane == 0) s_red[j][warp] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < P3) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarpsPerBlock; ++w) v += s_red[threadIdx.x][w];
+            a.grad_partial[((size_t)partial_row0 + blockIdx.x) * P3 + threadIdx.x] = v;
+        }
+    }
+    if (a.stats) {
+        unsigned long long t = n_lit;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0 && t) atomicAdd((unsigned long long*)&a.stats->lit_paths, t);
+    }
+}
+
 // Pathtracer<T>::trace(scene, orig, dir) for user-supplied rays (pathtracer.hpp:121-136).
 template <typename R, bool MESH>
 __global__ void __launch_bounds__(kBlock)
@@ -365,6 +468,9 @@ struct drtb_ctx {
     int32_t* d_tri_emis = nullptr;
     double mesh_build_ms = 0.0;
     int mesh_nodes = 0;
+    // wavefront buffers (mesh scenes), grown on demand
+    void* wf_mem = nullptr;       size_t wf_cap = 0;
+    bool mesh_megakernel = false; // DRTB_MESH_PIPELINE=megakernel: trace meshes inside render_kernel (A/B aid)
 };
 
 namespace {
@@ -564,6 +670,10 @@ int effective_max_depth(const drtb_render_opts* o)
     return o->absorb == 1.0 ? std::max(1, o->min_bounces) : kMaxDepth;
 }
 
+template <typename R>
+int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opts* o, const double* d_seed, double* d_img,
+                     double* d_grad, drtb_stats* d_stats, cudaStream_t stream);
+
 // Enqueue one render (+ gradient reduction) on `stream`; all pointers device.
 int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed, double* d_img,
                        double* d_grad, drtb_stats* d_stats, cudaStream_t stream)
@@ -574,6 +684,9 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     const bool want_img = (o->flags & DRTB_FLAG_IMAGE) != 0;
     if (want_grad && !d_grad) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_GRAD set but grad is NULL");
     if (want_img && !d_img) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_IMAGE set but img is NULL");
+    if (ctx->n_tris > 0 && !ctx->mesh_megakernel)
+        return o->precision == DRTB_F32 ? launch_wavefront<float>(ctx, ctx->sc32, o, d_seed, d_img, d_grad, d_stats, stream)
+                                        : launch_wavefront<double>(ctx, ctx->sc64, o, d_seed, d_img, d_grad, d_stats, stream);
     const int cnt = o->shard_count > 1 ? o->shard_count : 1;
     const int rows = shard_rows_impl(H, o->shard_index, cnt, o->band_rows);
 
@@ -613,6 +726,108 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     if (rc != DRTB_OK) return rc;
     if (want_grad && smallp) {
         reduce_grad_kernel<<<1, 256, 0, stream>>>(ctx->d_partial, int(grid), P3, d_grad);
+        CK(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    return DRTB_OK;
+}
+
+// Mesh scenes: the wavefront of wavefront.cuh, batch by batch.
+template <typename R>
+int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opts* o, const double* d_seed, double* d_img,
+                     double* d_grad, drtb_stats* d_stats, cudaStream_t stream)
+{
+    const int W = ctx->camera.width, H = ctx->camera.height;
+    const int P = int(ctx->params.size() / 3), P3 = P * 3;
+    const bool want_grad = (o->flags & DRTB_FLAG_GRAD) != 0, want_img = (o->flags & DRTB_FLAG_IMAGE) != 0;
+    const int cnt = o->shard_count > 1 ? o->shard_count : 1;
+    const int rows = shard_rows_impl(H, o->shard_index, cnt, o->band_rows);
+    const long long npix = (long long)rows * W;
+    const int D = effective_max_depth(o);
+    const bool smallp = P <= kSmallP;
+    // whole pixels per batch, a multiple of 32 so that warps of wf_adjoint never straddle batches
+    long long pix_per_batch = std::max<long long>(32, (kBatchPaths / o->spp) / 32 * 32);
+    pix_per_batch = std::min<long long>(pix_per_batch, (npix + 31) / 32 * 32);
+    const long long batch = pix_per_batch * o->spp;
+    if (batch > (1ll << 30)) return fail(ctx, DRTB_ERR_UNSUPPORTED, "spp too large for one wavefront batch");
+    const int n_batches = int((npix + pix_per_batch - 1) / pix_per_batch);
+
+    // carve the buffers out of one allocation
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t sz_ray = up(size_t(batch) * sizeof(R4<R>)), sz_i = up(size_t(batch) * 4);
+    const size_t sz_rw = up(size_t(batch) * D * sizeof(R)), sz_rp = up(size_t(batch) * D * 4), sz_cnt = up(size_t(D + 2) * 4);
+    const size_t total = 2 * sz_ray + 2 * sz_i + sz_rw + sz_rp + 2 * sz_cnt;
+    if (total > ctx->wf_cap) {
+        cudaFree(ctx->wf_mem); ctx->wf_mem = nullptr; ctx->wf_cap = 0;
+        cudaError_t e = cudaMalloc(&ctx->wf_mem, total);
+        if (e != cudaSuccess) return fail(ctx, DRTB_ERR_NOMEM, std::string("cudaMalloc (wavefront buffers): ") + cudaGetErrorString(e));
+        ctx->wf_cap = total;
+    }
+    char* mem = static_cast<char*>(ctx->wf_mem);
+    WfBuffers<R> b{};
+    b.ray_a = reinterpret_cast<R4<R>*>(mem); mem += sz_ray;
+    b.ray_b = reinterpret_cast<R4<R>*>(mem); mem += sz_ray;
+    b.hit = reinterpret_cast<int32_t*>(mem); mem += sz_i;
+    b.state = reinterpret_cast<uint32_t*>(mem); mem += sz_i;
+    b.rec_w = reinterpret_cast<R*>(mem); mem += sz_rw;
+    b.rec_prim = reinterpret_cast<int32_t*>(mem); mem += sz_rp;
+    b.alive_count = reinterpret_cast<int32_t*>(mem); mem += sz_cnt;
+    b.fetch = reinterpret_cast<uint32_t*>(mem);
+
+    WfArgs a{};
+    a.spp = o->spp; a.min_bounces = o->min_bounces; a.max_depth = D; a.flags = o->flags; a.absorb = o->absorb;
+    a.key0 = o->seed * kSeedMul;
+    a.shard_index = o->shard_index; a.shard_count = cnt; a.band_rows = o->band_rows > 0 ? o->band_rows : 1;
+    a.batch = int(batch); a.seed_scale = o->seed_scale;
+    a.params = ctx->d_params; a.seed_img = d_seed; a.img = want_img ? d_img : nullptr;
+    a.stats = (o->flags & DRTB_FLAG_STATS) ? d_stats : nullptr;
+    a.mesh = mesh_view(ctx);
+    if (a.stats) CK(ctx, cudaMemsetAsync(d_stats, 0, sizeof(drtb_stats), stream));
+    if (want_grad && !smallp) {
+        CK(ctx, cudaMemsetAsync(d_grad, 0, sizeof(double) * P3, stream));
+        a.grad_atomic = d_grad;
+    }
+    // grids
+    int trav_per_sm = 0;
+    CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trav_per_sm, wf_traverse<R>, 128, 0));
+    const int trav_grid = ctx->sm_count * std::max(1, trav_per_sm);
+    const size_t adj_smem = (smallp && want_grad) ? size_t(P3) * kBlock * sizeof(double) : 0;
+    const int adj_grid = ctx->sm_count * 8;
+    if (want_grad && smallp) {
+        int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, size_t(adj_grid) * n_batches * P3);
+        if (rc != DRTB_OK) return rc;
+        a.grad_partial = ctx->d_partial;
+    }
+    const bool no_bvh = (o->flags & DRTB_FLAG_NO_BVH) != 0;
+    const bool deep = D > kQueueDepth;
+    for (int bi = 0; bi < n_batches; ++bi) {
+        const long long p0 = (long long)bi * pix_per_batch;
+        a.first_path = p0 * o->spp;
+        a.n_paths = int(std::min<long long>(pix_per_batch, npix - p0) * o->spp);
+        const int g256 = (a.n_paths + 255) / 256;
+        CK(ctx, cudaMemsetAsync(b.alive_count, 0, 2 * sz_cnt, stream));          // alive_count and fetch
+        a.depth = 0;
+        wf_generate<R><<<g256, 256, 0, stream>>>(sc, a, b);
+        for (int depth = 0; depth < D; ++depth) {
+            a.depth = depth;
+            if (no_bvh) wf_traverse_brute<R><<<(a.n_paths + 127) / 128, 128, 0, stream>>>(a, b);
+            else        wf_traverse<R><<<trav_grid, 128, 0, stream>>>(a, b);
+            wf_shade<R><<<g256, 256, 0, stream>>>(sc, a, b);
+        }
+        if (smallp) {
+            if (deep) { CK(ctx, cudaFuncSetAttribute(wf_adjoint<R, true, kMaxDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(adj_smem)));
+                        wf_adjoint<R, true, kMaxDepth><<<adj_grid, kBlock, adj_smem, stream>>>(sc, a, b, bi * adj_grid); }
+            else      { CK(ctx, cudaFuncSetAttribute(wf_adjoint<R, true, kQueueDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(adj_smem)));
+                        wf_adjoint<R, true, kQueueDepth><<<adj_grid, kBlock, adj_smem, stream>>>(sc, a, b, bi * adj_grid); }
+        } else {
+            if (deep) wf_adjoint<R, false, kMaxDepth><<<adj_grid, kBlock, 0, stream>>>(sc, a, b, 0);
+            else      wf_adjoint<R, false, kQueueDepth><<<adj_grid, kBlock, 0, stream>>>(sc, a, b, 0);
+        }
+        CK(ctx, cudaGetLastError());
+        ctx->launches += 2 + 2 * D;
+    }
+    if (want_grad && smallp) {
+        reduce_grad_kernel<<<1, 256, 0, stream>>>(ctx->d_partial, adj_grid * n_batches, P3, d_grad);
         CK(ctx, cudaGetLastError());
         ctx->launches++;
     }
@@ -691,6 +906,7 @@ int drtb_create(int device, drtb_ctx** out)
     if (!ctx) return fail(nullptr, DRTB_ERR_NOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = std::getenv("DRTB_MESH_PIPELINE")) ctx->mesh_megakernel = std::string(e) == "megakernel";
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
@@ -711,7 +927,7 @@ void drtb_destroy(drtb_ctx* ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     cudaFree(ctx->d_params); cudaFree(ctx->d_partial); cudaFree(ctx->d_img);
-    cudaFree(ctx->d_seed); cudaFree(ctx->d_grad); cudaFree(ctx->d_stats);
+    cudaFree(ctx->d_seed); cudaFree(ctx->d_grad); cudaFree(ctx->d_stats); cudaFree(ctx->wf_mem);
     free_mesh(ctx);
     delete ctx;
 }

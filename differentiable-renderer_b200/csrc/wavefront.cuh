@@ -1,0 +1,345 @@
+// wavefront.cuh — the mesh-scene integrator: a wavefront over SoA ray / hit /
+// state buffers in HBM (config 4 of BASELINE.json).
+//
+// Why a second integrator.  For the analytic scenes the megakernel
+// (render_kernel) is the right shape: a segment is ~600 register-resident
+// instructions and nothing reaches HBM.  With a BVH the cost of a segment is
+// dominated by a traversal whose length varies 4x between the lanes of a warp
+// (ncu: 10.7 of 32 lanes active in node steps, 4.0 in leaf steps even with
+// warp-synchronous stepping), and inside a megakernel a lane that is done has
+// to wait for the slowest ray of its warp.  Here the traversal is its own
+// persistent kernel that REFILLS finished lanes from the ray queue, so the warp
+// stays full, and it carries no path state, so more warps fit on an SM.
+//
+// One batch of paths (<= kBatchPaths camera samples, whole pixels) goes through
+//   wf_generate                      camera ray + first segment set-up
+//   repeat depth = 0 .. max_depth:
+//       wf_traverse                  closest triangle, persistent + dynamic fetch
+//       wf_shade                     vertex record, BRDF sample, next segment set-up
+//   wf_adjoint                       radiance recurrence + adjoint, pixel and gradient sums
+// and every path advances exactly one segment per iteration, so the depth is
+// the host's loop counter.  Path slot p <-> (pixel, sample) is static: no
+// compaction, the image is summed per pixel in sample order (bit-reproducible).
+//
+// Buffers (SoA, one element per path slot, every access coalesced):
+//   ray_a  = (o.x, o.y, o.z, d.x)   ray_b = (d.y, d.z, t_hit, -)    as R4 (float4 / double4)
+//   hit    = scene index of the closest primitive so far, -1 = none
+//   state  = alive | lit | n (vertices) | next stream slot
+//   rec_w[v][p], rec_prim[v][p]      the vertex record the adjoint sweeps read
+// The functions of the reference each stage replaces are the ones named in
+// path.cuh; this file only re-schedules them.
+#pragma once
+#include "path.cuh"
+
+namespace drtb {
+
+constexpr int kBatchPaths = 1 << 22;          // camera samples per wavefront batch
+constexpr int kFetchBelow = 20;               // traversal: refill the warp when fewer lanes than this hold a ray
+
+template <typename R> struct alignas(4 * sizeof(R)) R4 { R x, y, z, w; };
+
+constexpr uint32_t kStAlive = 1u << 31, kStLit = 1u << 30;      // state = alive | lit | n << 16 | slot
+
+template <typename R>
+struct WfBuffers {
+    R4<R>*    ray_a;
+    R4<R>*    ray_b;
+    int32_t*  hit;
+    uint32_t* state;
+    R*        rec_w;                          // [max_depth][batch]
+    int32_t*  rec_prim;                       // [max_depth][batch]
+    int32_t*  alive_count;                    // [max_depth + 2]: paths alive entering depth d
+    uint32_t* fetch;                          // traversal queue cursor, one per depth
+};
+
+struct WfArgs {
+    int32_t  spp, min_bounces, max_depth;
+    uint32_t flags;
+    double   absorb;
+    uint64_t key0;
+    int32_t  shard_index, shard_count, band_rows;
+    long long first_path;                     // of this batch, in the shard's compact (pixel, sample) order
+    int32_t  n_paths;                         // in this batch
+    int32_t  batch;                           // slot stride of the record arrays
+    int32_t  depth;
+    double   seed_scale;
+    const double* params;
+    const double* seed_img;
+    double*  img;
+    double*  grad_partial;
+    double*  grad_atomic;
+    drtb_stats* stats;
+    MeshView mesh;
+};
+
+template <typename R>
+__device__ __forceinline__ void wf_pixel_of(const DevScene<R>& sc, const WfArgs& a, long long gp, long long& pix, int& i,
+                                            int& x, int& y)
+{
+    pix = gp / a.spp;
+    i = int(gp - pix * a.spp);
+    const int r = int(pix / sc.width);
+    x = int(pix - (long long)r * sc.width);
+    y = a.shard_count > 1 ? ((r / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + r % a.band_rows : r;
+}
+
+template <typename R>
+__device__ __forceinline__ uint64_t wf_base(const DevScene<R>& sc, const WfArgs& a, int x, int y, int i)
+{
+    return (a.key0 + ((uint64_t)y * sc.width + x) * (uint64_t)a.spp + (uint64_t)i) * kKeyMul;
+}
+
+// Start of a segment at `depth` (Pathtracer::trace, pathtracer.hpp:121-136 up to the
+// raycast): Russian roulette, the record-capacity cut, then the analytic primitives.
+// Returns false when the path ends here.
+template <typename R>
+__device__ __forceinline__ bool wf_begin_segment(const DevScene<R>& sc, const WfArgs& a, const WfBuffers<R>& b, int p,
+                                                 int depth, uint64_t base, uint32_t& slot, int n, V3<R> o, V3<R> d,
+                                                 uint32_t& truncated)
+{
+    if (depth >= a.min_bounces) {
+        const double u = Real<double>::uniform(stream_draw_base(base, slot++));
+        if (u < a.absorb) return false;
+    }
+    if (n >= a.max_depth) { ++truncated; return false; }
+    R t = Real<R>::inf();
+    int k = -1;
+    if (sc.n_prims > 0) { k = closest_hit(sc, o, d, t); if (k < 0) t = Real<R>::inf(); }
+    b.ray_a[p] = {o.x, o.y, o.z, d.x};
+    b.ray_b[p] = {d.y, d.z, t, R(0)};
+    b.hit[p] = k;
+    return true;
+}
+
+// ---- camera rays -----------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256)
+wf_generate(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArgs a, const WfBuffers<R> b)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t truncated = 0;
+    bool alive = false;
+    if (p < a.n_paths) {
+        long long pix; int i, x, y;
+        wf_pixel_of(sc, a, a.first_path + p, pix, i, x, y);
+        const uint64_t base = wf_base(sc, a, x, y, i);
+        const V3<R> o = {sc.eye[0], sc.eye[1], sc.eye[2]};
+        const V3<R> d = camera_ray(sc, x, y, base);
+        uint32_t slot = 2u;
+        alive = wf_begin_segment(sc, a, b, p, 0, base, slot, 0, o, d, truncated);
+        b.state[p] = (alive ? kStAlive : 0u) | slot;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, alive);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(b.alive_count, __popc(m));
+    if (truncated && a.stats) atomicAdd((unsigned long long*)&a.stats->truncated_paths, 1ull);
+}
+
+// ---- closest triangle: persistent warps, finished lanes refilled from the queue ---
+template <typename R> __device__ __forceinline__ void wf_reload_ray(const WfBuffers<R>& b, int p, V3<R>& o, V3<R>& d)
+{
+    const R4<R> ra = b.ray_a[p], rb = b.ray_b[p];
+    o = {ra.x, ra.y, ra.z}; d = {ra.w, rb.x, rb.y};
+}
+
+#ifndef DRTB_WF_MIN_BLOCKS
+#define DRTB_WF_MIN_BLOCKS 6
+#endif
+template <typename R>
+__global__ void __launch_bounds__(128, DRTB_WF_MIN_BLOCKS)
+wf_traverse(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
+{
+    if (b.alive_count[a.depth] == 0) return;
+    const MeshView& m = a.mesh;
+    const int lane = threadIdx.x & 31;
+    uint32_t n_nodes = 0, n_tests = 0;
+    // lane state
+    int p = -1;                                   // path slot whose ray this lane traverses, -1 = none
+    RayF r{};
+    R tmin = R(0);
+    float tmax = 0.f;
+    int best = -1, cur = 0, sp = 0;
+    bool overflow = false;
+    int2 stack[kBvhStack];
+    bool exhausted = false;                       // warp-uniform: the queue has no more rays
+    for (;;) {
+        const unsigned busy = __ballot_sync(0xffffffffu, p >= 0);
+        if (!exhausted && __popc(busy) < kFetchBelow) {
+            // refill every idle lane with the next rays of the queue (consecutive slots: coalesced)
+            const unsigned idle = ~busy;
+            uint32_t first = 0;
+            if (lane == 0) first = atomicAdd(b.fetch + a.depth, (uint32_t)__popc(idle));
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (p < 0) {
+                const uint32_t q = first + __popc(idle & ((1u << lane) - 1u));
+                if (q < (uint32_t)a.n_paths && (b.state[q] & kStAlive)) {
+                    p = int(q);
+                    const R4<R> ra = b.ray_a[p], rb = b.ray_b[p];
+                    r = make_rayf<R>(V3<R>{ra.x, ra.y, ra.z}, V3<R>{ra.w, rb.x, rb.y});
+                    tmin = rb.z; tmax = upper_float<R>(tmin);
+                    best = -1; cur = 0; sp = 0; overflow = false;
+                }
+            }
+            exhausted = first + (uint32_t)__popc(idle) >= (uint32_t)a.n_paths;
+            if (__ballot_sync(0xffffffffu, p >= 0) == 0u) { if (exhausted) break; else continue; }
+        } else if (busy == 0u) break;
+        // one step of the kind more lanes wait for (see bvh_closest)
+        const bool at_node = p >= 0 && cur >= 0, at_leaf = p >= 0 && cur < 0;
+        const unsigned node_m = __ballot_sync(0xffffffffu, at_node), leaf_m = __ballot_sync(0xffffffffu, at_leaf);
+        const bool leaf_step = node_m == 0u || __popc(leaf_m) >= __popc(node_m);
+        bool pop = false;
+        if (!leaf_step) {
+            if (at_node) {
+                ++n_nodes;
+                pop = bvh_node_step(m, r, tmax, cur, stack, sp, overflow);
+            }
+        } else if (at_leaf) {
+            const int code = ~cur, first = code >> 2, count = (code & 3) + 1;
+            for (int k = 0; k < count; ++k) {
+                ++n_tests;
+                const TriF T = load_trif(m, first + k);
+                if constexpr (sizeof(R) == 8) {
+                    if (tri_cull_f(T, r, tmax)) continue;
+                    V3<R> o, d;
+                    wf_reload_ray(b, p, o, d);    // the exact test is rare (~1 per segment): keep o, d out of the registers
+                    tri_test_exact<R>(load_tri<R>(m, T.id), T.id, o, d, tmin, best);
+                } else {
+                    const TriData<R> D = {{T.v0x, T.v0y, T.v0z}, {T.e1x, T.e1y, T.e1z}, {T.e2x, T.e2y, T.e2z}};
+                    tri_test_exact<R>(D, T.id, V3<R>{r.ox, r.oy, r.oz}, V3<R>{r.dx, r.dy, r.dz}, tmin, best);
+                }
+            }
+            tmax = upper_float<R>(tmin);
+            pop = true;
+        }
+        if (pop) {
+            bool more = false;
+            while (sp > 0) {
+                const int2 e = stack[--sp];
+                if (__int_as_float(e.x & ~3) <= tmax) { cur = e.y; more = true; break; }
+            }
+            if (!more) {                          // this ray is done: publish the hit, free the lane
+                if (overflow) {
+                    V3<R> o, d;
+                    wf_reload_ray(b, p, o, d);
+                    brute_closest<R>(m, o, d, tmin, best, n_tests);
+                }
+                if (best >= 0) { b.ray_b[p].z = tmin; b.hit[p] = m.n_prims + best; }
+                p = -1;
+            }
+        }
+    }
+    if (a.stats) {
+        unsigned long long nn = n_nodes, nt = n_tests;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { nn += __shfl_xor_sync(0xffffffffu, nn, o); nt += __shfl_xor_sync(0xffffffffu, nt, o); }
+        if (lane == 0) {
+            atomicAdd((unsigned long long*)&a.stats->bvh_nodes, nn);
+            atomicAdd((unsigned long long*)&a.stats->tri_tests, nt);
+        }
+    }
+}
+
+// test aid (DRTB_FLAG_NO_BVH): every triangle against every ray
+template <typename R>
+__global__ void __launch_bounds__(128)
+wf_traverse_brute(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_paths || !(b.state[p] & kStAlive)) return;
+    V3<R> o, d;
+    wf_reload_ray(b, p, o, d);
+    R tmin = b.ray_b[p].z;
+    int best = -1;
+    uint32_t n_tests = 0;
+    brute_closest<R>(a.mesh, o, d, tmin, best, n_tests);
+    if (best >= 0) { b.ray_b[p].z = tmin; b.hit[p] = a.mesh.n_prims + best; }
+    if (a.stats) atomicAdd((unsigned long long*)&a.stats->tri_tests, (unsigned long long)n_tests);
+}
+
+// ---- the vertex: record, sample, next segment (Pathtracer::scatter, pathtracer.hpp:91-115)
+template <typename R>
+__global__ void __launch_bounds__(256)
+wf_shade(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArgs a, const WfBuffers<R> b)
+{
+    if (b.alive_count[a.depth] == 0) return;
+    __shared__ BlockScene<R> bs;
+    load_block_scene(bs, sc, a.params);
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t truncated = 0;
+    bool alive = false, was_alive = false;
+    if (p < a.n_paths) {
+        uint32_t st = b.state[p];
+        was_alive = (st & kStAlive) != 0;
+        if (was_alive) {
+            Materials<R, true> mat;
+            mat.bs = &bs; mat.mesh = a.mesh; mat.params = a.params;
+            int n = int((st >> 16) & 0xffu);
+            uint32_t slot = st & 0xffffu;
+            bool lit = (st & kStLit) != 0;
+            const int k = b.hit[p];
+            if (k >= 0) {                                         // else: miss, pathtracer.hpp:134-135
+                const R4<R> ra = b.ray_a[p], rb = b.ray_b[p];
+                V3<R> o = {ra.x, ra.y, ra.z}, d = {ra.w, rb.x, rb.y};
+                const R t = rb.z;
+                const V3<R> pt = {o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
+                const int em = mat.em(k), col = mat.col(k);
+                lit |= em >= 0;
+                b.rec_prim[(size_t)n * a.batch + p] = k;
+                if (col < 0) {                                    // null BxDF, :25-26, 38-39
+                    b.rec_w[(size_t)n * a.batch + p] = R(0);
+                    ++n;
+                } else {
+                    V3<R> nrm, tg, bt;
+                    if (k >= a.mesh.n_prims) {                    // unit geometric normal, drtb.h
+                        const TriData<R> T = load_tri<R>(a.mesh, k - a.mesh.n_prims);
+                        nrm = normalize(cross(T.e1, T.e2));
+                        unit_frame(nrm, tg, bt);
+                    } else {
+                        nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]};
+                        if (bs.type[k] == DRTB_SPHERE) {          // shape.hpp:105-106
+                            nrm = normalize(V3<R>{pt.x - nrm.x, pt.y - nrm.y, pt.z - nrm.z});
+                            unit_frame(nrm, tg, bt);
+                        } else {
+                            tg = {bs.frame[k][0], bs.frame[k][1], bs.frame[k][2]};
+                            bt = {bs.frame[k][3], bs.frame[k][4], bs.frame[k][5]};
+                        }
+                    }
+                    long long pix; int i, x, y;
+                    wf_pixel_of(sc, a, a.first_path + p, pix, i, x, y);
+                    const uint64_t base = wf_base(sc, a, x, y, i);
+                    const R u_theta = Real<R>::uniform_fast(stream_draw_base(base, slot));
+                    const R u_phi = Real<R>::uniform_fast(stream_draw_base(base, slot + 1));
+                    slot += 2;
+                    R w;
+                    const V3<R> dout = diffuse_sample(nrm, tg, bt, u_theta, u_phi, w);
+                    b.rec_w[(size_t)n * a.batch + p] = w;
+                    ++n;
+                    const R eps = Real<R>::origin_eps();          // 1e-3, pathtracer.hpp:99
+                    o = {Real<R>::fma(eps, dout.x, pt.x), Real<R>::fma(eps, dout.y, pt.y), Real<R>::fma(eps, dout.z, pt.z)};
+                    alive = wf_begin_segment(sc, a, b, p, a.depth + 1, base, slot, n, o, dout, truncated);
+                }
+            }
+            b.state[p] = (alive ? kStAlive : 0u) | (lit ? kStLit : 0u) | (uint32_t(n) << 16) | slot;
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, alive), s = __ballot_sync(0xffffffffu, was_alive);
+    const unsigned tr = __ballot_sync(0xffffffffu, truncated != 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (m) atomicAdd(b.alive_count + a.depth + 1, __popc(m));
+        if (a.stats && s) atomicAdd((unsigned long long*)&a.stats->segments, (unsigned long long)__popc(s));
+        if (a.stats && tr) atomicAdd((unsigned long long*)&a.stats->truncated_paths, (unsigned long long)__popc(tr));
+    }
+}
+
+// A path's record in the wavefront buffers, as radiance_and_adjoint reads it.
+template <typename R, int CAP>
+struct WfRecordView {
+    static constexpr int kCap = CAP;
+    const R* w_;
+    const int32_t* prim_;
+    int stride;
+    __device__ __forceinline__ R w(int v) const { return w_[(size_t)v * stride]; }
+    __device__ __forceinline__ int prim(int v) const { return prim_[(size_t)v * stride]; }
+};
+
+} // namespace drtb
