@@ -521,10 +521,33 @@ __device__ __forceinline__ int pick_link(float4 lk, int j)
     return __float_as_int((j & 2) ? b : a);
 }
 
+// Traversal stacks.  Entries are (sort key, link).  LocalStack lives in local memory:
+// lanes sit at different depths, so one push touches up to 32 different cache lines.
+// SmemStack keeps the first kSmemStack entries in shared memory as [entry][thread]
+// (every lane owns a bank column: conflict-free whatever its depth) and spills deeper
+// entries to local memory.
+struct LocalStack {
+    int2 e[kBvhStack];
+    __device__ __forceinline__ void put(int i, int2 v) { e[i] = v; }
+    __device__ __forceinline__ int2 get(int i) const { return e[i]; }
+};
+#ifndef DRTB_SMEM_STACK
+#define DRTB_SMEM_STACK 16
+#endif
+constexpr int kSmemStack = DRTB_SMEM_STACK;
+template <int THREADS>
+struct SmemStack {
+    int2* col;                                   // &s_stack[0][threadIdx.x]
+    int2 spill[kBvhStack - kSmemStack];
+    __device__ __forceinline__ void put(int i, int2 v) { if (i < kSmemStack) col[i * THREADS] = v; else spill[i - kSmemStack] = v; }
+    __device__ __forceinline__ int2 get(int i) const { return i < kSmemStack ? col[i * THREADS] : spill[i - kSmemStack]; }
+};
+
 // One wide-node step of a lane: slab-test the 4 children, sort the hits by entry
 // distance, push the far ones (far first, so the nearest is popped first), descend
 // into the nearest.  Returns true when nothing was hit (the caller pops).
-__device__ __forceinline__ bool bvh_node_step(const MeshView& m, const RayF& r, float tmax, int& cur, int2* stack, int& sp,
+template <typename Stack>
+__device__ __forceinline__ bool bvh_node_step(const MeshView& m, const RayF& r, float tmax, int& cur, Stack& stack, int& sp,
                                               bool& overflow)
 {
     const float4* nd = m.nodes + (size_t)cur * kNodeStride;
@@ -549,7 +572,7 @@ __device__ __forceinline__ bool bvh_node_step(const MeshView& m, const RayF& r, 
 #pragma unroll
     for (int k = 3; k >= 1; --k) {
         const bool hit = key[k] != 0x7fffffff;
-        if (hit && sp < kBvhStack) stack[sp] = make_int2(key[k], pick_link(lk, key[k] & 3));
+        if (hit && sp < kBvhStack) stack.put(sp, make_int2(key[k], pick_link(lk, key[k] & 3)));
         overflow |= hit && sp >= kBvhStack;
         sp += (hit && sp < kBvhStack) ? 1 : 0;
     }
@@ -564,7 +587,7 @@ __device__ __forceinline__ void bvh_closest(const MeshView& m, V3<R> o, V3<R> d,
 {
     const RayF r = make_rayf(o, d);
     float tmax = upper_float<R>(tmin);
-    int2 stack[kBvhStack];                               // (key, link)
+    LocalStack stack;                                    // (key, link)
     int sp = 0, cur = 0;
     bool overflow = false, alive = true;
     // Warp-synchronous stepping with a majority vote.  Left to the compiler's own
@@ -598,7 +621,7 @@ __device__ __forceinline__ void bvh_closest(const MeshView& m, V3<R> o, V3<R> d,
         if (pop) {
             alive = false;
             while (sp > 0) {
-                const int2 e = stack[--sp];
+                const int2 e = stack.get(--sp);
                 if (__int_as_float(e.x & ~3) <= tmax) { cur = e.y; alive = true; break; }
             }
         }

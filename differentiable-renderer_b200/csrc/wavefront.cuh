@@ -34,7 +34,11 @@
 namespace drtb {
 
 constexpr int kBatchPaths = 1 << 22;          // camera samples per wavefront batch
-constexpr int kFetchBelow = 20;               // traversal: refill the warp when fewer lanes than this hold a ray
+#ifndef DRTB_FETCH_BELOW
+#define DRTB_FETCH_BELOW 20
+#endif
+constexpr int kFetchBelow = DRTB_FETCH_BELOW; // traversal: refill the warp when fewer lanes than this hold a ray
+constexpr int kExactTag = 1 << 30;            // stack link ~(kExactTag | tri): exact test of triangle tri pending
 
 template <typename R> struct alignas(4 * sizeof(R)) R4 { R x, y, z, w; };
 
@@ -159,7 +163,9 @@ wf_traverse(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
     float tmax = 0.f;
     int best = -1, cur = 0, sp = 0;
     bool overflow = false;
-    int2 stack[kBvhStack];
+    __shared__ int2 s_stack[kSmemStack][128];
+    SmemStack<128> stack;
+    stack.col = &s_stack[0][threadIdx.x];
     bool exhausted = false;                       // warp-uniform: the queue has no more rays
     for (;;) {
         const unsigned busy = __ballot_sync(0xffffffffu, p >= 0);
@@ -182,38 +188,57 @@ wf_traverse(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
             exhausted = first + (uint32_t)__popc(idle) >= (uint32_t)a.n_paths;
             if (__ballot_sync(0xffffffffu, p >= 0) == 0u) { if (exhausted) break; else continue; }
         } else if (busy == 0u) break;
-        // one step of the kind more lanes wait for (see bvh_closest)
-        const bool at_node = p >= 0 && cur >= 0, at_leaf = p >= 0 && cur < 0;
-        const unsigned node_m = __ballot_sync(0xffffffffu, at_node), leaf_m = __ballot_sync(0xffffffffu, at_leaf);
-        const bool leaf_step = node_m == 0u || __popc(leaf_m) >= __popc(node_m);
+        // One step of the kind most lanes wait for (see bvh_closest).  Three kinds in the
+        // double instantiation: wide node, leaf (float cull of its triangles), and the exact
+        // double test of ONE triangle that survived a cull -- survivors are pushed on the
+        // lane's stack as entries of their own, so the expensive test (80-byte triangle +
+        // 64-byte ray reload + ~50 FP64 operations) also runs with many lanes instead of
+        // the 1.5 of 32 it had inside the leaf loop (profiles/r01_wf_traverse_f64_v1_summary.txt).
+        const int code = ~cur;
+        const bool on = p >= 0;
+        const bool at_node = on && cur >= 0;
+        const bool at_exact = on && cur < 0 && (code & kExactTag);
+        const bool at_leaf = on && cur < 0 && !(code & kExactTag);
+        const int nn = __popc(__ballot_sync(0xffffffffu, at_node)), nl = __popc(__ballot_sync(0xffffffffu, at_leaf)),
+                  ne = sizeof(R) == 8 ? __popc(__ballot_sync(0xffffffffu, at_exact)) : 0;
+        const int kind = (ne > 0 && ne >= nl && ne >= nn) ? 2 : (nl > 0 && nl >= nn) ? 1 : 0;
         bool pop = false;
-        if (!leaf_step) {
+        if (kind == 0) {
             if (at_node) {
                 ++n_nodes;
                 pop = bvh_node_step(m, r, tmax, cur, stack, sp, overflow);
             }
-        } else if (at_leaf) {
-            const int code = ~cur, first = code >> 2, count = (code & 3) + 1;
-            for (int k = 0; k < count; ++k) {
-                ++n_tests;
-                const TriF T = load_trif(m, first + k);
-                if constexpr (sizeof(R) == 8) {
-                    if (tri_cull_f(T, r, tmax)) continue;
-                    V3<R> o, d;
-                    wf_reload_ray(b, p, o, d);    // the exact test is rare (~1 per segment): keep o, d out of the registers
-                    tri_test_exact<R>(load_tri<R>(m, T.id), T.id, o, d, tmin, best);
-                } else {
-                    const TriData<R> D = {{T.v0x, T.v0y, T.v0z}, {T.e1x, T.e1y, T.e1z}, {T.e2x, T.e2y, T.e2z}};
-                    tri_test_exact<R>(D, T.id, V3<R>{r.ox, r.oy, r.oz}, V3<R>{r.dx, r.dy, r.dz}, tmin, best);
+        } else if (kind == 1) {
+            if (at_leaf) {
+                const int first = code >> 2, count = (code & 3) + 1;
+                for (int k = 0; k < count; ++k) {
+                    ++n_tests;
+                    const TriF T = load_trif(m, first + k);
+                    if constexpr (sizeof(R) == 8) {
+                        const bool keep = !tri_cull_f(T, r, tmax);
+                        if (keep && sp < kBvhStack) stack.put(sp, make_int2(0, ~(kExactTag | T.id)));
+                        overflow |= keep && sp >= kBvhStack;
+                        sp += (keep && sp < kBvhStack) ? 1 : 0;
+                    } else {
+                        const TriData<R> D = {{T.v0x, T.v0y, T.v0z}, {T.e1x, T.e1y, T.e1z}, {T.e2x, T.e2y, T.e2z}};
+                        tri_test_exact<R>(D, T.id, V3<R>{r.ox, r.oy, r.oz}, V3<R>{r.dx, r.dy, r.dz}, tmin, best);
+                    }
                 }
+                tmax = upper_float<R>(tmin);
+                pop = true;
             }
+        } else if (at_exact) {
+            const int tri = code & (kExactTag - 1);
+            V3<R> o, d;
+            wf_reload_ray(b, p, o, d);                // o, d stay out of the registers between the rare exact tests
+            tri_test_exact<R>(load_tri<R>(m, tri), tri, o, d, tmin, best);
             tmax = upper_float<R>(tmin);
             pop = true;
         }
         if (pop) {
             bool more = false;
             while (sp > 0) {
-                const int2 e = stack[--sp];
+                const int2 e = stack.get(--sp);
                 if (__int_as_float(e.x & ~3) <= tmax) { cur = e.y; more = true; break; }
             }
             if (!more) {                          // this ray is done: publish the hit, free the lane
