@@ -40,7 +40,7 @@ constexpr int kBvhStack   = 64;           // traversal stack entries per lane (o
 constexpr int kLeafMax    = DRTB_LEAF_MAX; // triangles per leaf, <= 4 (2 bits of the leaf link)
 constexpr int kPlocRadius = 16;           // PLOC neighbour search radius along the Morton order
 constexpr int kTri64Stride = 10;          // doubles per triangle: v0, e1, e2, pad (16-byte aligned rows)
-constexpr int kTri32Stride = 3;           // float4 per triangle
+constexpr int kTri32Stride = 4;           // float4 per triangle (64 B: two 256-bit loads)
 constexpr int kNodeStride  = 8;           // float4 per wide node
 constexpr int kEmptyLink   = 0x7fffffff;
 
@@ -378,9 +378,10 @@ __global__ void leaf_triangles_kernel(const int32_t* __restrict__ leaf_order, co
     // max-norms rounded up: they scale the float cull's error bound
     const float c1 = fmaxf(fabsf(f[3]), fmaxf(fabsf(f[4]), fabsf(f[5]))) * 1.0000002f;
     const float c2 = fmaxf(fabsf(f[6]), fmaxf(fabsf(f[7]), fabsf(f[8]))) * 1.0000002f;
-    tri32[(size_t)s * 3 + 0] = make_float4(f[0], f[1], f[2], f[3]);
-    tri32[(size_t)s * 3 + 1] = make_float4(f[4], f[5], f[6], f[7]);
-    tri32[(size_t)s * 3 + 2] = make_float4(f[8], c1, c2, __int_as_float(tri));
+    tri32[(size_t)s * kTri32Stride + 0] = make_float4(f[0], f[1], f[2], f[3]);
+    tri32[(size_t)s * kTri32Stride + 1] = make_float4(f[4], f[5], f[6], f[7]);
+    tri32[(size_t)s * kTri32Stride + 2] = make_float4(f[8], c1, c2, __int_as_float(tri));
+    tri32[(size_t)s * kTri32Stride + 3] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------------------
@@ -396,11 +397,21 @@ template <typename R> __device__ __forceinline__ TriData<R> load_tri(const MeshV
     return {{R(a.x), R(a.y), R(b.x)}, {R(b.y), R(c.x), R(c.y)}, {R(d.x), R(d.y), R(e.x)}};
 }
 
+// 256-bit read-only load (LDG.E.ENL2.256 on sm_100): one L1 wavefront per lane where two
+// LDG.128 cost two -- the traversal kernel is bound by L1 data-pipe wavefronts
+// (profiles/r01_wf_traverse_f64_v3_smemstack_summary.txt: 73 % of peak).
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
+{
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
 struct TriF { float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z, c1, c2; int id; };
 __device__ __forceinline__ TriF load_trif(const MeshView& m, int slot)
 {
-    const float4 a = __ldg(m.tri32 + (size_t)slot * 3), b = __ldg(m.tri32 + (size_t)slot * 3 + 1),
-                 c = __ldg(m.tri32 + (size_t)slot * 3 + 2);
+    float4 a, b;
+    ldg256(m.tri32 + (size_t)slot * kTri32Stride, a, b);
+    const float4 c = __ldg(m.tri32 + (size_t)slot * kTri32Stride + 2);
     return {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, __float_as_int(c.w)};
 }
 
@@ -528,7 +539,7 @@ __device__ __forceinline__ int pick_link(float4 lk, int j)
 // entries to local memory.
 struct LocalStack {
     int2 e[kBvhStack];
-    __device__ __forceinline__ void put(int i, int2 v) { e[i] = v; }
+    __device__ __forceinline__ void put(int i, int2 v, bool pred) { if (pred) e[i] = v; }
     __device__ __forceinline__ int2 get(int i) const { return e[i]; }
 };
 #ifndef DRTB_SMEM_STACK
@@ -537,9 +548,14 @@ struct LocalStack {
 constexpr int kSmemStack = DRTB_SMEM_STACK;
 template <int THREADS>
 struct SmemStack {
-    int2* col;                                   // &s_stack[0][threadIdx.x]
+    int2* col;                                   // &s_stack[0][threadIdx.x]; row kSmemStack is a write-only dummy
     int2 spill[kBvhStack - kSmemStack];
-    __device__ __forceinline__ void put(int i, int2 v) { if (i < kSmemStack) col[i * THREADS] = v; else spill[i - kSmemStack] = v; }
+    // predicated push without a branch on the common path: a lane that does not push writes the dummy row
+    __device__ __forceinline__ void put(int i, int2 v, bool pred)
+    {
+        if (pred && i >= kSmemStack) spill[i - kSmemStack] = v;
+        else col[(pred ? i : kSmemStack) * THREADS] = v;
+    }
     __device__ __forceinline__ int2 get(int i) const { return i < kSmemStack ? col[i * THREADS] : spill[i - kSmemStack]; }
 };
 
@@ -551,8 +567,9 @@ __device__ __forceinline__ bool bvh_node_step(const MeshView& m, const RayF& r, 
                                               bool& overflow)
 {
     const float4* nd = m.nodes + (size_t)cur * kNodeStride;
-    const float4 lx = __ldg(nd), ly = __ldg(nd + 1), lz = __ldg(nd + 2), hx = __ldg(nd + 3), hy = __ldg(nd + 4),
-                 hz = __ldg(nd + 5), lk = __ldg(nd + 6);
+    float4 lx, ly, lz, hx, hy, hz;
+    ldg256(nd, lx, ly); ldg256(nd + 2, lz, hx); ldg256(nd + 4, hy, hz);
+    const float4 lk = __ldg(nd + 6);
     int key[4];
 #define DRTB_SLAB(J, C)                                                                           \
     {                                                                                             \
@@ -572,7 +589,7 @@ __device__ __forceinline__ bool bvh_node_step(const MeshView& m, const RayF& r, 
 #pragma unroll
     for (int k = 3; k >= 1; --k) {
         const bool hit = key[k] != 0x7fffffff;
-        if (hit && sp < kBvhStack) stack.put(sp, make_int2(key[k], pick_link(lk, key[k] & 3)));
+        stack.put(sp, make_int2(key[k], pick_link(lk, key[k] & 3)), hit && sp < kBvhStack);
         overflow |= hit && sp >= kBvhStack;
         sp += (hit && sp < kBvhStack) ? 1 : 0;
     }

@@ -163,7 +163,7 @@ wf_traverse(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
     float tmax = 0.f;
     int best = -1, cur = 0, sp = 0;
     bool overflow = false;
-    __shared__ int2 s_stack[kSmemStack][128];
+    __shared__ int2 s_stack[kSmemStack + 1][128];
     SmemStack<128> stack;
     stack.col = &s_stack[0][threadIdx.x];
     bool exhausted = false;                       // warp-uniform: the queue has no more rays
@@ -216,7 +216,7 @@ wf_traverse(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
                     const TriF T = load_trif(m, first + k);
                     if constexpr (sizeof(R) == 8) {
                         const bool keep = !tri_cull_f(T, r, tmax);
-                        if (keep && sp < kBvhStack) stack.put(sp, make_int2(0, ~(kExactTag | T.id)));
+                        stack.put(sp, make_int2(0, ~(kExactTag | T.id)), keep && sp < kBvhStack);
                         overflow |= keep && sp >= kBvhStack;
                         sp += (keep && sp < kBvhStack) ? 1 : 0;
                     } else {
