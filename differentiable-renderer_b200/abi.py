@@ -12,11 +12,11 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "lib" / "libdrtb.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 SPHERE, PLANE = 0, 1
-DIFFUSE = 0
+DIFFUSE, SPECULAR = 0, 1
 F64, F32, MIXED = 0, 1, 2
 FLAG_IMAGE, FLAG_GRAD, FLAG_STATS, FLAG_NO_BVH = 1, 2, 4, 8
 
@@ -83,6 +83,10 @@ SYMBOLS = [
     ("drtb_render", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), _dp, _dp, _dp, C.POINTER(Stats)]),
     ("drtb_render_device", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("drtb_render_grad_image", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), C.c_int32, _dp, _dp, _dp, _dp,
+                                         C.POINTER(Stats)]),
+    ("drtb_render_grad_image_device", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), C.c_int32, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("drtb_trace_rays", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), C.c_int64, _dp, _dp,
                                   C.POINTER(C.c_uint64), _dp, _dp]),
     ("drtb_fma_peak", C.c_int, [C.c_void_p, C.c_int32, _dp]),

@@ -58,6 +58,19 @@ struct AtomicSink {
         atomicAdd(grad + 3 * p + c, double(v));
     }
 };
+// Gradient image (drtb_render_grad_image): parameter kp's contributions are
+// additionally summed into the lane's per-pixel accumulator g[3].
+template <typename Inner>
+struct PixelSink {
+    Inner inner;
+    int kp;
+    double* g;
+    template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
+    {
+        inner.add(p, c, v);
+        if (p == kp) g[c] += double(v);
+    }
+};
 struct JacSink {
     double* row;                                   // this ray's n_params x 3 block
     template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
@@ -77,7 +90,9 @@ struct JacSink {
 #define DRTB_MESH_MIN_BLOCKS DRTB_MIN_BLOCKS
 #endif
 //   MESH  : a triangle mesh + BVH is attached (ids are 32-bit, parameters in global memory)
-template <typename R, bool SMALLP, bool QUEUE, bool MESH>
+//   GEN   : the general variant -- SpecularBxDF materials (bxdf.hpp:85-124) and the
+//           per-pixel gradient image; the all-diffuse kernels do not carry that code
+template <typename R, bool SMALLP, bool QUEUE, bool MESH, bool GEN>
 __global__ void __launch_bounds__(kBlock, MESH ? DRTB_MESH_MIN_BLOCKS : DRTB_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ RenderArgs a)
 {
@@ -142,12 +157,20 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
             }
         }
         double acc[3] = {0.0, 0.0, 0.0};
+        double gacc[3] = {0.0, 0.0, 0.0};          // GEN: this lane's share of the pixel's gradient-image value
 
         // sweeps over one record; accumulates this lane's share of the pixel and the gradients
         auto sweep = [&](const auto& rec, int n) {
             R L0[3];
-            if (SMALLP) radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ssink);
-            else        radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, asink);
+            if constexpr (GEN) {
+                PixelSink<SmemSink> ps{ssink, a.gimg_param, gacc};
+                PixelSink<AtomicSink> pa{asink, a.gimg_param, gacc};
+                if (SMALLP) radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ps);
+                else        radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, pa);
+            } else {
+                if (SMALLP) radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ssink);
+                else        radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, asink);
+            }
             acc[0] += double(L0[0]); acc[1] += double(L0[1]); acc[2] += double(L0[2]);       // render.cpp:78
             n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
         };
@@ -174,7 +197,8 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                 const uint64_t base = key * kKeyMul;
                 V3<R> o = {sc.eye[0], sc.eye[1], sc.eye[2]};
                 V3<R> d = camera_ray(sc, x, y, base);
-                n = trace_path(sc, bs, mat, no_bvh, base, 2u, o, d, a.min_bounces, a.absorb, a.max_depth, rec, lit, cnt);
+                n = trace_path<R, MESH, QUEUE ? kQueueDepth : kMaxDepth, GEN>(sc, bs, mat, no_bvh, base, 2u, o, d, a.min_bounces,
+                                                                              a.absorb, a.max_depth, rec, lit, cnt);
                 if (!QUEUE && lit) sweep(rec, n);
             }
             if (QUEUE) {
@@ -195,29 +219,31 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
         if (QUEUE && q_count > 0) drain(q_count);
 
         // pixel_radiance / samples (render.cpp:82): sum the lanes of each pixel
-        if (a.img) {
+        auto write_pixel = [&](double* dst, double* v, bool mean) {
             if (spp >= 32) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) acc[c] = warp_sum(acc[c]);
+                for (int c = 0; c < 3; ++c) v[c] = warp_sum(v[c]);
                 if (lane == 0 && lane_ok) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) a.img[pix * 3 + c] = acc[c] / double(spp);
+                    for (int c = 0; c < 3; ++c) dst[pix * 3 + c] = mean ? v[c] / double(spp) : v[c];
                 }
             } else {
-                double tot[3] = {acc[0], acc[1], acc[2]};
+                double tot[3] = {v[0], v[1], v[2]};
                 for (int j = 1; j < spp; ++j) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        double o = __shfl_down_sync(0xffffffffu, acc[c], j);
+                        double o = __shfl_down_sync(0xffffffffu, v[c], j);
                         if (i0 + j < spp) tot[c] += o;
                     }
                 }
                 if (lane_ok && i0 == 0) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) a.img[pix * 3 + c] = tot[c] / double(spp);
+                    for (int c = 0; c < 3; ++c) dst[pix * 3 + c] = mean ? tot[c] / double(spp) : tot[c];
                 }
             }
-        }
+        };
+        if (a.img) write_pixel(a.img, acc, true);
+        if constexpr (GEN) { if (a.gimg) write_pixel(a.gimg, gacc, false); }
     }
 
     if (SMALLP && want_grad) {
@@ -324,6 +350,9 @@ wf_adjoint(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArg
             for (int c = 0; c < 3; ++c) g0[c] = R(a.seed_scale * (a.seed_img ? a.seed_img[pix * 3 + c] : 1.0));
         }
         double acc[3] = {0.0, 0.0, 0.0};
+        double gacc[3] = {0.0, 0.0, 0.0};                     // gradient image (gimg_param == -1: stays zero)
+        PixelSink<SmemSink> ps{ssink, a.gimg_param, gacc};
+        PixelSink<AtomicSink> pa{asink, a.gimg_param, gacc};
         for (int pass = 0; pass < passes; ++pass) {
             const int i = i0 + pass * 32;
             if (!(lane_ok && i < spp)) continue;
@@ -333,34 +362,36 @@ wf_adjoint(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArg
             const int n = int((st >> 16) & 0xffu);
             const WfRecordView<R, CAP> rec{b.rec_w + p, b.rec_prim + p, a.batch};
             R L0[3];
-            if (SMALLP) radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ssink);
-            else        radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, asink);
+            if (SMALLP) radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ps);
+            else        radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, pa);
             acc[0] += double(L0[0]); acc[1] += double(L0[1]); acc[2] += double(L0[2]);
             n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
         }
-        if (a.img) {
+        auto write_pixel = [&](double* dst, double* v, bool mean) {
             if (spp >= 32) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) acc[c] = warp_sum(acc[c]);
+                for (int c = 0; c < 3; ++c) v[c] = warp_sum(v[c]);
                 if (lane == 0 && lane_ok) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) a.img[pix * 3 + c] = acc[c] / double(spp);
+                    for (int c = 0; c < 3; ++c) dst[pix * 3 + c] = mean ? v[c] / double(spp) : v[c];
                 }
             } else {
-                double tot[3] = {acc[0], acc[1], acc[2]};
+                double tot[3] = {v[0], v[1], v[2]};
                 for (int j = 1; j < spp; ++j) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        double o = __shfl_down_sync(0xffffffffu, acc[c], j);
+                        double o = __shfl_down_sync(0xffffffffu, v[c], j);
                         if (i0 + j < spp) tot[c] += o;
                     }
                 }
                 if (lane_ok && i0 == 0) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) a.img[pix * 3 + c] = tot[c] / double(spp);
+                    for (int c = 0; c < 3; ++c) dst[pix * 3 + c] = mean ? tot[c] / double(spp) : tot[c];
                 }
             }
-        }
+        };
+        if (a.img) write_pixel(a.img, acc, true);
+        if (a.gimg) write_pixel(a.gimg, gacc, false);
     }
     if (SMALLP && want_grad) {
         for (int j = 0; j < P3; ++j) {
@@ -405,8 +436,8 @@ trace_rays_kernel(const __grid_constant__ DevScene<R> sc, const double* __restri
     PathRecord<R, MESH, kMaxDepth> rec;
     bool lit;
     TraceCounters cnt;
-    int nv = trace_path(sc, bs, mat, (flags & DRTB_FLAG_NO_BVH) != 0, keys[i] * kKeyMul, 2u, o, d, min_bounces, absorb,
-                        max_depth, rec, lit, cnt);
+    int nv = trace_path<R, MESH, kMaxDepth, true>(sc, bs, mat, (flags & DRTB_FLAG_NO_BVH) != 0, keys[i] * kKeyMul, 2u, o, d,
+                                                  min_bounces, absorb, max_depth, rec, lit, cnt);
     R L0[3] = {R(0), R(0), R(0)};
     if (lit) {
         const R one[3] = {R(1), R(1), R(1)};
@@ -444,6 +475,7 @@ struct drtb_ctx {
     int sm_count = 0;
     std::string err;
     bool has_scene = false;
+    bool has_specular = false;    // some primitive carries a DRTB_SPECULAR material
     std::vector<drtb_prim> prims;
     std::vector<drtb_material> materials;
     std::vector<double> params;
@@ -457,6 +489,7 @@ struct drtb_ctx {
     double* d_img = nullptr;      size_t img_cap = 0;
     double* d_seed = nullptr;     size_t seed_cap = 0;
     double* d_grad = nullptr;     size_t grad_cap = 0;
+    double* d_gimg = nullptr;     size_t gimg_cap = 0;
     drtb_stats* d_stats = nullptr;
     unsigned long long launches = 0;
     // triangle mesh + BVH (device)
@@ -530,6 +563,8 @@ void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
         const drtb_prim& p = c.prims[i];
         d.type[i] = int8_t(p.type);
         d.color[i] = p.material >= 0 ? c.materials[p.material].color : -1;
+        d.mtype[i] = int8_t(p.material >= 0 ? c.materials[p.material].type : DRTB_DIFFUSE);
+        d.expo[i] = R(p.material >= 0 ? c.materials[p.material].exponent : 0.0);
         d.emis[i] = p.emission;
         if (p.type == DRTB_PLANE) {
             // make_frame(normal), bxdf.hpp:29-41, in double with the reference's own operation order
@@ -589,12 +624,12 @@ int occupancy(drtb_ctx* ctx, K kernel, size_t smem, int& out)
     return DRTB_OK;
 }
 
-template <typename R, bool SMALLP, bool QUEUE, bool MESH>
+template <typename R, bool SMALLP, bool QUEUE, bool MESH, bool GEN>
 int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t smem, long long need_blocks,
                    int P3, bool want_grad, cudaStream_t stream, int& grid_out)
 {
     int per_sm = 0;
-    int rc = occupancy(ctx, render_kernel<R, SMALLP, QUEUE, MESH>, smem, per_sm);
+    int rc = occupancy(ctx, render_kernel<R, SMALLP, QUEUE, MESH, GEN>, smem, per_sm);
     if (rc != DRTB_OK) return rc;
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > need_blocks) grid = need_blocks;
@@ -604,7 +639,7 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
         if (rc != DRTB_OK) return rc;
         a.grad_partial = ctx->d_partial;
     }
-    render_kernel<R, SMALLP, QUEUE, MESH><<<int(grid), kBlock, smem, stream>>>(sc, a);
+    render_kernel<R, SMALLP, QUEUE, MESH, GEN><<<int(grid), kBlock, smem, stream>>>(sc, a);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     grid_out = int(grid);
@@ -612,10 +647,17 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
 }
 
 template <typename R>
-int launch_precision(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, bool smallp, bool queue, bool mesh,
+int launch_precision(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, bool smallp, bool queue, bool mesh, bool gen,
                      size_t smem, long long need_blocks, int P3, bool want_grad, cudaStream_t stream, int& grid)
 {
-#define DRTB_LAUNCH(SP, Q, M) launch_variant<R, SP, Q, M>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid)
+#define DRTB_LAUNCH(SP, Q, M) launch_variant<R, SP, Q, M, false>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid)
+#define DRTB_LAUNCH_GEN(SP, Q) launch_variant<R, SP, Q, false, true>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid)
+    if (gen) {
+        // SpecularBxDF materials and/or a gradient image (analytic scenes; mesh scenes take the wavefront)
+        if (mesh) return fail(ctx, DRTB_ERR_UNSUPPORTED, "specular materials / gradient images on a mesh scene need the wavefront pipeline");
+        if (smallp) return queue ? DRTB_LAUNCH_GEN(true, true) : DRTB_LAUNCH_GEN(true, false);
+        return queue ? DRTB_LAUNCH_GEN(false, true) : DRTB_LAUNCH_GEN(false, false);
+    }
     if (mesh) {
         // mesh scenes: parameters live in global memory; small sets still use the smem gradient columns
         if (smallp) return queue ? DRTB_LAUNCH(true, true, true) : DRTB_LAUNCH(true, false, true);
@@ -624,6 +666,7 @@ int launch_precision(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, bool s
     if (smallp) return queue ? DRTB_LAUNCH(true, true, false) : DRTB_LAUNCH(true, false, false);
     return queue ? DRTB_LAUNCH(false, true, false) : DRTB_LAUNCH(false, false, false);
 #undef DRTB_LAUNCH
+#undef DRTB_LAUNCH_GEN
 }
 
 MeshView mesh_view(const drtb_ctx* ctx)
@@ -670,13 +713,19 @@ int effective_max_depth(const drtb_render_opts* o)
     return o->absorb == 1.0 ? std::max(1, o->min_bounces) : kMaxDepth;
 }
 
+// Optional per-pixel gradient image of one parameter (drtb_render_grad_image).
+struct GradImage {
+    int32_t param = -1;
+    double* d_out = nullptr;             // shard_rows x W x 3 (device)
+};
+
 template <typename R>
 int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opts* o, const double* d_seed, double* d_img,
-                     double* d_grad, drtb_stats* d_stats, cudaStream_t stream);
+                     double* d_grad, drtb_stats* d_stats, const GradImage& gi, cudaStream_t stream);
 
 // Enqueue one render (+ gradient reduction) on `stream`; all pointers device.
 int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed, double* d_img,
-                       double* d_grad, drtb_stats* d_stats, cudaStream_t stream)
+                       double* d_grad, drtb_stats* d_stats, const GradImage& gi, cudaStream_t stream)
 {
     const int W = ctx->camera.width, H = ctx->camera.height;
     const int P = int(ctx->params.size() / 3), P3 = P * 3;
@@ -685,8 +734,8 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     if (want_grad && !d_grad) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_GRAD set but grad is NULL");
     if (want_img && !d_img) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_IMAGE set but img is NULL");
     if (ctx->n_tris > 0 && !ctx->mesh_megakernel)
-        return o->precision == DRTB_F32 ? launch_wavefront<float>(ctx, ctx->sc32, o, d_seed, d_img, d_grad, d_stats, stream)
-                                        : launch_wavefront<double>(ctx, ctx->sc64, o, d_seed, d_img, d_grad, d_stats, stream);
+        return o->precision == DRTB_F32 ? launch_wavefront<float>(ctx, ctx->sc32, o, d_seed, d_img, d_grad, d_stats, gi, stream)
+                                        : launch_wavefront<double>(ctx, ctx->sc64, o, d_seed, d_img, d_grad, d_stats, gi, stream);
     const int cnt = o->shard_count > 1 ? o->shard_count : 1;
     const int rows = shard_rows_impl(H, o->shard_index, cnt, o->band_rows);
 
@@ -697,6 +746,10 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     a.shard_rows = rows; a.seed_scale = o->seed_scale;
     a.params = ctx->d_params; a.seed_img = d_seed; a.img = want_img ? d_img : nullptr;
     a.stats = (o->flags & DRTB_FLAG_STATS) ? d_stats : nullptr;
+    const bool want_gimg = want_grad && gi.d_out != nullptr;
+    a.gimg = want_gimg ? gi.d_out : nullptr;
+    a.gimg_param = want_gimg ? gi.param : -1;
+    const bool gen = ctx->has_specular || want_gimg;
 
     const bool smallp = P <= kSmallP;
     const bool f32 = o->precision == DRTB_F32;
@@ -721,8 +774,8 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
         a.grad_atomic = d_grad;
     }
     int grid = 0;
-    int rc = f32 ? launch_precision<float>(ctx, ctx->sc32, a, smallp, queue, mesh, smem, need, P3, want_grad, stream, grid)
-                 : launch_precision<double>(ctx, ctx->sc64, a, smallp, queue, mesh, smem, need, P3, want_grad, stream, grid);
+    int rc = f32 ? launch_precision<float>(ctx, ctx->sc32, a, smallp, queue, mesh, gen, smem, need, P3, want_grad, stream, grid)
+                 : launch_precision<double>(ctx, ctx->sc64, a, smallp, queue, mesh, gen, smem, need, P3, want_grad, stream, grid);
     if (rc != DRTB_OK) return rc;
     if (want_grad && smallp) {
         reduce_grad_kernel<<<1, 256, 0, stream>>>(ctx->d_partial, int(grid), P3, d_grad);
@@ -735,7 +788,7 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
 // Mesh scenes: the wavefront of wavefront.cuh, batch by batch.
 template <typename R>
 int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opts* o, const double* d_seed, double* d_img,
-                     double* d_grad, drtb_stats* d_stats, cudaStream_t stream)
+                     double* d_grad, drtb_stats* d_stats, const GradImage& gi, cudaStream_t stream)
 {
     const int W = ctx->camera.width, H = ctx->camera.height;
     const int P = int(ctx->params.size() / 3), P3 = P * 3;
@@ -782,6 +835,9 @@ int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opt
     a.params = ctx->d_params; a.seed_img = d_seed; a.img = want_img ? d_img : nullptr;
     a.stats = (o->flags & DRTB_FLAG_STATS) ? d_stats : nullptr;
     a.mesh = mesh_view(ctx);
+    a.gimg = (want_grad && gi.d_out) ? gi.d_out : nullptr;
+    a.gimg_param = a.gimg ? gi.param : -1;
+    a.specular = ctx->has_specular ? 1 : 0;
     if (a.stats) CK(ctx, cudaMemsetAsync(d_stats, 0, sizeof(drtb_stats), stream));
     if (want_grad && !smallp) {
         CK(ctx, cudaMemsetAsync(d_grad, 0, sizeof(double) * P3, stream));
@@ -839,21 +895,25 @@ int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opt
 // gradients from stream `adjoint_seed`.  With a counter-based RNG that is simply
 // a second, gradient-only launch keyed differently.
 int launch_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed, double* d_img,
-                  double* d_grad, drtb_stats* d_stats, cudaStream_t stream)
+                  double* d_grad, drtb_stats* d_stats, const GradImage& gi, cudaStream_t stream)
 {
+    if (gi.d_out) {
+        if (!(o->flags & DRTB_FLAG_GRAD)) return fail(ctx, DRTB_ERR_INVALID, "a gradient image needs DRTB_FLAG_GRAD");
+        if (gi.param < 0 || size_t(gi.param) * 3 >= ctx->params.size()) return fail(ctx, DRTB_ERR_INVALID, "gradient-image parameter index out of range");
+    }
     const bool split = o->adjoint_seed != 0 && (o->flags & DRTB_FLAG_GRAD) && (o->flags & DRTB_FLAG_IMAGE);
     if (!split) {
         drtb_render_opts one = *o;
         if (o->adjoint_seed != 0 && (o->flags & DRTB_FLAG_GRAD)) one.seed = o->adjoint_seed;   // gradient-only call
-        return launch_render_once(ctx, &one, d_seed, d_img, d_grad, d_stats, stream);
+        return launch_render_once(ctx, &one, d_seed, d_img, d_grad, d_stats, gi, stream);
     }
     drtb_render_opts fwd = *o, adj = *o;
     fwd.flags &= ~DRTB_FLAG_GRAD;
     adj.flags &= ~(DRTB_FLAG_IMAGE | DRTB_FLAG_STATS);       // stats describe the image pass
     adj.seed = o->adjoint_seed;
-    int rc = launch_render_once(ctx, &fwd, nullptr, d_img, nullptr, d_stats, stream);
+    int rc = launch_render_once(ctx, &fwd, nullptr, d_img, nullptr, d_stats, GradImage{}, stream);
     if (rc != DRTB_OK) return rc;
-    return launch_render_once(ctx, &adj, d_seed, nullptr, d_grad, nullptr, stream);
+    return launch_render_once(ctx, &adj, d_seed, nullptr, d_grad, nullptr, gi, stream);
 }
 
 } // namespace
@@ -927,7 +987,7 @@ void drtb_destroy(drtb_ctx* ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     cudaFree(ctx->d_params); cudaFree(ctx->d_partial); cudaFree(ctx->d_img);
-    cudaFree(ctx->d_seed); cudaFree(ctx->d_grad); cudaFree(ctx->d_stats); cudaFree(ctx->wf_mem);
+    cudaFree(ctx->d_seed); cudaFree(ctx->d_grad); cudaFree(ctx->d_gimg); cudaFree(ctx->d_stats); cudaFree(ctx->wf_mem);
     free_mesh(ctx);
     delete ctx;
 }
@@ -944,7 +1004,7 @@ int drtb_scene_upload(drtb_ctx* ctx, const drtb_scene* s)
     if (s->n_prims > kMaxPrims)
         return fail(ctx, DRTB_ERR_UNSUPPORTED, "more than 32 analytic primitives is not supported by this build");
     for (int m = 0; m < s->n_materials; ++m) {
-        if (s->materials[m].type != DRTB_DIFFUSE) return fail(ctx, DRTB_ERR_UNSUPPORTED, "only DRTB_DIFFUSE materials are supported");
+        if (s->materials[m].type != DRTB_DIFFUSE && s->materials[m].type != DRTB_SPECULAR) return fail(ctx, DRTB_ERR_INVALID, "unknown material type");
         if (s->materials[m].color < 0 || s->materials[m].color >= s->n_params) return fail(ctx, DRTB_ERR_INVALID, "material colour index out of range");
     }
     for (int i = 0; i < s->n_prims; ++i) {
@@ -960,6 +1020,9 @@ int drtb_scene_upload(drtb_ctx* ctx, const drtb_scene* s)
     ctx->materials.assign(s->materials, s->materials + s->n_materials);
     ctx->params.assign(s->params, s->params + size_t(s->n_params) * 3);
     ctx->camera = s->camera;
+    ctx->has_specular = false;
+    for (const drtb_prim& p : ctx->prims)
+        if (p.material >= 0 && ctx->materials[p.material].type == DRTB_SPECULAR) ctx->has_specular = true;
     fill_dev_scene(ctx->sc64, *ctx);
     fill_dev_scene(ctx->sc32, *ctx);
     int rc = ensure(ctx, ctx->d_params, ctx->params_cap, std::max<size_t>(3, ctx->params.size()));
@@ -1144,8 +1207,11 @@ int32_t drtb_shard_rows(int32_t height, int32_t shard_index, int32_t shard_count
     return shard_rows_impl(height, shard_index, shard_count, band_rows);
 }
 
-int drtb_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* seed_img, double* img,
-                double* grad, drtb_stats* stats)
+namespace {
+
+// drtb_render / drtb_render_grad_image with host buffers
+int render_host(drtb_ctx* ctx, const drtb_render_opts* o, int32_t gparam, const double* seed_img, double* img,
+                double* grad, double* grad_img, drtb_stats* stats)
 {
     if (!ctx) return DRTB_ERR_INVALID;
     int rc = validate_opts(ctx, o);
@@ -1160,6 +1226,11 @@ int drtb_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* seed_img
     if (want_grad && !grad) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_GRAD set but grad is NULL");
     if (want_img && (rc = ensure(ctx, ctx->d_img, ctx->img_cap, std::max<size_t>(npx3, 3))) != DRTB_OK) return rc;
     if (want_grad && (rc = ensure(ctx, ctx->d_grad, ctx->grad_cap, std::max<size_t>(P3, 3))) != DRTB_OK) return rc;
+    GradImage gi;
+    if (grad_img) {
+        if ((rc = ensure(ctx, ctx->d_gimg, ctx->gimg_cap, std::max<size_t>(npx3, 3))) != DRTB_OK) return rc;
+        gi.param = gparam; gi.d_out = ctx->d_gimg;
+    }
     cudaStream_t st = ctx->stream;
     if (seed_img) {
         if ((rc = ensure(ctx, ctx->d_seed, ctx->seed_cap, std::max<size_t>(npx3, 3))) != DRTB_OK) return rc;
@@ -1168,11 +1239,12 @@ int drtb_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* seed_img
     drtb_render_opts oo = *o;
     if (stats) oo.flags |= DRTB_FLAG_STATS;
     CK(ctx, cudaEventRecord(ctx->ev0, st));
-    rc = launch_render(ctx, &oo, seed_img ? ctx->d_seed : nullptr, ctx->d_img, ctx->d_grad, ctx->d_stats, st);
+    rc = launch_render(ctx, &oo, seed_img ? ctx->d_seed : nullptr, ctx->d_img, ctx->d_grad, ctx->d_stats, gi, st);
     if (rc != DRTB_OK) return rc;
     CK(ctx, cudaEventRecord(ctx->ev1, st));
     if (want_img && npx3) CK(ctx, cudaMemcpyAsync(img, ctx->d_img, sizeof(double) * npx3, cudaMemcpyDeviceToHost, st));
     if (want_grad && P3) CK(ctx, cudaMemcpyAsync(grad, ctx->d_grad, sizeof(double) * P3, cudaMemcpyDeviceToHost, st));
+    if (grad_img && npx3) CK(ctx, cudaMemcpyAsync(grad_img, ctx->d_gimg, sizeof(double) * npx3, cudaMemcpyDeviceToHost, st));
     if (stats) CK(ctx, cudaMemcpyAsync(stats, ctx->d_stats, sizeof(drtb_stats), cudaMemcpyDeviceToHost, st));
     CK(ctx, cudaStreamSynchronize(st));
     if (stats) {
@@ -1185,15 +1257,45 @@ int drtb_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* seed_img
     return DRTB_OK;
 }
 
-int drtb_render_device(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed_img, double* d_img,
-                       double* d_grad, drtb_stats* d_stats, void* stream)
+int render_device(drtb_ctx* ctx, const drtb_render_opts* o, const GradImage& gi, const double* d_seed_img, double* d_img,
+                  double* d_grad, drtb_stats* d_stats, void* stream)
 {
     if (!ctx) return DRTB_ERR_INVALID;
     int rc = validate_opts(ctx, o);
     if (rc != DRTB_OK) return rc;
     CK(ctx, cudaSetDevice(ctx->device));
     if ((o->flags & DRTB_FLAG_STATS) && !d_stats) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_STATS set but d_stats is NULL");
-    return launch_render(ctx, o, d_seed_img, d_img, d_grad, d_stats, (cudaStream_t)stream);
+    return launch_render(ctx, o, d_seed_img, d_img, d_grad, d_stats, gi, (cudaStream_t)stream);
+}
+
+} // namespace
+
+int drtb_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* seed_img, double* img,
+                double* grad, drtb_stats* stats)
+{
+    return render_host(ctx, o, -1, seed_img, img, grad, nullptr, stats);
+}
+
+int drtb_render_grad_image(drtb_ctx* ctx, const drtb_render_opts* o, int32_t param, const double* seed_img, double* img,
+                           double* grad, double* grad_img, drtb_stats* stats)
+{
+    if (ctx && !grad_img) return fail(ctx, DRTB_ERR_INVALID, "grad_img is NULL");
+    return render_host(ctx, o, param, seed_img, img, grad, grad_img, stats);
+}
+
+int drtb_render_device(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed_img, double* d_img,
+                       double* d_grad, drtb_stats* d_stats, void* stream)
+{
+    return render_device(ctx, o, GradImage{}, d_seed_img, d_img, d_grad, d_stats, stream);
+}
+
+int drtb_render_grad_image_device(drtb_ctx* ctx, const drtb_render_opts* o, int32_t param, const double* d_seed_img,
+                                  double* d_img, double* d_grad, double* d_grad_img, drtb_stats* d_stats, void* stream)
+{
+    if (ctx && !d_grad_img) return fail(ctx, DRTB_ERR_INVALID, "d_grad_img is NULL");
+    GradImage gi;
+    gi.param = param; gi.d_out = d_grad_img;
+    return render_device(ctx, o, gi, d_seed_img, d_img, d_grad, d_stats, stream);
 }
 
 int drtb_trace_rays(drtb_ctx* ctx, const drtb_render_opts* o, int64_t n, const double* orig, const double* dir,

@@ -42,6 +42,8 @@ struct alignas(16) DevScene {
     int32_t color[kMaxPrims];            // param index of the albedo, -1 = null BxDF
     int32_t emis[kMaxPrims];             // param index of the emission, -1 = no emitter
     int8_t  slot[kMaxPrims];             // scene index -> scan slot
+    int8_t  mtype[kMaxPrims];            // DRTB_DIFFUSE | DRTB_SPECULAR (only read by the SPEC kernels)
+    R       expo[kMaxPrims];             // SpecularBxDF::m_exponent (bxdf.hpp:123)
     int32_t n_prims;
     int32_t n_params;
     // Camera (camera.hpp:51-60), constants folded on the host in double with the
@@ -88,6 +90,8 @@ struct RenderArgs {
     double*  grad_partial;               // gridDim.x x (n_params*3)  (small-P path)
     double*  grad_atomic;                // n_params*3, pre-zeroed     (large-P path)
     drtb_stats* stats;                   // or null
+    double*  gimg;                       // shard_rows x W x 3 gradient image of parameter gimg_param, or null
+    int32_t  gimg_param;                 // -1 = none
     MeshView mesh;                       // n_tris == 0: analytic scene only
 };
 
@@ -100,6 +104,8 @@ struct BlockScene {
     R       param[kMaxParams * 3];       // staged only when n_params <= kMaxParams
     int32_t color[kMaxPrims], emis[kMaxPrims];
     int8_t  type[kMaxPrims];
+    int8_t  mtype[kMaxPrims];
+    R       expo[kMaxPrims];
 };
 
 template <typename R>
@@ -112,6 +118,7 @@ __device__ __forceinline__ void load_block_scene(BlockScene<R>& bs, const DevSce
         bs.frame[i / 6][i % 6] = sc.frame[i / 6][i % 6];
     for (int i = threadIdx.x; i < sc.n_prims; i += blockDim.x) {
         bs.type[i] = sc.type[i]; bs.color[i] = sc.color[i]; bs.emis[i] = sc.emis[i];
+        bs.mtype[i] = sc.mtype[i]; bs.expo[i] = sc.expo[i];
     }
     if (sc.n_params <= kMaxParams)
         for (int i = threadIdx.x; i < sc.n_params * 3; i += blockDim.x) bs.param[i] = R(params[i]);
@@ -270,6 +277,44 @@ __device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, V3<R> tg, V3<R> bt, R u
     return dout;
 }
 
+// ---------------------------------------------------------------------------
+// SpecularBxDF (bxdf.hpp:85-124): sample() draws a half vector around the
+// normal from the two uniforms (theta = acos(sqrt(u^(2/(e+2)))), phi = 2 pi u),
+// flips it to the side of dir_in = -d with reflect(h, n) (vector.hpp:602-606),
+// and returns reflect(dir_in, h) with pdf = (e+2)/(2 pi) cos^(e+1)(theta)
+// sin(theta); operator() re-derives the half vector from (dir_in, dir_out) and
+// returns color * (e+2)/(2 pi) (n.h)^e sqrt(1 - (n.h)^2).  The scatter term of
+// pathtracer.hpp:100-104 is brdf * L * dot(n, dir_out) / pdf, so the record
+// keeps w = pi * lobe * dot(n, dir_out) / pdf and the sweeps, which multiply by
+// rho / pi, need not know which BxDF made the vertex.  (e+2)/(2 pi) is common to
+// lobe and pdf and is cancelled.  cos(acos x) = x, sin(acos x) = sqrt(1 - x^2).
+// Nothing is clamped: a direction below the surface keeps its negative cosine
+// and a lobe argument above 1 (non-unit plane normal) yields NaN, as upstream.
+// ---------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ V3<R> specular_sample(V3<R> n, V3<R> tg, V3<R> bt, V3<R> d, R expo, R u_theta, R u_phi, R& w)
+{
+    const R ct2 = Real<R>::pow(u_theta, Real<R>::div(R(2), expo + R(2)));
+    const R ct = Real<R>::sqrt(ct2), st = Real<R>::sqrt(R(1) - ct2);
+    R sp, cp;
+    Real<R>::sincos2pi(u_phi, &sp, &cp);
+    const R x = cp * st, y = sp * st;
+    V3<R> h = {x * tg.x + y * bt.x + ct * n.x, x * tg.y + y * bt.y + ct * n.y, x * tg.z + y * bt.z + ct * n.z};
+    const V3<R> din = {-d.x, -d.y, -d.z};                              // pathtracer.hpp:101, 109
+    if (dot(h, din) < R(0)) {                                          // bxdf.hpp:114-115
+        const R k2 = R(2) * dot(n, h);
+        h = {k2 * n.x - h.x, k2 * n.y - h.y, k2 * n.z - h.z};
+    }
+    const R k2 = R(2) * dot(h, din);
+    const V3<R> dout = {k2 * h.x - din.x, k2 * h.y - din.y, k2 * h.z - din.z};   // reflect(dir_in, h), :116
+    const R pdf = Real<R>::pow(ct, expo + R(1)) * st;                  // x (e+2)/(2 pi), :117-118
+    const V3<R> hw = normalize(V3<R>{din.x + dout.x, din.y + dout.y, din.z + dout.z});   // :98
+    const R c = dot(n, hw);
+    const R lobe = Real<R>::pow(c, expo) * Real<R>::sqrt(Real<R>::fma(-c, c, R(1)));      // x (e+2)/(2 pi), :99-103
+    w = Real<R>::div(Real<R>::pi() * lobe * dot(n, dout), pdf);
+    return dout;
+}
+
 // Per-path vertex record: what the reference keeps as ~17 heap-allocated tape
 // nodes per segment (vector.hpp:194-213) shrinks to (prim id, w) per vertex;
 // p_v is a function of the depth alone (pathtracer.hpp:130).  Scene indices fit
@@ -340,7 +385,9 @@ struct TraceCounters { uint32_t segments = 0, truncated = 0, bvh_nodes = 0, tri_
 // gradient of the path are exactly zero and the sweeps are skipped).
 // `slot` is the next stream slot (2 after the camera draws).
 // ---------------------------------------------------------------------------
-template <typename R, bool MESH, int CAP>
+// SPEC: the scene has SpecularBxDF materials (per-lane material lookup and the
+// lobe code are compiled in; the all-diffuse kernels do not carry them).
+template <typename R, bool MESH, int CAP, bool SPEC = false>
 __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScene<R>& bs,
                                           const Materials<R, MESH>& mat, bool no_bvh,
                                           uint64_t base, uint32_t slot, V3<R> o, V3<R> d,
@@ -408,7 +455,17 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
         R u_phi   = Real<R>::uniform_fast(stream_draw_base(base, slot + 1));
         slot += 2;
         R w;
-        V3<R> dout = diffuse_sample(nrm, tg, bt, u_theta, u_phi, w);
+        V3<R> dout;
+        bool spec = false;
+        if constexpr (SPEC) spec = !on_mesh && bs.mtype[k] == DRTB_SPECULAR;
+        if (spec) {
+            dout = specular_sample(nrm, tg, bt, d, bs.expo[k], u_theta, u_phi, w);
+            // upstream a NaN/inf weight poisons the path even if it never meets the light (NaN * 0):
+            // such a path must run the sweeps, which then produce the reference's NaN
+            lit |= !(Real<R>::abs(w) < Real<R>::inf());
+        } else {
+            dout = diffuse_sample(nrm, tg, bt, u_theta, u_phi, w);
+        }
         rec.w_[n++] = w;
         const R eps = Real<R>::origin_eps();                // 1e-3, pathtracer.hpp:99
         o = {Real<R>::fma(eps, dout.x, pt.x), Real<R>::fma(eps, dout.y, pt.y), Real<R>::fma(eps, dout.z, pt.z)};

@@ -83,6 +83,7 @@ template <> struct Real<double> {
         const double s = x * rsqrt(x);
         return select(is_nonzero(x), s, 0.0);                    // 0 * inf guard
     }
+    static __device__ __forceinline__ double pow(double a, double b) { return ::pow(a, b); }   // SpecularBxDF only
     // sin/cos(2*pi*u), u in [0, 1).  The reference forms phi = 2*pi*u in double and
     // calls libm cos/sin (bxdf.hpp:74, 48-49).  Here: x = 4u = q + r with q the
     // nearest integer and |r| <= 1/2, i.e. phi = q*pi/2 + r*pi/2 exactly; Taylor
@@ -147,6 +148,7 @@ template <> struct Real<float> {
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));    // MUFU.SQRT, 2^-23 relative
         return r;
     }
+    static __device__ __forceinline__ float pow(float a, float b) { return ::powf(a, b); }
     static __device__ __forceinline__ void sincos2pi(float u, float* s, float* c) { ::sincospif(2.0f * u, s, c); }
     // Top 24 bits of the 31-bit draw: u in [0, 1 - 2^-24], never 1.0f
     // (float(k/2147483647.0) would round the top ~64 draws to 1 and make

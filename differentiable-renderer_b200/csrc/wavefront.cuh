@@ -73,6 +73,9 @@ struct WfArgs {
     double*  grad_partial;
     double*  grad_atomic;
     drtb_stats* stats;
+    double*  gimg;                            // gradient image of parameter gimg_param (or null)
+    int32_t  gimg_param;                      // -1 = none
+    int32_t  specular;                        // some analytic primitive has a SpecularBxDF
     MeshView mesh;
 };
 
@@ -280,9 +283,19 @@ wf_traverse_brute(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
     if (a.stats) atomicAdd((unsigned long long*)&a.stats->tri_tests, (unsigned long long)n_tests);
 }
 
+// Out of line: the lobe code (three pow calls) must not raise the register count of the
+// all-diffuse shade stage, which runs at 4 blocks of 256 threads per SM.
+template <typename R>
+__device__ __noinline__ void wf_specular_sample(const V3<R>* in /* n, tg, bt, d */, R expo, R u_theta, R u_phi, R* out /* dout.xyz, w */)
+{
+    R w;
+    const V3<R> dout = specular_sample(in[0], in[1], in[2], in[3], expo, u_theta, u_phi, w);
+    out[0] = dout.x; out[1] = dout.y; out[2] = dout.z; out[3] = w;
+}
+
 // ---- the vertex: record, sample, next segment (Pathtracer::scatter, pathtracer.hpp:91-115)
 template <typename R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 wf_shade(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArgs a, const WfBuffers<R> b)
 {
     if (b.alive_count[a.depth] == 0) return;
@@ -336,7 +349,16 @@ wf_shade(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArgs 
                     const R u_phi = Real<R>::uniform_fast(stream_draw_base(base, slot + 1));
                     slot += 2;
                     R w;
-                    const V3<R> dout = diffuse_sample(nrm, tg, bt, u_theta, u_phi, w);
+                    V3<R> dout;
+                    // SpecularBxDF (bxdf.hpp:85-124) on analytic primitives; triangles are diffuse (drtb.h)
+                    if (a.specular && k < a.mesh.n_prims && bs.mtype[k] == DRTB_SPECULAR) {
+                        const V3<R> in[4] = {nrm, tg, bt, d};
+                        R out[4];
+                        wf_specular_sample<R>(in, bs.expo[k], u_theta, u_phi, out);
+                        dout = {out[0], out[1], out[2]}; w = out[3];
+                        lit |= !(Real<R>::abs(w) < Real<R>::inf());   // NaN * 0 = NaN upstream: see trace_path
+                    } else
+                        dout = diffuse_sample(nrm, tg, bt, u_theta, u_phi, w);
                     b.rec_w[(size_t)n * a.batch + p] = w;
                     ++n;
                     const R eps = Real<R>::origin_eps();          // 1e-3, pathtracer.hpp:99

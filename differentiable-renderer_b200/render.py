@@ -94,6 +94,24 @@ class Context:
                                           _ptr(grad), C.byref(st)))
         return (img, grad, st) if stats else (img, grad)
 
+    def render_grad_image(self, opts: abi.RenderOpts, param, seed_img: Optional[np.ndarray] = None):
+        """drtb_render_grad_image: (img, grad, grad_img[rows,W,3]) where grad_img is
+        parameter `param`'s (a `Param` or an index) share of the gradient per pixel
+        (README.md:138-145)."""
+        assert self.scene is not None, "upload a scene first"
+        k = param if isinstance(param, int) else param.index
+        cam = self.scene.camera
+        rows = shard_rows(cam.height, opts.shard_index, max(1, opts.shard_count), max(1, opts.band_rows))
+        img = np.empty((rows, cam.width, 3), dtype=np.float64) if opts.flags & abi.FLAG_IMAGE else None
+        grad = np.empty((self.scene.n_params, 3), dtype=np.float64)
+        gimg = np.empty((rows, cam.width, 3), dtype=np.float64)
+        if seed_img is not None:
+            seed_img = np.ascontiguousarray(seed_img, dtype=np.float64)
+            assert seed_img.shape == (rows, cam.width, 3)
+        self._check(self._lib.drtb_render_grad_image(self._h, C.byref(opts), int(k), _ptr(seed_img), _ptr(img),
+                                                     _ptr(grad), _ptr(gimg), None))
+        return img, grad, gimg
+
     def render_host_ptrs(self, opts: abi.RenderOpts, seed_ptr: int, img_ptr: int, grad_ptr: int,
                          st: Optional[abi.Stats] = None):
         """drtb_render on caller-owned (e.g. pinned) host memory, by address."""

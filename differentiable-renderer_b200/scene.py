@@ -37,6 +37,15 @@ class DiffuseBxDF:
 
 
 @dataclass
+class SpecularBxDF:
+    """SpecularBxDF(color, exponent), bxdf.hpp:85-124: normalised Blinn-Phong
+    lobe, half-vector sampling."""
+    color: Param
+    exponent: float
+    index: int = -1
+
+
+@dataclass
 class AreaEmitter:
     """AreaEmitter(emission), emitter.hpp:15-25."""
     emission: Param
@@ -147,7 +156,7 @@ class SceneDesc:
         self.params.append(p)
         return p.index
 
-    def _material_index(self, m: DiffuseBxDF) -> int:
+    def _material_index(self, m) -> int:
         for q in self.materials:
             if q is m:
                 return q.index
@@ -174,9 +183,10 @@ class SceneDesc:
                 pr.v[j] = float(vals[j])
         mats = (abi.Material * max(1, len(self.materials)))()
         for m in self.materials:
-            mats[m.index].type = abi.DIFFUSE
+            spec = isinstance(m, SpecularBxDF)
+            mats[m.index].type = abi.SPECULAR if spec else abi.DIFFUSE
             mats[m.index].color = m.color.index
-            mats[m.index].exponent = 0.0
+            mats[m.index].exponent = float(m.exponent) if spec else 0.0
         mesh = self.mesh
         if mesh is not None:                      # register what the mesh references before sizing params[]
             if isinstance(mesh.albedo, Param):
@@ -253,6 +263,20 @@ def cornell_box(width: int, height: int, *, red=(0.5, 0, 0), green=(0, 0.5, 0),
     # register parameters in declaration order red, green, white, emission
     for p in (red, green, white, emission):
         sc._param_index(p)
+    return sc
+
+
+def specular_box(width: int, height: int, *, exponent_ball: float = 20.0, exponent_wall: float = 4.0,
+                 gloss=(0.8, 0.7, 0.6)) -> SceneDesc:
+    """The Cornell box of src/render.cpp:26-65 with the reference's SpecularBxDF
+    (bxdf.hpp:85-124; src/render.cpp:35 builds one and never attaches it) on the
+    front sphere and on the back wall, sharing one differentiable tint `gloss`.
+    Everything else, including the scene order, is the Cornell box's."""
+    sc = cornell_box(width, height)
+    tint = Param(np.asarray(gloss, dtype=np.float64), "gloss")
+    sc.shapes[0].bxdf = SpecularBxDF(tint, exponent_ball)          # sphere_front
+    sc.shapes[4].bxdf = SpecularBxDF(tint, exponent_wall)          # back_plane, unit normal
+    sc._param_index(tint)
     return sc
 
 

@@ -77,9 +77,9 @@ public:
     const Vector<T, 3, true>& color() const override { return albedo_; }
 };
 
-// Normalised Blinn-Phong-like lobe around the half vector.  Declared so that
-// programs written against the reference keep compiling (src/render.cpp:35
-// instantiates one and never uses it); the GPU path reports it as unsupported.
+// Normalised Blinn-Phong-like lobe around the half vector (reference
+// bxdf.hpp:85-124).  The CUDA path samples and evaluates it on the device
+// (DRTB_SPECULAR, csrc/path.cuh specular_sample); these host methods mirror it.
 template <typename T>
 class SpecularBxDF : public BxDF<T> {
     Vector<T, 3, true> tint_;

@@ -55,15 +55,15 @@ FlatScene<T> flatten(const Scene<T>& scene)
         p.material = -1;
         p.emission = -1;
         if (const BxDF<T>* b = s->bxdf()) {
-            if (b->kind() != BxDFKind::Diffuse)
-                throw std::runtime_error("drt::gpu: only DiffuseBxDF is supported by the GPU path");
             int m = -1;
             for (std::size_t i = 0; i < seen.size(); ++i)
                 if (seen[i] == b) m = int(i);
             if (m < 0) {
                 m = int(seen.size());
                 seen.push_back(b);
-                f.materials.push_back(drtb_material{DRTB_DIFFUSE, f.param_index(b->color()), 0.0});
+                const bool spec = b->kind() == BxDFKind::Specular;
+                f.materials.push_back(drtb_material{spec ? DRTB_SPECULAR : DRTB_DIFFUSE, f.param_index(b->color()),
+                                                    spec ? b->exponent() : 0.0});
             }
             p.material = m;
         }

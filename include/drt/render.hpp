@@ -10,6 +10,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <stdexcept>
 #include <vector>
 #include "camera.hpp"
 #include "gpu.hpp"
@@ -28,6 +29,10 @@ struct RenderOptions {
     int precision = DRTB_F64;                      // DRTB_F64 (parity) | DRTB_F32 (throughput)
     int device = 0;
     drtb_stats* stats = nullptr;
+    // Per-pixel gradient image (README.md:138-145): if grad_image != nullptr it receives, per
+    // pixel, the share of grad_image_of.grad() that the pixel's samples contributed (w*h entries).
+    Vector<double, 3>* grad_image = nullptr;
+    const void* grad_image_of = nullptr;           // &parameter (any Vector<T,3,true> handle of it)
 };
 
 static_assert(sizeof(Vector<double, 3>) == 3 * sizeof(double), "Vector<double,3> must be 3 packed doubles");
@@ -51,13 +56,27 @@ void render(const Scene<T>& scene, const Camera<T>& cam, const Pathtracer<T>& tr
     o.seed_scale = opt.seed_scale;
     o.adjoint_seed = opt.adjoint_stream;
     std::vector<double> grad(flat.params.size(), 0.0);
+    int gparam = -1;
+    if (opt.grad_image) {
+        if (!opt.gradients || !opt.grad_image_of) throw std::runtime_error("drt::render: grad_image needs gradients and grad_image_of");
+        const auto& h = *static_cast<const Vector<T, 3, true>*>(opt.grad_image_of);
+        for (std::size_t k = 0; k < flat.handles.size(); ++k)
+            if (flat.handles[k].id() == h.id()) gparam = int(k);
+        if (gparam < 0) throw std::runtime_error("drt::render: grad_image_of is not a parameter of this scene");
+    }
     {
         gpu::Device& dev = gpu::device(opt.device);
         std::lock_guard<std::mutex> g(dev.lock);
         dev.sync(flat, c);
-        dev.check("drtb_render",
-                  drtb_render(dev.ctx(), &o, reinterpret_cast<const double*>(opt.seed_image),
-                              reinterpret_cast<double*>(img), opt.gradients ? grad.data() : nullptr, opt.stats));
+        if (opt.grad_image)
+            dev.check("drtb_render_grad_image",
+                      drtb_render_grad_image(dev.ctx(), &o, gparam, reinterpret_cast<const double*>(opt.seed_image),
+                                             reinterpret_cast<double*>(img), grad.data(),
+                                             reinterpret_cast<double*>(opt.grad_image), opt.stats));
+        else
+            dev.check("drtb_render",
+                      drtb_render(dev.ctx(), &o, reinterpret_cast<const double*>(opt.seed_image),
+                                  reinterpret_cast<double*>(img), opt.gradients ? grad.data() : nullptr, opt.stats));
     }
     if (!opt.gradients) return;
     for (std::size_t k = 0; k < flat.handles.size(); ++k) {

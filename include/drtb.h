@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DRTB_ABI_VERSION 1
+#define DRTB_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 #define DRTB_OK                 0
@@ -51,7 +51,12 @@ extern "C" {
                                        (shape.hpp:58-59)                        */
 
 /* BxDF<T> subclasses, include/drt/bxdf.hpp:56-124 */
-#define DRTB_DIFFUSE  0             /* DiffuseBxDF(color)                      */
+#define DRTB_DIFFUSE  0             /* DiffuseBxDF(color), bxdf.hpp:56-83      */
+#define DRTB_SPECULAR 1             /* SpecularBxDF(color, exponent),
+                                       bxdf.hpp:85-124: half-vector sampling of a
+                                       normalised Blinn-Phong lobe, reflect()
+                                       (vector.hpp:602-606); direction-dependent
+                                       BRDF value, the same two draws per vertex */
 
 typedef struct drtb_prim {
     int32_t type;                   /* DRTB_SPHERE | DRTB_PLANE                */
@@ -66,11 +71,12 @@ typedef struct drtb_prim {
                                        priority (pathtracer.hpp:78-87)         */
 
 typedef struct drtb_material {
-    int32_t type;                   /* DRTB_DIFFUSE                            */
+    int32_t type;                   /* DRTB_DIFFUSE | DRTB_SPECULAR            */
     int32_t color;                  /* index into params[] of the albedo RGB
                                        (bxdf.hpp:59-60); shapes sharing one
                                        Vector<T,3,true> share one index         */
-    double  exponent;               /* reserved (SpecularBxDF, bxdf.hpp:88-91) */
+    double  exponent;               /* SpecularBxDF::m_exponent (bxdf.hpp:88-91);
+                                       ignored for DRTB_DIFFUSE                */
 } drtb_material;                    /* 16 bytes                                */
 
 /* Camera<T>, include/drt/camera.hpp:13-37 (after look_at) */
@@ -228,6 +234,26 @@ int drtb_render(drtb_ctx* ctx, const drtb_render_opts* opts,
 int drtb_render_device(drtb_ctx* ctx, const drtb_render_opts* opts,
                        const double* d_seed_img, double* d_img, double* d_grad,
                        drtb_stats* d_stats, void* stream);
+
+/* drtb_render plus the PER-PIXEL gradient image of ONE parameter (the figure of
+ * README.md:138-145, "gradients of the pixel colors with respect to the
+ * parameter controlling the color of the left wall"): the same adjoint sweep,
+ * with parameter `param`'s contributions additionally summed per pixel.
+ *   grad_img : shard_rows*W*3 doubles,
+ *              grad_img[(y*W + x)*3 + c] = sum over the pixel's samples of
+ *              seed_c * d radiance_c / d params[param][c]   (seed as in
+ *              drtb_render; with seed_scale = 1/spp and no seed_img this is
+ *              d pixel_c / d param_c).  Summed over all pixels it equals
+ *              grad[param].
+ * Needs DRTB_FLAG_GRAD; img / grad as in drtb_render. */
+int drtb_render_grad_image(drtb_ctx* ctx, const drtb_render_opts* opts, int32_t param,
+                           const double* seed_img, double* img, double* grad,
+                           double* grad_img, drtb_stats* stats);
+
+/* Same with DEVICE buffers on `stream` (asynchronous, see drtb_render_device). */
+int drtb_render_grad_image_device(drtb_ctx* ctx, const drtb_render_opts* opts, int32_t param,
+                                  const double* d_seed_img, double* d_img, double* d_grad,
+                                  double* d_grad_img, drtb_stats* d_stats, void* stream);
 
 /* Batch of explicit rays: replaces Pathtracer<T>::trace(scene, orig, dir)
  * (pathtracer.hpp:121-136) called from user code, plus radiance.backward().

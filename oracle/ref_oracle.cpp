@@ -140,9 +140,14 @@ struct World {
         }
         for (int m = 0; m < s.n_materials; ++m) {
             const drtb_material& mm = s.materials[m];
-            if (mm.type != DRTB_DIFFUSE || mm.color < 0 || mm.color >= s.n_params)
+            if (mm.color < 0 || mm.color >= s.n_params)
                 throw std::runtime_error("bad material");
-            materials.push_back(std::make_shared<DiffuseBxDF<T>>(params[mm.color]));
+            if (mm.type == DRTB_DIFFUSE)
+                materials.push_back(std::make_shared<DiffuseBxDF<T>>(params[mm.color]));
+            else if (mm.type == DRTB_SPECULAR)           // the reference's own SpecularBxDF, bxdf.hpp:85-124
+                materials.push_back(std::make_shared<SpecularBxDF<T>>(params[mm.color], mm.exponent));
+            else
+                throw std::runtime_error("bad material");
         }
         for (int i = 0; i < s.n_prims; ++i) {
             const drtb_prim& p = s.prims[i];
@@ -203,11 +208,15 @@ extern "C" {
 // Rows are written compactly in increasing y, exactly as drtb_render does.
 // rand_mode 0: counter stream (drtb.h); 1: as-shipped sequential glibc rand()
 // (single thread, loop order of src/render.cpp:72-76).  Returns 0 or -1.
-int drt_ref_render_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drtb_render_opts* o,
-                        const double* seed_img, double* img, double* grad,
+// gimg != nullptr: additionally the per-pixel gradient image of parameter gparam
+// (the README.md:138-145 figure): every pixel's samples back-propagate into
+// zeroed grad() accumulators, which are read and added to the running totals.
+int drt_ref_render_gimg(const drtb_scene* s, const drtb_mesh* mesh, const drtb_render_opts* o,
+                        const double* seed_img, double* img, double* grad, int gparam, double* gimg,
                         int n_threads, int rand_mode, uint64_t* draws_out)
 {
     if (mesh && mesh->n_triangles == 0) mesh = nullptr;
+    if (gimg && (gparam < 0 || gparam >= s->n_params)) return -1;
     try {
         const int W = s->camera.width, H = s->camera.height, spp = o->spp;
         std::vector<int> rows;
@@ -235,6 +244,7 @@ int drt_ref_render_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drtb_r
             Pathtracer<T> tracer(o->absorb, size_t(o->min_bounces));
             g_libc = rand_mode;
             g_draws = 0;
+            std::vector<double> gtot(size_t(P) * 3, 0.0);   // gimg mode: totals over finished pixels
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 1)
 #endif
@@ -259,11 +269,19 @@ int drt_ref_render_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drtb_r
                     if (img)
                         for (int c = 0; c < 3; ++c)
                             img[(r * W + x) * 3 + c] = px[c];
+                    if (gimg) {
+                        for (int c = 0; c < 3; ++c)
+                            gimg[(r * W + x) * 3 + c] = w.params[gparam].grad()[c];
+                        for (int k = 0; k < P; ++k) {
+                            for (int c = 0; c < 3; ++c) gtot[size_t(k) * 3 + c] += w.params[k].grad()[c];
+                            w.params[k].grad() = Vector<T, 3>(0);
+                        }
+                    }
                 }
             }
             for (int k = 0; k < P; ++k)
                 for (int c = 0; c < 3; ++c)
-                    gsum[(size_t(tid) * P + k) * 3 + c] = w.params[k].grad()[c];
+                    gsum[(size_t(tid) * P + k) * 3 + c] = w.params[k].grad()[c] + gtot[size_t(k) * 3 + c];
             draws += g_draws;
         }
         if (grad) {
@@ -278,6 +296,13 @@ int drt_ref_render_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drtb_r
     } catch (...) {
         return -1;
     }
+}
+
+int drt_ref_render_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drtb_render_opts* o,
+                        const double* seed_img, double* img, double* grad,
+                        int n_threads, int rand_mode, uint64_t* draws_out)
+{
+    return drt_ref_render_gimg(s, mesh, o, seed_img, img, grad, -1, nullptr, n_threads, rand_mode, draws_out);
 }
 
 int drt_ref_render(const drtb_scene* s, const drtb_render_opts* o,

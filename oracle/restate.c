@@ -174,37 +174,87 @@ static int prim_color(const drtb_scene* s, const drtb_mesh* m, int64_t k)
     if (k < s->n_prims) return s->prims[k].material >= 0 ? s->materials[s->prims[k].material].color : -1;
     return m->color ? m->color[k - s->n_prims] : -1;
 }
+/* SpecularBxDF exponent of an analytic primitive, or -1 for DiffuseBxDF (triangles are diffuse, drtb.h) */
+static double prim_specular(const drtb_scene* s, int64_t k)
+{
+    if (k >= s->n_prims || s->prims[k].material < 0) return -1.0;
+    const drtb_material* m = &s->materials[s->prims[k].material];
+    return m->type == DRTB_SPECULAR ? m->exponent : -1.0;
+}
 static int prim_emission(const drtb_scene* s, const drtb_mesh* m, int64_t k)
 {
     if (k < s->n_prims) return s->prims[k].emission;
     return m->emission ? m->emission[k - s->n_prims] : -1;
 }
 
-/* ---- DiffuseBxDF::sample, bxdf.hpp:69-79 with make_frame :29-41 and
- *      angle_to_dir :43-52 ------------------------------------------------- */
+/* make_frame, bxdf.hpp:29-41 (normal used RAW) */
+static void make_frame(v3 n, v3* tangent, v3* bitangent)
+{
+    v3 e1 = {1, 0, 0}, e2 = {0, 1, 0};
+    if (fabs(dot3(e1, n)) < fabs(dot3(e2, n)))
+        *tangent = normalize3(sub3(e1, mul3(n, dot3(e1, n))));
+    else
+        *tangent = normalize3(sub3(e2, mul3(n, dot3(e2, n))));
+    *bitangent = normalize3(cross3(n, *tangent));
+}
+
+/* angle_to_dir, bxdf.hpp:43-52 */
+static v3 angle_to_dir(double theta, double phi, v3 tangent, v3 bitangent, v3 n)
+{
+    double x = cos(phi) * sin(theta);
+    double y = sin(phi) * sin(theta);
+    double z = cos(theta);
+    return add3(add3(mul3(tangent, x), mul3(bitangent, y)), mul3(n, z));
+}
+
+/* ---- DiffuseBxDF::sample, bxdf.hpp:69-79 ---------------------------------- */
 static v3 diffuse_sample(stream_t* rng, v3 n, double* pdf)
 {
     double theta = asin(sqrt(uniform(rng)));
     double phi = 2 * PI * uniform(rng);
-    v3 e1 = {1, 0, 0}, e2 = {0, 1, 0}, tangent;
-    if (fabs(dot3(e1, n)) < fabs(dot3(e2, n)))
-        tangent = normalize3(sub3(e1, mul3(n, dot3(e1, n))));
-    else
-        tangent = normalize3(sub3(e2, mul3(n, dot3(e2, n))));
-    v3 bitangent = normalize3(cross3(n, tangent));
-    double x = cos(phi) * sin(theta);
-    double y = sin(phi) * sin(theta);
-    double z = cos(theta);
-    v3 dir = add3(add3(mul3(tangent, x), mul3(bitangent, y)), mul3(n, z));
+    v3 tangent, bitangent;
+    make_frame(n, &tangent, &bitangent);
+    v3 dir = angle_to_dir(theta, phi, tangent, bitangent, n);
     *pdf = cos(theta) / PI;
     return dir;
+}
+
+/* reflect(), vector.hpp:602-606: -v + 2*dot(n, v)*n */
+static v3 reflect3(v3 v, v3 n)
+{
+    return add3(mul3(v, -1.0), mul3(n, 2 * dot3(n, v)));
+}
+
+/* ---- SpecularBxDF::sample, bxdf.hpp:107-120 -------------------------------- */
+static v3 specular_sample(stream_t* rng, v3 n, v3 dir_in, double e, double* pdf)
+{
+    double theta = acos(sqrt(pow(uniform(rng), 2 / (e + 2))));
+    double phi = 2 * PI * uniform(rng);
+    v3 tangent, bitangent;
+    make_frame(n, &tangent, &bitangent);
+    v3 halfway = angle_to_dir(theta, phi, tangent, bitangent, n);
+    if (dot3(halfway, dir_in) < 0)
+        halfway = reflect3(halfway, n);
+    v3 dir = reflect3(dir_in, halfway);
+    *pdf = (e + 2) / (2 * PI) * pow(cos(theta), e + 1) * sin(theta);
+    return dir;
+}
+
+/* ---- SpecularBxDF::operator(), bxdf.hpp:93-105: the scalar in front of m_color */
+static double specular_factor(v3 n, v3 dir_in, v3 dir_out, double e)
+{
+    v3 halfway = normalize3(add3(dir_in, dir_out));
+    double cos_theta = dot3(n, halfway);
+    double sin_theta = sqrt(1 - cos_theta * cos_theta);
+    return (e + 2) / (2 * PI) * pow(cos_theta, e) * sin_theta;
 }
 
 /* ---- one path: Pathtracer::trace/scatter, pathtracer.hpp:91-136, unrolled
  *      from recursion into a vertex list, then the tape's backward
  *      (vector.hpp:418-486) as two sweeps -------------- */
 
-typedef struct { int64_t prim; double p, cosn, pdf; } vertex_t;
+/* is_spec == 0: DiffuseBxDF (brdf = color/pi); else SpecularBxDF with brdf = spec * color */
+typedef struct { int64_t prim; double p, cosn, pdf, spec; int is_spec; } vertex_t;
 
 typedef struct {
     vertex_t* v; int n, cap;
@@ -239,11 +289,11 @@ static void trace_path(const drtb_scene* s, const drtb_mesh* mesh, const drtb_re
             if (uniform(rng) < absorb) break;
             p = 1 - absorb;
         }
-        v3 pt, n;
+        v3 pt = {0, 0, 0}, n = {0, 0, 0};
         int64_t k = raycast(s, mesh, o, d, &pt, &n);
         cnt->segments++;
         if (k < 0) break;                                /* :134-135 */
-        vertex_t vx = {k, p, 0.0, 1.0};
+        vertex_t vx = {k, p, 0.0, 1.0, 0.0, 0};
         if (prim_color(s, mesh, k) < 0) {
             /* null BxDF: dir_out = 0, pdf = 1, brdf = 0 (pathtracer.hpp:25-26,
              * 38-39): every deeper term is multiplied by 0, so the path ends
@@ -252,7 +302,16 @@ static void trace_path(const drtb_scene* s, const drtb_mesh* mesh, const drtb_re
             break;
         }
         double pdf;
-        v3 dout = diffuse_sample(rng, n, &pdf);          /* :106-109 */
+        v3 dout;
+        const double e = prim_specular(s, k);
+        if (e >= 0) {
+            v3 dir_in = mul3(d, -1.0);                   /* -dir_in, :101, 109 */
+            dout = specular_sample(rng, n, dir_in, e, &pdf);
+            vx.spec = specular_factor(n, dir_in, dout, e);   /* eval_bxdf, :100-101 */
+            vx.is_spec = 1;
+        } else {
+            dout = diffuse_sample(rng, n, &pdf);         /* :106-109 */
+        }
         vx.cosn = dot3(n, dout);                         /* :103 */
         vx.pdf = pdf;
         push_vertex(b, vx);
@@ -278,7 +337,8 @@ static void trace_path(const drtb_scene* s, const drtb_mesh* mesh, const drtb_re
             double diffuse = 0.0;
             if (colp >= 0) {
                 double rho = s->params[3*colp + c];
-                diffuse = 0.0 + (((rho / PI) * L[3*(v+1)+c]) * vx->cosn) / vx->pdf;
+                double brdf = vx->is_spec ? vx->spec * rho : rho / PI;
+                diffuse = 0.0 + ((brdf * L[3*(v+1)+c]) * vx->cosn) / vx->pdf;
             }
             L[3*v+c] = (E + diffuse) / vx->p;
         }
@@ -300,10 +360,11 @@ static void trace_path(const drtb_scene* s, const drtb_mesh* mesh, const drtb_re
                 int col = colp;
                 double g2 = gp / vx->pdf;                /* ScalarDivBackward (/pdf) */
                 double g3 = vx->cosn * g2;               /* ScalarMulBackward (*cos) */
-                /* MulBackward lhs: brdf.backward(radiance * g3); brdf = color/pi */
-                grad[3*col + c] += (L[3*(v+1)+c] * g3) / PI;
+                const int is_spec = vx->is_spec;
+                /* MulBackward lhs: brdf.backward(radiance * g3); brdf = color/pi or factor*color */
+                grad[3*col + c] += is_spec ? vx->spec * (L[3*(v+1)+c] * g3) : (L[3*(v+1)+c] * g3) / PI;
                 /* MulBackward rhs: radiance.backward(brdf * g3) */
-                g[c] = (s->params[3*col + c] / PI) * g3;
+                g[c] = (is_spec ? vx->spec * s->params[3*col + c] : s->params[3*col + c] / PI) * g3;
             } else {
                 g[c] = 0.0;
             }
@@ -336,11 +397,15 @@ static int row_in_shard(int y, const drtb_render_opts* o)
 
 /* The pixel loop, src/render.cpp:72-86, gradient seed per SAMPLE, not divided
  * by spp or pdf.  Same contract as drtb_render. */
-int drt_oracle_render_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drtb_render_opts* o,
+/* gimg != NULL: additionally the per-pixel gradient image of parameter gparam
+ * (drtb_render_grad_image): each pixel's samples accumulate into a zeroed
+ * scratch gradient that is then added to the totals. */
+int drt_oracle_render_gimg(const drtb_scene* s, const drtb_mesh* mesh, const drtb_render_opts* o,
                            const double* seed_img, double* img, double* grad,
-                           int n_threads, drtb_stats* stats)
+                           int gparam, double* gimg, int n_threads, drtb_stats* stats)
 {
     if (mesh && mesh->n_triangles == 0) mesh = NULL;
+    if (gimg && (gparam < 0 || gparam >= s->n_params)) return -1;
     const int W = s->camera.width, H = s->camera.height, spp = o->spp;
     const int P = s->n_params;
     int* rows = (int*)malloc(sizeof(int) * (size_t)(H > 0 ? H : 1));
@@ -363,6 +428,7 @@ int drt_oracle_render_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drt
         path_buf buf; memset(&buf, 0, sizeof buf);
         counters_t cnt = {0, 0};
         double* g = gsum + (size_t)tid * P * 3;
+        double* gpix = gimg ? (double*)calloc((size_t)P * 3 + 1, sizeof(double)) : NULL;
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 1)
 #endif
@@ -380,15 +446,20 @@ int drt_oracle_render_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drt
                     v3 dir = camera_sample(&s->camera, x, y, &rng);
                     double L[3];
                     trace_path(s, mesh, o, &rng, eye, dir, &buf, L,
-                               want_grad ? seed : NULL, g, &cnt);
+                               want_grad ? seed : NULL, gpix ? gpix : g, &cnt);
                     for (int c = 0; c < 3; ++c) acc[c] += L[c] / 1.0;   /* /pdf, pdf = 1 */
+                }
+                if (gpix) {
+                    for (int c = 0; c < 3; ++c)
+                        gimg[((size_t)r * W + x) * 3 + c] = gpix[3*gparam + c];
+                    for (int j = 0; j < P * 3; ++j) { g[j] += gpix[j]; gpix[j] = 0.0; }
                 }
                 if (img)
                     for (int c = 0; c < 3; ++c)
                         img[((size_t)r * W + x) * 3 + c] = acc[c] / (double)spp;
             }
         }
-        free(buf.v); free(buf.L);
+        free(buf.v); free(buf.L); free(gpix);
         segments += cnt.segments; lit += cnt.lit;
     }
     if (grad)
@@ -405,6 +476,13 @@ int drt_oracle_render_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drt
     }
     free(gsum); free(rows);
     return 0;
+}
+
+int drt_oracle_render_mesh(const drtb_scene* s, const drtb_mesh* mesh, const drtb_render_opts* o,
+                           const double* seed_img, double* img, double* grad,
+                           int n_threads, drtb_stats* stats)
+{
+    return drt_oracle_render_gimg(s, mesh, o, seed_img, img, grad, -1, NULL, n_threads, stats);
 }
 
 int drt_oracle_render(const drtb_scene* s, const drtb_render_opts* o,

@@ -128,7 +128,11 @@ int main(int argc, char**)
     CHECK(flat.prims[2].material == -1 && flat.prims[2].emission == 1 && flat.params[1] == 0.25);
     auto spec = std::make_shared<SpecularBxDF<double>>(albedo, 30);
     Sphere<double> s2(V{0, 0, 3}, 1, spec);
-    Scene<double> bad_scene{&s2};
+    Scene<double> glossy_scene{&s2, &p0};          // SpecularBxDF flattens to DRTB_SPECULAR + its exponent
+    auto gflat = gpu::flatten(glossy_scene);
+    CHECK(gflat.materials.size() == 2 && gflat.materials[0].type == DRTB_SPECULAR && gflat.materials[0].exponent == 30);
+    CHECK(gflat.materials[1].type == DRTB_DIFFUSE && gflat.materials[0].color == gflat.materials[1].color);
+    Scene<double> bad_scene{&s2, nullptr};
     threw = false;
     try { gpu::flatten(bad_scene); } catch (const std::runtime_error&) { threw = true; }
     CHECK(threw);

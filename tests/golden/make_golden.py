@@ -30,8 +30,31 @@ CASES = {
 }
 
 
+def specular_and_grad_image():
+    """The reference's own SpecularBxDF (bxdf.hpp:85-124) in the Cornell box, and the
+    per-pixel gradient image of one parameter (README.md:138-145)."""
+    for name, (W, H, spp, mb, ab, seed) in {"specbox_40x28_6spp_b4_p1": (40, 28, 6, 4, 1.0, 2),
+                                            "specbox_40x28_6spp_b1_p05": (40, 28, 6, 1, 0.5, 2),
+                                            "specbox_24x16_40spp_b3_p03": (24, 16, 40, 3, 0.3, 5)}.items():
+        scene = drt.specular_box(W, H)
+        img, grad, gimg = oracle_lib.ref_render(scene, drt.make_opts(spp, mb, ab, seed=seed), grad_image_of=4)
+        assert np.isfinite(img).all() and np.isfinite(grad).all()
+        np.savez_compressed(HERE / f"{name}.npz", img=img, grad=grad, gimg_gloss=gimg,
+                            meta=np.array([W, H, spp, mb, ab, seed, 0], dtype=np.float64))
+        print(name, img.reshape(-1, 3).mean(0), grad[4])
+    # gradient image of the red wall's albedo in the plain Cornell box (the README figure)
+    W, H, spp, mb, ab = 48, 32, 8, 8, 1.0
+    img, grad, gimg = oracle_lib.ref_render(drt.cornell_box(W, H), drt.make_opts(spp, mb, ab, seed_scale=1.0 / spp),
+                                            grad_image_of=0)
+    np.savez_compressed(HERE / "cbox_48x32_8spp_b8_p1_gimg_red.npz", img=img, grad=grad, gimg=gimg,
+                        meta=np.array([W, H, spp, mb, ab, 0, 0], dtype=np.float64))
+    print("gimg red", gimg.sum((0, 1)), grad[0])
+
+
 def main():
     assert oracle_lib.have_ref(), "needs /root/reference (build container only)"
+    if "--only-specular" in sys.argv:
+        return specular_and_grad_image()
     for name, (W, H, spp, mb, ab, seed, mode) in CASES.items():
         scene = drt.cornell_box(W, H)
         opts = drt.make_opts(spp, mb, ab, seed=seed)
@@ -72,6 +95,7 @@ def main():
     img, grad = oracle_lib.ref_render(scene, drt.make_opts(4, 4, 1.0))
     np.savez_compressed(HERE / "mesh_room_98tri_32x24_4spp_b4.npz", img=img, grad=grad)
     print("mesh", img.reshape(-1, 3).mean(0), np.count_nonzero(grad))
+    specular_and_grad_image()
 
 
 if __name__ == "__main__":

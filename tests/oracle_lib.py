@@ -38,6 +38,9 @@ def load_restate() -> C.CDLL:
     lib.drt_oracle_render_mesh.restype = C.c_int
     lib.drt_oracle_render_mesh.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Mesh), C.POINTER(abi.RenderOpts), _dp, _dp,
                                            _dp, C.c_int, C.POINTER(abi.Stats)]
+    lib.drt_oracle_render_gimg.restype = C.c_int
+    lib.drt_oracle_render_gimg.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Mesh), C.POINTER(abi.RenderOpts), _dp, _dp,
+                                           _dp, C.c_int, _dp, C.c_int, C.POINTER(abi.Stats)]
     lib.drt_oracle_trace_rays_mesh.restype = C.c_int
     lib.drt_oracle_trace_rays_mesh.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Mesh), C.POINTER(abi.RenderOpts),
                                                C.c_int64, _dp, _dp, C.POINTER(C.c_uint64), _dp, _dp]
@@ -68,6 +71,9 @@ def load_ref() -> C.CDLL:
     lib.drt_ref_render_mesh.restype = C.c_int
     lib.drt_ref_render_mesh.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Mesh), C.POINTER(abi.RenderOpts), _dp, _dp,
                                         _dp, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    lib.drt_ref_render_gimg.restype = C.c_int
+    lib.drt_ref_render_gimg.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Mesh), C.POINTER(abi.RenderOpts), _dp, _dp,
+                                        _dp, C.c_int, _dp, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     lib.drt_ref_trace_ray.restype = C.c_int
     lib.drt_ref_trace_ray.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.RenderOpts), _dp, _dp,
                                       C.c_uint64, _dp, _dp]
@@ -87,36 +93,44 @@ def _rows(scene, opts):
     return sum(1 for y in range(H) if (y // band) % opts.shard_count == opts.shard_index)
 
 
-def restate_render(scene, opts, seed_img=None, threads=1, want_stats=False):
+def restate_render(scene, opts, seed_img=None, threads=1, want_stats=False, grad_image_of=None):
+    """grad_image_of = parameter index: also returns the per-pixel gradient image (last)."""
     lib = load_restate()
     sc = scene.flatten()
     mesh = scene.flatten_mesh()
     rows = _rows(scene, opts)
     img = np.zeros((rows, scene.camera.width, 3))
     grad = np.zeros((scene.n_params, 3))
+    gimg = np.zeros((rows, scene.camera.width, 3)) if grad_image_of is not None else None
     st = abi.Stats()
     if seed_img is not None:
         seed_img = np.ascontiguousarray(seed_img, dtype=np.float64)
-    rc = lib.drt_oracle_render_mesh(C.byref(sc), C.byref(mesh) if mesh is not None else None, C.byref(opts),
-                                    _ptr(seed_img), _ptr(img), _ptr(grad), threads, C.byref(st))
+    rc = lib.drt_oracle_render_gimg(C.byref(sc), C.byref(mesh) if mesh is not None else None, C.byref(opts),
+                                    _ptr(seed_img), _ptr(img), _ptr(grad),
+                                    -1 if grad_image_of is None else int(grad_image_of), _ptr(gimg), threads, C.byref(st))
     assert rc == 0
-    return (img, grad, st) if want_stats else (img, grad)
+    out = (img, grad, st) if want_stats else (img, grad)
+    return out + (gimg,) if gimg is not None else out
 
 
-def ref_render(scene, opts, seed_img=None, threads=1, rand_mode=0, want_draws=False):
+def ref_render(scene, opts, seed_img=None, threads=1, rand_mode=0, want_draws=False, grad_image_of=None):
     lib = load_ref()
     sc = scene.flatten()
     mesh = scene.flatten_mesh()
     rows = _rows(scene, opts)
     img = np.zeros((rows, scene.camera.width, 3))
     grad = np.zeros((scene.n_params, 3))
+    gimg = np.zeros((rows, scene.camera.width, 3)) if grad_image_of is not None else None
     draws = C.c_uint64()
     if seed_img is not None:
         seed_img = np.ascontiguousarray(seed_img, dtype=np.float64)
-    rc = lib.drt_ref_render_mesh(C.byref(sc), C.byref(mesh) if mesh is not None else None, C.byref(opts),
-                                 _ptr(seed_img), _ptr(img), _ptr(grad), threads, rand_mode, C.byref(draws))
+    rc = lib.drt_ref_render_gimg(C.byref(sc), C.byref(mesh) if mesh is not None else None, C.byref(opts),
+                                 _ptr(seed_img), _ptr(img), _ptr(grad),
+                                 -1 if grad_image_of is None else int(grad_image_of), _ptr(gimg), threads, rand_mode,
+                                 C.byref(draws))
     assert rc == 0
-    return (img, grad, draws.value) if want_draws else (img, grad)
+    out = (img, grad, draws.value) if want_draws else (img, grad)
+    return out + (gimg,) if gimg is not None else out
 
 
 def rel_err(a: np.ndarray, b: np.ndarray, floor: float | None = None) -> np.ndarray:
