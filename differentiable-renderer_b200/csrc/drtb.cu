@@ -50,7 +50,22 @@ struct SmemSink {
         col[(3 * p + c) * kBlock] += double(v);
     }
 };
-// Large parameter sets: one red.global.add.f64 per contribution.
+// Medium parameter sets (9 .. kMaxParams, analytic scenes): the columns no longer fit per
+// thread, so `cols` (a power of two, chosen by the launcher to fit shared memory) columns are
+// shared by the threads with equal (threadIdx.x mod cols) and updated with shared-memory
+// atomics (a CAS loop, ATOMS.CAST.SPIN.64).  Contention stays inside the block and is spread
+// over P3 x cols words; the block reduction and reduce_grad_kernel are the small-set ones.
+// (Global atomics here cost 8x the whole render at 9 parameters: every lit path of the grid
+// hammers the same 27 words.)
+struct SmemAtomicSink {
+    double* col;                                   // &acc[threadIdx.x & (cols - 1)]
+    int cols;
+    template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
+    {
+        atomicAdd(col + (3 * p + c) * cols, double(v));
+    }
+};
+// Large parameter sets (mesh scenes, per-triangle albedos): one red.global.add.f64 per contribution.
 struct AtomicSink {
     double* grad;
     template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
@@ -101,10 +116,13 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     __shared__ BlockScene<R> bs;
     __shared__ double s_red[kSmallP * 3][kWarpsPerBlock];
 
+    // gradient sink: per-thread columns (SMALLP), shared atomic columns (analytic scenes with
+    // more parameters) or global atomics (mesh scenes with more parameters)
+    constexpr bool kSharedAtomic = !SMALLP && !MESH;
     const bool want_grad = (a.flags & DRTB_FLAG_GRAD) != 0;
     const int P3 = sc.n_params * 3;
     double* s_acc = s_dyn;
-    const int acc_doubles = (SMALLP && want_grad) ? P3 * kBlock : 0;
+    const int acc_doubles = !want_grad ? 0 : SMALLP ? P3 * kBlock : kSharedAtomic ? P3 * a.sink_cols : 0;
     load_block_scene(bs, sc, a.params);
     for (int i = threadIdx.x; i < acc_doubles; i += kBlock) s_acc[i] = 0.0;
     __syncthreads();
@@ -131,6 +149,7 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
 
     SmemSink ssink{s_acc + threadIdx.x};
     AtomicSink asink{a.grad_atomic};
+    SmemAtomicSink msink{s_acc + (threadIdx.x & (a.sink_cols - 1)), a.sink_cols};
     Materials<R, MESH> mat;
     mat.bs = &bs;
     if constexpr (MESH) { mat.mesh = a.mesh; mat.params = a.params; }
@@ -162,14 +181,15 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
         // sweeps over one record; accumulates this lane's share of the pixel and the gradients
         auto sweep = [&](const auto& rec, int n) {
             R L0[3];
+            auto run = [&](auto& sink) { radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, sink); };
             if constexpr (GEN) {
-                PixelSink<SmemSink> ps{ssink, a.gimg_param, gacc};
-                PixelSink<AtomicSink> pa{asink, a.gimg_param, gacc};
-                if (SMALLP) radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ps);
-                else        radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, pa);
+                if constexpr (SMALLP)             { PixelSink<SmemSink> s{ssink, a.gimg_param, gacc}; run(s); }
+                else if constexpr (kSharedAtomic) { PixelSink<SmemAtomicSink> s{msink, a.gimg_param, gacc}; run(s); }
+                else                              { PixelSink<AtomicSink> s{asink, a.gimg_param, gacc}; run(s); }
             } else {
-                if (SMALLP) radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ssink);
-                else        radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, asink);
+                if constexpr (SMALLP)             run(ssink);
+                else if constexpr (kSharedAtomic) run(msink);
+                else                              run(asink);
             }
             acc[0] += double(L0[0]); acc[1] += double(L0[1]); acc[2] += double(L0[2]);       // render.cpp:78
             n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
@@ -258,6 +278,14 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
 #pragma unroll
             for (int w = 0; w < kWarpsPerBlock; ++w) v += s_red[threadIdx.x][w];
             a.grad_partial[(size_t)blockIdx.x * P3 + threadIdx.x] = v;
+        }
+    }
+    if (kSharedAtomic && want_grad) {
+        __syncthreads();                           // every warp's atomics have landed
+        for (int j = threadIdx.x; j < P3; j += kBlock) {
+            double v = 0.0;
+            for (int c = 0; c < a.sink_cols; ++c) v += s_acc[j * a.sink_cols + c];
+            a.grad_partial[(size_t)blockIdx.x * P3 + j] = v;
         }
     }
     if (a.stats) {
@@ -634,7 +662,7 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > need_blocks) grid = need_blocks;
     if (grid < 1) grid = 1;
-    if (want_grad && SMALLP) {
+    if (want_grad && (SMALLP || !MESH)) {
         rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, size_t(grid) * P3);
         if (rc != DRTB_OK) return rc;
         a.grad_partial = ctx->d_partial;
@@ -758,8 +786,19 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     const bool mesh = ctx->n_tris > 0;
     a.mesh = mesh_view(ctx);
     size_t smem = (smallp && want_grad) ? size_t(P3) * kBlock * sizeof(double) : 0;
-    if (queue) smem += kWarpsPerBlock * queue_bytes_per_warp(a.max_depth, f32 ? sizeof(float) : sizeof(double),
-                                                             mesh ? sizeof(int32_t) : sizeof(uint8_t));
+    const size_t ring_bytes = queue ? kWarpsPerBlock * queue_bytes_per_warp(a.max_depth, f32 ? sizeof(float) : sizeof(double),
+                                                                            mesh ? sizeof(int32_t) : sizeof(uint8_t)) : 0;
+    // analytic scenes with 9 .. 64 parameters: shared atomic columns, as many as keep 5 blocks on an SM
+    const bool shared_atomic = !smallp && !mesh;
+    a.sink_cols = 1;
+    if (shared_atomic && want_grad) {
+        const size_t budget = 44 * 1024 - 6 * 1024 - ring_bytes;          // 227 KB / 5 blocks, minus static smem
+        int cols = kBlock;
+        while (cols > 1 && size_t(P3) * cols * sizeof(double) > budget) cols >>= 1;
+        a.sink_cols = cols;
+        smem = size_t(P3) * cols * sizeof(double);
+    }
+    smem += ring_bytes;
     smem = (smem + 15) & ~size_t(15);
     const long long npix = (long long)rows * W;
     const int ppw = o->spp >= 32 ? 1 : 32 / o->spp;
@@ -769,7 +808,7 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     if (a.stats) {
         CK(ctx, cudaMemsetAsync(d_stats, 0, sizeof(drtb_stats), stream));
     }
-    if (want_grad && !smallp) {
+    if (want_grad && !smallp && !shared_atomic) {
         CK(ctx, cudaMemsetAsync(d_grad, 0, sizeof(double) * P3, stream));
         a.grad_atomic = d_grad;
     }
@@ -777,7 +816,7 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     int rc = f32 ? launch_precision<float>(ctx, ctx->sc32, a, smallp, queue, mesh, gen, smem, need, P3, want_grad, stream, grid)
                  : launch_precision<double>(ctx, ctx->sc64, a, smallp, queue, mesh, gen, smem, need, P3, want_grad, stream, grid);
     if (rc != DRTB_OK) return rc;
-    if (want_grad && smallp) {
+    if (want_grad && (smallp || shared_atomic)) {
         reduce_grad_kernel<<<1, 256, 0, stream>>>(ctx->d_partial, int(grid), P3, d_grad);
         CK(ctx, cudaGetLastError());
         ctx->launches++;

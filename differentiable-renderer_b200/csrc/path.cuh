@@ -92,6 +92,7 @@ struct RenderArgs {
     drtb_stats* stats;                   // or null
     double*  gimg;                       // shard_rows x W x 3 gradient image of parameter gimg_param, or null
     int32_t  gimg_param;                 // -1 = none
+    int32_t  sink_cols;                  // shared atomic gradient columns (9 .. 64 parameters), a power of two
     MeshView mesh;                       // n_tris == 0: analytic scene only
 };
 
