@@ -18,7 +18,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libdrtb.so"
 SOURCES = [CSRC / "drtb.cu"]
-HEADERS = [CSRC / "path.cuh", CSRC / "real.cuh", CSRC / "rng.cuh", ROOT / "include" / "drtb.h"]
+HEADERS = sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "drtb.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -70,7 +70,7 @@ def build_example(force: bool = False) -> Path:
     headers) -> build/render, linked against libdrtb.so."""
     exe = ROOT / "build" / "render"
     src = ROOT / "examples" / "render.cpp"
-    hdrs = list((ROOT / "include" / "drt").glob("*.hpp")) + [ROOT / "include" / "drtb.h", src]
+    hdrs = list((ROOT / "include" / "drt").glob("*.hpp")) + [ROOT / "include" / "drtb.h", src, src.parent / "write.hpp"]
     if not force and exe.exists() and all(h.stat().st_mtime <= exe.stat().st_mtime for h in hdrs) \
             and LIB.stat().st_mtime <= exe.stat().st_mtime:
         return exe

@@ -4,9 +4,10 @@
 // (src/args.hpp:20-67: -x/--width 640, -y/--height 480, -n/--samples 100,
 // -b/--min-bounces 1, -p/--absorb-prob 0.5, -o/--output required), with the
 // gradient call of src/render.cpp:79-80 enabled.  TCLAP and OpenEXR are not
-// needed: flags are parsed by hand and the image is written as a PFM (float32
-// RGB, lossless enough to diff, no half-precision rounding like the EXR writer
-// of src/write.hpp).
+// needed: flags are parsed by hand and the image is written by the
+// dependency-free write_exr of examples/write.hpp (half RGBA scanlines, what
+// src/write.hpp:10-26 produces through OpenEXR); an output name ending in
+// ".pfm" selects a float32 PFM instead (no half-precision rounding, for diffs).
 //
 //   g++ -std=c++17 -O2 -Iinclude examples/render.cpp -o build/render
 //       -Ldifferentiable-renderer_b200/lib -ldrtb   (plus an rpath to that lib directory)
@@ -24,6 +25,7 @@
 #include "drt/render.hpp"
 #include "drt/shape.hpp"
 #include "drt/vector.hpp"
+#include "write.hpp"
 
 using namespace drt;
 
@@ -129,8 +131,17 @@ int main(int argc, const char* argv[])
     for (int k = 0; k < 4; ++k)
         std::printf("%s.grad = %.9f %.9f %.9f\n", names[k], ps[k]->grad()[0], ps[k]->grad()[1], ps[k]->grad()[2]);
 
-    if (!write_pfm(args.output.c_str(), img.data(), args.width, args.height)) {
-        std::fprintf(stderr, "cannot write %s\n", args.output.c_str());
+    // Write radiance to file: src/render.cpp:90
+    const std::string& out = args.output;
+    const bool pfm = out.size() > 4 && out.compare(out.size() - 4, 4, ".pfm") == 0;
+    try {
+        if (pfm) {
+            if (!write_pfm(out.c_str(), img.data(), args.width, args.height)) throw std::runtime_error("cannot write " + out);
+        } else {
+            write_exr(out.c_str(), img.data(), args.width, args.height);
+        }
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "%s\n", e.what());
         return EXIT_FAILURE;
     }
     return 0;

@@ -39,3 +39,78 @@ def test_reference_style_program_compiles_against_the_new_headers():
     exe = mod.build_example()
     r = subprocess.run([str(exe), "-x", "8"], capture_output=True, text=True)
     assert r.returncode != 0 and "Required argument missing: output" in r.stderr   # args.hpp:60-66 semantics
+
+
+def _read_scanline_exr(path):
+    """Minimal reader for uncompressed single-part scanline EXR files with HALF channels."""
+    import struct
+    import numpy as np
+    b = Path(path).read_bytes()
+    assert b[:4] == bytes([0x76, 0x2f, 0x31, 0x01]) and b[4:8] == bytes([2, 0, 0, 0])
+    pos, attrs = 8, {}
+    def cstr(p):
+        e = b.index(0, p)
+        return b[p:e].decode(), e + 1
+    while b[pos] != 0:
+        name, pos = cstr(pos)
+        typ, pos = cstr(pos)
+        size = struct.unpack_from("<i", b, pos)[0]
+        attrs[name] = (typ, b[pos + 4:pos + 4 + size])
+        pos += 4 + size
+    pos += 1
+    chans, p = [], 0
+    cl = attrs["channels"][1]
+    while cl[p] != 0:
+        e = cl.index(0, p)
+        name = cl[p:e].decode()
+        ptype, plin, xs, ys = struct.unpack_from("<iB3xii", cl, e + 1)
+        assert (ptype, xs, ys) == (1, 1, 1)
+        chans.append(name)
+        p = e + 1 + 16
+    assert attrs["compression"] == ("compression", b"\x00") and attrs["lineOrder"] == ("lineOrder", b"\x00")
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
+    assert attrs["displayWindow"][1] == attrs["dataWindow"][1] and (x0, y0) == (0, 0)
+    for need in ("pixelAspectRatio", "screenWindowCenter", "screenWindowWidth"):
+        assert need in attrs
+    w, h = x1 + 1, y1 + 1
+    offs = struct.unpack_from(f"<{h}Q", b, pos)
+    out = {c: np.zeros((h, w), np.float16) for c in chans}
+    for y in range(h):
+        yy, size = struct.unpack_from("<ii", b, offs[y])
+        assert yy == y and size == w * 2 * len(chans)
+        q = offs[y] + 8
+        for c in chans:
+            out[c][y] = np.frombuffer(b, "<f2", w, q)
+            q += 2 * w
+    assert offs[-1] + 8 + w * 2 * len(chans) == len(b)
+    return chans, out
+
+
+def test_dependency_free_exr_writer(tmp_path):
+    """examples/write.hpp: same pixels as the reference's Imf::Rgba writer (src/write.hpp:10-26):
+    half-precision R, G, B rounded to nearest even, alpha 1, row 0 on top."""
+    import numpy as np
+    exe, out = tmp_path / "test_write_exr", tmp_path / "t.exr"
+    r = subprocess.run([GXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", str(ROOT / "include"), "-I", str(ROOT / "examples"),
+                        str(ROOT / "tests" / "cpp" / "test_write_exr.cpp"), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stderr.strip() == "", r.stderr
+    r = subprocess.run([str(exe), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0 and "exr written" in r.stdout, r.stdout + r.stderr
+    chans, px = _read_scanline_exr(out)
+    assert chans == ["A", "B", "G", "R"]
+    w, h = 7, 5
+    img = np.zeros((h, w, 3))
+    for y in range(h):
+        for x in range(w):
+            img[y, x] = (0.125 * x + 1e-3 * y, 2.0 ** (x - 20 - y), y * 1000.0 + 1.0 / 3.0)
+    img[0, 0] = (0.0, 1e6, -2.5)
+    img[0, 1] = (6.1e-5, 5.9604644775390625e-8, 2.9802322387695312e-8)
+    img[0, 2] = (65504.0, 65519.9, 65520.0)
+    img[0, 3] = (np.nan, 1.00048828125, 1.00146484375)
+    with np.errstate(over="ignore"):
+        want = img.astype(np.float32).astype(np.float16)          # numpy rounds to nearest even, overflow -> inf
+    assert np.all(px["A"] == np.float16(1.0))
+    for i, c in enumerate("RGB"):
+        assert np.array_equal(px[c].view(np.uint16)[~np.isnan(want[..., i])], want[..., i].view(np.uint16)[~np.isnan(want[..., i])]), c
+    assert np.isnan(px["R"][0, 3]) and np.isinf(px["G"][0, 0]) and np.isinf(px["B"][0, 2]) and px["G"][0, 2] == np.float16(65504.0)
+    assert px["B"][0, 1] == 0 and px["G"][0, 1] == np.float16(5.9604644775390625e-8)
