@@ -569,10 +569,21 @@ void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
     memset(&d, 0, sizeof d);
     d.n_prims = int(c.prims.size());
     d.n_params = int(c.params.size() / 3);
-    // scan slots (see DevScene): the first kFast planes / spheres right-aligned in
-    // the straight-line windows, the rest appended in scene order
-    std::vector<int> planes, spheres;
-    for (int i = 0; i < d.n_prims; ++i) (c.prims[i].type == DRTB_PLANE ? planes : spheres).push_back(i);
+    // scan slots (see DevScene): axis-aligned unit planes go to the per-axis windows (at most
+    // kAxisFast each, the rest are scanned as general planes -- same t bit for bit); the first
+    // kFast other planes / spheres sit right-aligned in the straight-line windows, the rest are
+    // appended in scene order
+    std::vector<int> planes, spheres, axis_planes[3];
+    for (int i = 0; i < d.n_prims; ++i) {
+        const drtb_prim& p = c.prims[i];
+        if (p.type != DRTB_PLANE) { spheres.push_back(i); continue; }
+        int axis = -1, nz = 0;
+        for (int j = 0; j < 3; ++j) if (p.v[j] != 0.0) { ++nz; axis = j; }
+        if (nz == 1 && std::fabs(p.v[axis]) == 1.0 && std::isfinite(p.v[3]) && int(axis_planes[axis].size()) < kAxisFast)
+            axis_planes[axis].push_back(i);
+        else
+            planes.push_back(i);
+    }
     d.n_fast_planes = std::min<int>(kFast, int(planes.size()));
     d.n_fast_spheres = std::min<int>(kFast, int(spheres.size()));
     d.n_over_planes = int(planes.size()) - d.n_fast_planes;
@@ -587,6 +598,17 @@ void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
     for (int j = 0; j < int(spheres.size()); ++j)
         put(j < d.n_fast_spheres ? 2 * kFast - d.n_fast_spheres + j
                                  : 2 * kFast + d.n_over_planes + (j - d.n_fast_spheres), spheres[j]);
+    int store = 2 * kFast + d.n_over_planes + d.n_over_spheres;       // unscanned storage: n, off by scene index
+    for (int ax = 0; ax < 3; ++ax) {
+        const int n = int(axis_planes[ax].size());
+        d.n_aa[ax] = n;
+        for (int j = 0; j < n; ++j) {
+            const int i = axis_planes[ax][j];
+            d.aa_c[ax][kAxisFast - n + j] = R(c.prims[i].v[ax] * c.prims[i].v[3]);   // s * off, exact (s = +-1)
+            d.aa_id[ax][kAxisFast - n + j] = i;
+            put(store++, i);
+        }
+    }
     for (int i = 0; i < d.n_prims; ++i) {
         const drtb_prim& p = c.prims[i];
         d.type[i] = int8_t(p.type);

@@ -18,6 +18,7 @@ constexpr int kSmallP     = 8;     // <= this many parameters: per-thread smem g
 constexpr int kBlock      = 128;
 constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr int kFast       = 8;     // planes / spheres scanned by straight-line code (compile-time slots)
+constexpr int kAxisFast   = 2;     // axis-aligned unit planes per axis scanned by straight-line code (a slab)
 constexpr int kSlots      = 2 * kFast + kMaxPrims;
 
 // Scene as the kernels see it.  Passed BY VALUE as a __grid_constant__ kernel
@@ -31,10 +32,18 @@ struct alignas(16) DevScene {
     // enters straight-line code at slot kFast - n, so every operand of those
     // tests is a compile-time constant-bank address (no LDC, no loop).  From
     // 2 kFast on: the planes, then the spheres, that did not fit (rolled loops).
-    // Planes are scanned before spheres, each group in Scene<T> order; id[] is
-    // the position in Scene<T>, which decides exact ties (pathtracer.hpp:80).
+    // id[] is the position in Scene<T>, which decides exact ties (pathtracer.hpp:80).
+    // Planes whose normal is exactly +-e_x, +-e_y or +-e_z (the walls of a box
+    // scene; 5 of the Cornell box's 6) are NOT scanned there: for n = s e_a,
+    // t = (o.n - off) / (d.(-n)) = (s off - o_a) / d_a with every product exact, so
+    // they sit in aa_c / aa_id (up to kAxisFast per axis, right-aligned) and cost one
+    // subtraction and one multiplication by the per-segment 1 / d_a.  Their n, off
+    // stay in prim[] behind the scanned slots for the per-lane lookups.
     R       prim[kSlots][4];             // plane: n.xyz (RAW), offset ; sphere: c.xyz, r
     int32_t id[kSlots];                  // scan slot -> scene index
+    R       aa_c[3][kAxisFast];          // s * offset: the plane is  p_a = aa_c
+    int32_t aa_id[3][kAxisFast];
+    int32_t n_aa[3];
     int32_t n_fast_planes, n_fast_spheres, n_over_planes, n_over_spheres;
     // Indexed by SCENE index:
     R       frame[kMaxPrims][6];         // planes: make_frame(n) tangent, bitangent (bxdf.hpp:29-41), host double
@@ -143,22 +152,38 @@ __device__ __forceinline__ V3<R> camera_ray(const DevScene<R>& sc, int x, int y,
     return normalize(d);
 }
 
-// One plane / sphere against the running best (bn / bd, best).  SLOT is either
-// a compile-time constant (straight-line scan) or a warp-uniform register.
+// One plane / sphere against the running best (bt, best).  SLOT is either a
+// compile-time constant (straight-line scan) or a warp-uniform register.
+// Acceptance is the reference's (pathtracer.hpp:80, shape.hpp:55, 91-99):
+// t > 0, strictly closer than the best so far, the lower scene index winning
+// exact ties (the scan order here is not the scene order, so the index is
+// compared explicitly).  t = +-inf / NaN (ray parallel to a plane) fails every
+// compare, as upstream where inf >= tmin skips it.
 template <typename R>
-__device__ __forceinline__ void plane_test(const DevScene<R>& sc, int slot, V3<R> o, V3<R> d, R& bn, R& bd, int& best)
+__device__ __forceinline__ void accept(R t, int id, R& bt, int& best)
+{
+    const bool closer = (t < bt) | ((t == bt) & (id < best));           // bitwise: no branch
+    if (Real<R>::is_pos(t) & closer) { bt = t; best = id; }
+}
+
+// Axis-aligned unit plane p_a = c: t = (c - o_a) / d_a, inv_a = 1 / d_a once per segment.
+template <typename R>
+__device__ __forceinline__ void axis_plane_test(const DevScene<R>& sc, int axis, int slot, R o_a, R inv_a, R& bt, int& best)
+{
+    accept((sc.aa_c[axis][slot] - o_a) * inv_a, sc.aa_id[axis][slot], bt, best);
+}
+
+template <typename R>
+__device__ __forceinline__ void plane_test(const DevScene<R>& sc, int slot, V3<R> o, V3<R> d, R& bt, int& best)
 {
     const R a0 = sc.prim[slot][0], a1 = sc.prim[slot][1], a2 = sc.prim[slot][2], a3 = sc.prim[slot][3];
     const R h = Real<R>::fma(o.x, a0, Real<R>::fma(o.y, a1, Real<R>::fma(o.z, a2, -a3)));   // o.n - offset
     const R g = Real<R>::fma(d.x, a0, Real<R>::fma(d.y, a1, d.z * a2));                     // d.n ; t = h / -g
-    const R num = Real<R>::flip_if_pos(h, g);
-    const R den = Real<R>::abs(g);
-    // t > 0  <=>  num > 0 (den > 0);  den == 0 gives t = +-inf / NaN: rejected as in the reference
-    if (Real<R>::is_pos(num) && Real<R>::is_nonzero(g) && num * bd < bn * den) { bn = num; bd = den; best = sc.id[slot]; }
+    accept(-h * Real<R>::rcp(g), sc.id[slot], bt, best);
 }
 
 template <typename R>
-__device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<R> o, V3<R> d, R& bn, R& bd, int& best)
+__device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<R> o, V3<R> d, R& bt, int& best)
 {
     const R a0 = sc.prim[slot][0], a1 = sc.prim[slot][1], a2 = sc.prim[slot][2], a3 = sc.prim[slot][3];
     const V3<R> oc = {o.x - a0, o.y - a1, o.z - a2};
@@ -167,34 +192,40 @@ __device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<
     const R disc = Real<R>::fma(hb, hb, -c);       // (b^2 - 4c)/4, an exact rescaling
     const R sq = Real<R>::sqrt(disc);              // NaN when disc < 0: every compare below fails
     const R t1 = -hb - sq, t2 = sq - hb;           // t1 <= t2
-    const R t = Real<R>::select(Real<R>::is_pos(t1), t1, t2);
-    const int id = sc.id[slot];
-    const R lhs = t * bd;
-    const bool closer = (lhs < bn) | ((lhs == bn) & (id < best));       // bitwise: no branch
-    if (Real<R>::is_pos(t) & closer) { bn = t; bd = R(1); best = id; }
+    accept(Real<R>::select(Real<R>::is_pos(t1), t1, t2), sc.id[slot], bt, best);
 }
 
 // ---------------------------------------------------------------------------
 // Pathtracer::raycast, pathtracer.hpp:72-89 with Plane::intersect
 // (shape.hpp:49-56) and Sphere::intersect (shape.hpp:78-103, a == 1).
 //
-// The reference divides once per plane (t = h / dot(dir, -n)).  Here every
-// candidate is kept as a fraction num/den with den > 0 and compared by
-// cross-multiplication, so a segment costs ONE division (for the winner)
-// instead of one per plane.  Acceptance is the reference's: t > 0, strictly
-// closer than the best so far, the lower scene index winning exact ties.
-// The first kFast planes and kFast spheres are tested by straight-line code
-// entered at the first live slot (their operands are immediate constant-bank
-// addresses); larger scenes continue in rolled loops with a warp-uniform slot.
+// The reference divides once per plane (t = h / dot(dir, -n)).  Here a plane
+// costs a Newton reciprocal (no IEEE division), and the axis-aligned unit
+// planes share three reciprocals 1 / d_a per segment.  The first kAxisFast
+// axis planes per axis, kFast other planes and kFast spheres are tested by
+// straight-line code entered at the first live slot (their operands are
+// immediate constant-bank addresses); larger scenes continue in rolled loops
+// with a warp-uniform slot.
 // ---------------------------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R> d, R& tmin)
 {
-    R bn = Real<R>::inf(), bd = R(1);                  // best t = bn / bd
+    R bt = Real<R>::inf();
     int best = -1;
-    // Entry into the straight-line tests by a 3-level compare tree on the (warp-uniform)
+    // Entry into the straight-line tests by a compare tree on the (warp-uniform)
     // first live slot: ~6 instructions, where the compiler's jump table for the
     // equivalent switch cost ~20 per entry.
+    static_assert(kAxisFast == 2, "the axis windows below are written out for two slots");
+#define DRTB_AXIS(AX, OA, DA)                                                                  \
+    if (sc.n_aa[AX] > 0) {                                                                      \
+        const R inv = Real<R>::rcp(DA);                                                         \
+        if (sc.n_aa[AX] > 1) axis_plane_test(sc, AX, 0, OA, inv, bt, best);                     \
+        axis_plane_test(sc, AX, 1, OA, inv, bt, best);                                          \
+    }
+    DRTB_AXIS(0, o.x, d.x)
+    DRTB_AXIS(1, o.y, d.y)
+    DRTB_AXIS(2, o.z, d.z)
+#undef DRTB_AXIS
 #define DRTB_ENTER(first, L)                                                                   \
     if (first >= 4) { if (first >= 6) { if (first >= 7) { if (first == 7) goto L##7; goto L##8; } goto L##6; } \
                       if (first == 5) goto L##5; goto L##4; }                                   \
@@ -203,34 +234,34 @@ __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R>
     {
         const int first = kFast - sc.n_fast_planes;
         DRTB_ENTER(first, P)
-        plane_test(sc, 0, o, d, bn, bd, best);
-    P1: plane_test(sc, 1, o, d, bn, bd, best);
-    P2: plane_test(sc, 2, o, d, bn, bd, best);
-    P3: plane_test(sc, 3, o, d, bn, bd, best);
-    P4: plane_test(sc, 4, o, d, bn, bd, best);
-    P5: plane_test(sc, 5, o, d, bn, bd, best);
-    P6: plane_test(sc, 6, o, d, bn, bd, best);
-    P7: plane_test(sc, 7, o, d, bn, bd, best);
+        plane_test(sc, 0, o, d, bt, best);
+    P1: plane_test(sc, 1, o, d, bt, best);
+    P2: plane_test(sc, 2, o, d, bt, best);
+    P3: plane_test(sc, 3, o, d, bt, best);
+    P4: plane_test(sc, 4, o, d, bt, best);
+    P5: plane_test(sc, 5, o, d, bt, best);
+    P6: plane_test(sc, 6, o, d, bt, best);
+    P7: plane_test(sc, 7, o, d, bt, best);
     P8:;
     }
-    for (int i = 0; i < sc.n_over_planes; ++i) plane_test(sc, 2 * kFast + i, o, d, bn, bd, best);
+    for (int i = 0; i < sc.n_over_planes; ++i) plane_test(sc, 2 * kFast + i, o, d, bt, best);
     {
         const int first = kFast - sc.n_fast_spheres;
         DRTB_ENTER(first, S)
-        sphere_test(sc, kFast + 0, o, d, bn, bd, best);
-    S1: sphere_test(sc, kFast + 1, o, d, bn, bd, best);
-    S2: sphere_test(sc, kFast + 2, o, d, bn, bd, best);
-    S3: sphere_test(sc, kFast + 3, o, d, bn, bd, best);
-    S4: sphere_test(sc, kFast + 4, o, d, bn, bd, best);
-    S5: sphere_test(sc, kFast + 5, o, d, bn, bd, best);
-    S6: sphere_test(sc, kFast + 6, o, d, bn, bd, best);
-    S7: sphere_test(sc, kFast + 7, o, d, bn, bd, best);
+        sphere_test(sc, kFast + 0, o, d, bt, best);
+    S1: sphere_test(sc, kFast + 1, o, d, bt, best);
+    S2: sphere_test(sc, kFast + 2, o, d, bt, best);
+    S3: sphere_test(sc, kFast + 3, o, d, bt, best);
+    S4: sphere_test(sc, kFast + 4, o, d, bt, best);
+    S5: sphere_test(sc, kFast + 5, o, d, bt, best);
+    S6: sphere_test(sc, kFast + 6, o, d, bt, best);
+    S7: sphere_test(sc, kFast + 7, o, d, bt, best);
     S8:;
     }
 #undef DRTB_ENTER
     for (int i = 0; i < sc.n_over_spheres; ++i)
-        sphere_test(sc, 2 * kFast + sc.n_over_planes + i, o, d, bn, bd, best);
-    tmin = Real<R>::div(bn, bd);
+        sphere_test(sc, 2 * kFast + sc.n_over_planes + i, o, d, bt, best);
+    tmin = bt;
     return best;
 }
 
