@@ -20,6 +20,10 @@ constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr int kFast       = 8;     // planes / spheres scanned by straight-line code (compile-time slots)
 constexpr int kAxisFast   = 2;     // axis-aligned unit planes per axis scanned by straight-line code (a slab)
 constexpr int kSlots      = 2 * kFast + kMaxPrims;
+#ifndef DRTB_PACK_HIT
+#define DRTB_PACK_HIT 1
+#endif
+constexpr bool kPackHit   = DRTB_PACK_HIT;   // double analytic kernels: closest hit on integer keys (Closest<double, true>)
 
 // Scene as the kernels see it.  Passed BY VALUE as a __grid_constant__ kernel
 // parameter: the closest-hit scan indexes prim[] with a warp-uniform i, so
@@ -152,38 +156,70 @@ __device__ __forceinline__ V3<R> camera_ray(const DevScene<R>& sc, int x, int y,
     return normalize(d);
 }
 
-// One plane / sphere against the running best (bt, best).  SLOT is either a
-// compile-time constant (straight-line scan) or a warp-uniform register.
-// Acceptance is the reference's (pathtracer.hpp:80, shape.hpp:55, 91-99):
-// t > 0, strictly closer than the best so far, the lower scene index winning
-// exact ties (the scan order here is not the scene order, so the index is
-// compared explicitly).  t = +-inf / NaN (ray parallel to a plane) fails every
-// compare, as upstream where inf >= tmin skips it.
-template <typename R>
-__device__ __forceinline__ void accept(R t, int id, R& bt, int& best)
-{
-    const bool closer = (t < bt) | ((t == bt) & (id < best));           // bitwise: no branch
-    if (Real<R>::is_pos(t) & closer) { bt = t; best = id; }
-}
+// The running closest hit of one scan.  offer(t, id) is the reference's
+// acceptance (pathtracer.hpp:80, shape.hpp:55, 91-99): t > 0, strictly closer
+// than the best so far, the lower scene index winning exact ties (the scan
+// order here is not the scene order, so the index takes part in the compare).
+// t = +-inf / NaN (ray parallel to a plane) fails every compare, as upstream
+// where inf >= tmin skips it.
+template <typename R, bool PACK>
+struct Closest {
+    R bt; int best;
+    __device__ __forceinline__ Closest() : bt(Real<R>::inf()), best(-1) {}
+    __device__ __forceinline__ void offer(R t, int id)
+    {
+        const bool closer = (t < bt) | ((t == bt) & (id < best));           // bitwise: no branch
+        if (Real<R>::is_pos(t) & closer) { bt = t; best = id; }
+    }
+    __device__ __forceinline__ int finish(R& tmin) const { tmin = bt; return best; }
+};
+// Double, analytic scenes: the three FP64 compares per primitive (six issue
+// slots of the half-rate pipe) become integer ones.  Positive doubles order
+// like their bit patterns, negative ones and NaNs compare above +inf as
+// unsigned integers, so "0 < t < bt" is one unsigned 64-bit compare plus the
+// sign-word test that rejects +0.  The scene index rides in the five low
+// mantissa bits (kMaxPrims = 32), which makes the tie rule part of the same
+// compare: equal t -> lower index.  Cost: the t that comes back differs from
+// the computed one by < 32 ulp (7e-15 relative; the Newton rcp/sqrt feeding it
+// are good to 2 ulp), and two primitives whose t agree to 32 ulp are ordered by
+// index instead of by t.
+template <>
+struct Closest<double, true> {
+    static constexpr uint32_t keep = ~uint32_t(kMaxPrims - 1);
+    unsigned long long key;
+    __device__ __forceinline__ Closest() : key(0x7ff0000000000000ull) {}
+    __device__ __forceinline__ void offer(double t, int id)
+    {
+        const int hi = __double2hiint(t);
+        const uint32_t lo = (uint32_t(__double2loint(t)) & keep) | uint32_t(id);
+        const unsigned long long k = (unsigned long long)(uint32_t)hi << 32 | lo;
+        if ((hi > 0) & (k < key)) key = k;
+    }
+    __device__ __forceinline__ int finish(double& tmin) const
+    {
+        tmin = __longlong_as_double((long long)key);
+        return key == 0x7ff0000000000000ull ? -1 : int(uint32_t(key) & ~keep);
+    }
+};
 
 // Axis-aligned unit plane p_a = c: t = (c - o_a) / d_a, inv_a = 1 / d_a once per segment.
-template <typename R>
-__device__ __forceinline__ void axis_plane_test(const DevScene<R>& sc, int axis, int slot, R o_a, R inv_a, R& bt, int& best)
+template <typename R, typename C>
+__device__ __forceinline__ void axis_plane_test(const DevScene<R>& sc, int axis, int slot, R o_a, R inv_a, C& cl)
 {
-    accept((sc.aa_c[axis][slot] - o_a) * inv_a, sc.aa_id[axis][slot], bt, best);
+    cl.offer((sc.aa_c[axis][slot] - o_a) * inv_a, sc.aa_id[axis][slot]);
 }
 
-template <typename R>
-__device__ __forceinline__ void plane_test(const DevScene<R>& sc, int slot, V3<R> o, V3<R> d, R& bt, int& best)
+template <typename R, typename C>
+__device__ __forceinline__ void plane_test(const DevScene<R>& sc, int slot, V3<R> o, V3<R> d, C& cl)
 {
     const R a0 = sc.prim[slot][0], a1 = sc.prim[slot][1], a2 = sc.prim[slot][2], a3 = sc.prim[slot][3];
     const R h = Real<R>::fma(o.x, a0, Real<R>::fma(o.y, a1, Real<R>::fma(o.z, a2, -a3)));   // o.n - offset
     const R g = Real<R>::fma(d.x, a0, Real<R>::fma(d.y, a1, d.z * a2));                     // d.n ; t = h / -g
-    accept(-h * Real<R>::rcp(g), sc.id[slot], bt, best);
+    cl.offer(-h * Real<R>::rcp(g), sc.id[slot]);
 }
 
-template <typename R>
-__device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<R> o, V3<R> d, R& bt, int& best)
+template <typename R, typename C>
+__device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<R> o, V3<R> d, C& cl)
 {
     const R a0 = sc.prim[slot][0], a1 = sc.prim[slot][1], a2 = sc.prim[slot][2], a3 = sc.prim[slot][3];
     const V3<R> oc = {o.x - a0, o.y - a1, o.z - a2};
@@ -192,7 +228,7 @@ __device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<
     const R disc = Real<R>::fma(hb, hb, -c);       // (b^2 - 4c)/4, an exact rescaling
     const R sq = Real<R>::sqrt(disc);              // NaN when disc < 0: every compare below fails
     const R t1 = -hb - sq, t2 = sq - hb;           // t1 <= t2
-    accept(Real<R>::select(Real<R>::is_pos(t1), t1, t2), sc.id[slot], bt, best);
+    cl.offer(Real<R>::select(Real<R>::is_pos(t1), t1, t2), sc.id[slot]);
 }
 
 // ---------------------------------------------------------------------------
@@ -207,11 +243,10 @@ __device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<
 // immediate constant-bank addresses); larger scenes continue in rolled loops
 // with a warp-uniform slot.
 // ---------------------------------------------------------------------------
-template <typename R>
+template <typename R, bool PACK = false>
 __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R> d, R& tmin)
 {
-    R bt = Real<R>::inf();
-    int best = -1;
+    Closest<R, PACK> cl;
     // Entry into the straight-line tests by a compare tree on the (warp-uniform)
     // first live slot: ~6 instructions, where the compiler's jump table for the
     // equivalent switch cost ~20 per entry.
@@ -219,8 +254,8 @@ __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R>
 #define DRTB_AXIS(AX, OA, DA)                                                                  \
     if (sc.n_aa[AX] > 0) {                                                                      \
         const R inv = Real<R>::rcp(DA);                                                         \
-        if (sc.n_aa[AX] > 1) axis_plane_test(sc, AX, 0, OA, inv, bt, best);                     \
-        axis_plane_test(sc, AX, 1, OA, inv, bt, best);                                          \
+        if (sc.n_aa[AX] > 1) axis_plane_test(sc, AX, 0, OA, inv, cl);                     \
+        axis_plane_test(sc, AX, 1, OA, inv, cl);                                          \
     }
     DRTB_AXIS(0, o.x, d.x)
     DRTB_AXIS(1, o.y, d.y)
@@ -234,35 +269,34 @@ __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R>
     {
         const int first = kFast - sc.n_fast_planes;
         DRTB_ENTER(first, P)
-        plane_test(sc, 0, o, d, bt, best);
-    P1: plane_test(sc, 1, o, d, bt, best);
-    P2: plane_test(sc, 2, o, d, bt, best);
-    P3: plane_test(sc, 3, o, d, bt, best);
-    P4: plane_test(sc, 4, o, d, bt, best);
-    P5: plane_test(sc, 5, o, d, bt, best);
-    P6: plane_test(sc, 6, o, d, bt, best);
-    P7: plane_test(sc, 7, o, d, bt, best);
+        plane_test(sc, 0, o, d, cl);
+    P1: plane_test(sc, 1, o, d, cl);
+    P2: plane_test(sc, 2, o, d, cl);
+    P3: plane_test(sc, 3, o, d, cl);
+    P4: plane_test(sc, 4, o, d, cl);
+    P5: plane_test(sc, 5, o, d, cl);
+    P6: plane_test(sc, 6, o, d, cl);
+    P7: plane_test(sc, 7, o, d, cl);
     P8:;
     }
-    for (int i = 0; i < sc.n_over_planes; ++i) plane_test(sc, 2 * kFast + i, o, d, bt, best);
+    for (int i = 0; i < sc.n_over_planes; ++i) plane_test(sc, 2 * kFast + i, o, d, cl);
     {
         const int first = kFast - sc.n_fast_spheres;
         DRTB_ENTER(first, S)
-        sphere_test(sc, kFast + 0, o, d, bt, best);
-    S1: sphere_test(sc, kFast + 1, o, d, bt, best);
-    S2: sphere_test(sc, kFast + 2, o, d, bt, best);
-    S3: sphere_test(sc, kFast + 3, o, d, bt, best);
-    S4: sphere_test(sc, kFast + 4, o, d, bt, best);
-    S5: sphere_test(sc, kFast + 5, o, d, bt, best);
-    S6: sphere_test(sc, kFast + 6, o, d, bt, best);
-    S7: sphere_test(sc, kFast + 7, o, d, bt, best);
+        sphere_test(sc, kFast + 0, o, d, cl);
+    S1: sphere_test(sc, kFast + 1, o, d, cl);
+    S2: sphere_test(sc, kFast + 2, o, d, cl);
+    S3: sphere_test(sc, kFast + 3, o, d, cl);
+    S4: sphere_test(sc, kFast + 4, o, d, cl);
+    S5: sphere_test(sc, kFast + 5, o, d, cl);
+    S6: sphere_test(sc, kFast + 6, o, d, cl);
+    S7: sphere_test(sc, kFast + 7, o, d, cl);
     S8:;
     }
 #undef DRTB_ENTER
     for (int i = 0; i < sc.n_over_spheres; ++i)
-        sphere_test(sc, 2 * kFast + sc.n_over_planes + i, o, d, bt, best);
-    tmin = bt;
-    return best;
+        sphere_test(sc, 2 * kFast + sc.n_over_planes + i, o, d, cl);
+    return cl.finish(tmin);
 }
 
 // make_frame (bxdf.hpp:29-41) for a UNIT normal (spheres, triangles): with
@@ -444,7 +478,7 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
         }
         if (n >= max_depth) { ++cnt.truncated; alive = false; continue; }
         R t;
-        int k = closest_hit(sc, o, d, t);                   // analytic primitives
+        int k = closest_hit<R, kPackHit && !MESH>(sc, o, d, t);   // analytic primitives
         int tri = -1;
         if constexpr (MESH) {                               // then the mesh; analytic wins exact ties
             if (k < 0) t = Real<R>::inf();
