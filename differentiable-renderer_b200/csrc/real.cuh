@@ -78,10 +78,19 @@ template <> struct Real<double> {
         const double e = ::fma(-x * y, y, 1.0);                  // 1 - x y^2
         return ::fma(y, ::fma(0.375, e, 0.5) * e, y);            // y (1 + e/2 + 3e^2/8): ~e0^3
     }
-    static __device__ __forceinline__ double sqrt(double x)      // x >= 0; NaN for x < 0
+    // x >= 0; NaN for x < 0.  g = x y0 ~ sqrt(x) is corrected directly,
+    // g (1 + e/2 + 3e^2/8) with e = 1 - g y0: five FP64 instructions, no final
+    // multiply.  x == 0: the seed is taken at max(x, 2^-1022) -- an unsigned max on
+    // the high word, which leaves negative x (high word >= 2^31) alone -- so y0 is
+    // finite, g = 0, e = 1 and the result is an exact 0 without a select.
+    static __device__ __forceinline__ double sqrt(double x)
     {
-        const double s = x * rsqrt(x);
-        return select(is_nonzero(x), s, 0.0);                    // 0 * inf guard
+        const uint32_t xh = max(uint32_t(__double2hiint(x)), 0x00100000u);
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(__hiloint2double(int(xh), __double2loint(x))));   // e0 <= 2^-22
+        const double g = x * y;
+        const double e = ::fma(-g, y, 1.0);
+        return ::fma(g, ::fma(0.375, e, 0.5) * e, g);
     }
     static __device__ __forceinline__ double pow(double a, double b) { return ::pow(a, b); }   // SpecularBxDF only
     // sin/cos(2*pi*u), u in [0, 1).  The reference forms phi = 2*pi*u in double and
