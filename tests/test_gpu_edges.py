@@ -111,3 +111,37 @@ def test_large_seed_and_offset_keys_do_not_collide(drt, ctx):
     assert np.array_equal(a, b) and not np.array_equal(a, c)
     ref = restate_render(drt.cornell_box(32, 24), drt.make_opts(8, 4, 1.0, seed=2**40 + 12345))[0]
     assert rel_err(a, ref).max() <= 1e-9
+
+
+def _coincident_scene(drt, first, W=24, H=16):
+    """Three surfaces that every camera ray meets at bit-identical t: the unit
+    plane z = 4 (axis window of the scan), the same plane written with the
+    normal (0, 0, -2) (general-plane window; 8 / (2 d_z) == 4 / d_z exactly) and
+    a copy of one of them.  Each carries its own emitter, so the image tells which
+    one the closest-hit scan kept: pathtracer.hpp:80 keeps the first in scene order."""
+    P = lambda v, n: drt.Param(np.asarray(v, dtype=np.float64), n)
+    shapes = {
+        "axis": drt.Plane((0.0, 0.0, -1.0), -4.0, None, drt.AreaEmitter(P((1.0, 0.0, 0.0), "axis"))),
+        "general": drt.Plane((0.0, 0.0, -2.0), -8.0, None, drt.AreaEmitter(P((0.0, 1.0, 0.0), "general"))),
+        "axis_copy": drt.Plane((0.0, 0.0, -1.0), -4.0, None, drt.AreaEmitter(P((0.0, 0.0, 1.0), "axis_copy"))),
+        "general_copy": drt.Plane((0.0, 0.0, -2.0), -8.0, None, drt.AreaEmitter(P((1.0, 1.0, 0.0), "general_copy"))),
+    }
+    sc = drt.SceneDesc()
+    for name in first:
+        sc.push_back(shapes[name])
+    sc.camera = drt.Camera(W, H).look_at((0.0, 0.0, 0.0), (0.0, 0.0, 1.0))
+    return sc, np.asarray(shapes[first[0]].emitter.emission.value)
+
+
+@pytest.mark.parametrize("order", [("axis", "general", "axis_copy"), ("general", "axis", "general_copy"),
+                                   ("axis_copy", "axis", "general"), ("general_copy", "general", "axis")])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_exact_ties_keep_the_lower_scene_index(drt, ctx, order, precision):
+    scene, colour = _coincident_scene(drt, order)
+    kw = dict(spp=4, min_bounces=2, absorb=1.0)
+    ctx.upload(scene)
+    img, grad = ctx.render(drt.make_opts(precision=drt.F64 if precision == "f64" else drt.F32, **kw))
+    ref_img, ref_grad = restate_render(scene, drt.make_opts(**kw))
+    assert np.array_equal(ref_img, np.broadcast_to(colour, ref_img.shape))       # the oracle keeps scene-order shape 0
+    assert np.array_equal(img, ref_img)
+    assert np.array_equal(grad, ref_grad)
