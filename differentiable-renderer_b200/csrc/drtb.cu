@@ -1036,6 +1036,19 @@ int drtb_create(int device, drtb_ctx** out)
         delete ctx;
         return fail(nullptr, DRTB_ERR_CUDA, "context setup failed: " + m);
     }
+    {   // (sin, cos)(2 pi i 2^23 / M) for Real<double>::sincos_tab, in long double on the host
+        static double2 tab[drtb::kSinCosEntries];
+        const long double two_pi = 6.283185307179586476925286766559005768L;
+        for (int i = 0; i < drtb::kSinCosEntries; ++i) {
+            const long double ang = two_pi * ((long double)i * (long double)(1u << drtb::kSinCosShift)) / 2147483647.0L;
+            tab[i] = make_double2(double(sinl(ang)), double(cosl(ang)));
+        }
+        if (cudaMemcpyToSymbol(drtb::g_sincos_tab, tab, sizeof(tab)) != cudaSuccess) {
+            std::string m = cudaGetErrorString(cudaGetLastError());
+            drtb_destroy(ctx);
+            return fail(nullptr, DRTB_ERR_CUDA, "context setup failed: " + m);
+        }
+    }
     *out = ctx;
     return DRTB_OK;
 }

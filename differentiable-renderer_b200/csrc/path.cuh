@@ -120,6 +120,7 @@ struct BlockScene {
     int8_t  type[kMaxPrims];
     int8_t  mtype[kMaxPrims];
     R       expo[kMaxPrims];
+    SinCosTab<R> tab;                    // double: (sin, cos) table of Real<double>::sincos_tab
 };
 
 template <typename R>
@@ -136,6 +137,8 @@ __device__ __forceinline__ void load_block_scene(BlockScene<R>& bs, const DevSce
     }
     if (sc.n_params <= kMaxParams)
         for (int i = threadIdx.x; i < sc.n_params * 3; i += blockDim.x) bs.param[i] = R(params[i]);
+    if constexpr (Real<R>::kTable)
+        for (int i = threadIdx.x; i < kSinCosEntries; i += blockDim.x) bs.tab.t[i] = g_sincos_tab[i];
 }
 
 // ---------------------------------------------------------------------------
@@ -321,20 +324,19 @@ __device__ __forceinline__ void unit_frame(V3<R> n, V3<R>& tg, V3<R>& bt)
 
 // ---------------------------------------------------------------------------
 // DiffuseBxDF::sample (bxdf.hpp:69-79) + angle_to_dir (:43-52) on the frame
-// (tg, bt, n), then cos = dot(n, dir_out) (pathtracer.hpp:103).  Returns
+// (tg, bt, n), then cos = dot(n, dir_out) (pathtracer.hpp:103).  (sp, cp) =
+// (sin, cos)(phi), phi = 2 pi u_phi, come from the caller.  Returns
 // w = cos / pdf.  n is used RAW (the non-unit green-wall normal stays non-unit).
 // sin(asin(sqrt u)) = sqrt u, cos(asin(sqrt u)) = sqrt(1 - u); u < 1 always, so
 // one rsqrt(1 - u) yields both cos(theta) and the 1/cos(theta) that pdf needs.
 // ---------------------------------------------------------------------------
 template <typename R>
-__device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, V3<R> tg, V3<R> bt, R u_theta, R u_phi, R& w)
+__device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, V3<R> tg, V3<R> bt, R u_theta, R sp, R cp, R& w)
 {
     const R st = Real<R>::sqrt(u_theta);
     const R om = R(1) - u_theta;
     const R inv_ct = Real<R>::rsqrt(om);
     const R ct = om * inv_ct;
-    R sp, cp;
-    Real<R>::sincos2pi(u_phi, &sp, &cp);
     const R x = cp * st, y = sp * st;
     const V3<R> dout = {x * tg.x + y * bt.x + ct * n.x,
                         x * tg.y + y * bt.y + ct * n.y,
@@ -358,12 +360,10 @@ __device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, V3<R> tg, V3<R> bt, R u
 // and a lobe argument above 1 (non-unit plane normal) yields NaN, as upstream.
 // ---------------------------------------------------------------------------
 template <typename R>
-__device__ __forceinline__ V3<R> specular_sample(V3<R> n, V3<R> tg, V3<R> bt, V3<R> d, R expo, R u_theta, R u_phi, R& w)
+__device__ __forceinline__ V3<R> specular_sample(V3<R> n, V3<R> tg, V3<R> bt, V3<R> d, R expo, R u_theta, R sp, R cp, R& w)
 {
     const R ct2 = Real<R>::pow(u_theta, Real<R>::div(R(2), expo + R(2)));
     const R ct = Real<R>::sqrt(ct2), st = Real<R>::sqrt(R(1) - ct2);
-    R sp, cp;
-    Real<R>::sincos2pi(u_phi, &sp, &cp);
     const R x = cp * st, y = sp * st;
     V3<R> h = {x * tg.x + y * bt.x + ct * n.x, x * tg.y + y * bt.y + ct * n.y, x * tg.z + y * bt.z + ct * n.z};
     const V3<R> din = {-d.x, -d.y, -d.z};                              // pathtracer.hpp:101, 109
@@ -473,6 +473,8 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
         if constexpr (kSync) live = __ballot_sync(live, alive);
         if (!alive) break;
         if (depth >= min_bounces) {                         // Russian roulette, :128-130
+            // every draw is < 1 (k <= M - 1), so absorb >= 1 ends the path whatever the draw says
+            if (absorb >= 1.0) { alive = false; continue; }
             double u = Real<double>::uniform(stream_draw_base(base, slot++));
             if (u < absorb) { alive = false; continue; }
         }
@@ -518,19 +520,20 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
             }
         }
         R u_theta = Real<R>::uniform_fast(stream_draw_base(base, slot));
-        R u_phi   = Real<R>::uniform_fast(stream_draw_base(base, slot + 1));
+        R sp, cp;                                           // phi = 2 * pi * uniform(), bxdf.hpp:74
+        Real<R>::sincos_tab(bs.tab, stream_draw_base(base, slot + 1), &sp, &cp);
         slot += 2;
         R w;
         V3<R> dout;
         bool spec = false;
         if constexpr (SPEC) spec = !on_mesh && bs.mtype[k] == DRTB_SPECULAR;
         if (spec) {
-            dout = specular_sample(nrm, tg, bt, d, bs.expo[k], u_theta, u_phi, w);
+            dout = specular_sample(nrm, tg, bt, d, bs.expo[k], u_theta, sp, cp, w);
             // upstream a NaN/inf weight poisons the path even if it never meets the light (NaN * 0):
             // such a path must run the sweeps, which then produce the reference's NaN
             lit |= !(Real<R>::abs(w) < Real<R>::inf());
         } else {
-            dout = diffuse_sample(nrm, tg, bt, u_theta, u_phi, w);
+            dout = diffuse_sample(nrm, tg, bt, u_theta, sp, cp, w);
         }
         rec.w_[n++] = w;
         const R eps = Real<R>::origin_eps();                // 1e-3, pathtracer.hpp:99

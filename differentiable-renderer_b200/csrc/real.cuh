@@ -22,13 +22,30 @@ template <typename R> struct Real;
 struct ConstF64 {
     double sin_c[8], cos_c[8];
     double half_pi, pi, inv_pi, inv_m, m, origin_eps;
+    double tab_s[3], tab_c[2], tab_step;         // sincos_tab: -1/7!, 1/5!, -1/3! ; -1/6!, 1/4! ; 2 pi / M
 };
 __constant__ ConstF64 kC64 = {
     {2.8114572543455206e-15, -7.6471637318198164e-13, 1.6059043836821613e-10, -2.5052108385441720e-08,
      2.7557319223985893e-06, -1.9841269841269841e-04, 8.3333333333333332e-03, -1.6666666666666666e-01},
     {-1.5619206968586225e-16, 4.7794773323873853e-14, -1.1470745597729725e-11, 2.0876756987868100e-09,
      -2.7557319223985888e-07, 2.4801587301587302e-05, -1.3888888888888889e-03, 4.1666666666666664e-02},
-    1.5707963267948966, 3.14159265358979323846, 0.31830988618379067154, 1.0 / 2147483647.0, 2147483647.0, 1e-3};
+    1.5707963267948966, 3.14159265358979323846, 0.31830988618379067154, 1.0 / 2147483647.0, 2147483647.0, 1e-3,
+    {-1.984126984126984e-04, 8.333333333333333e-03, -1.6666666666666666e-01},
+    {-1.388888888888889e-03, 4.1666666666666664e-02}, 2.925836159896768e-09};
+
+// sin/cos(2 pi k / M) for the 31-bit draw k (M = 2^31 - 1): the draw's top bits
+// pick (sin, cos)(a_i) from a table, a_i = 2 pi (i 2^23) / M, the low bits are a
+// small angle delta = 2 pi j / M, |delta| <= pi/256, and the angle-sum formulas
+// need only degree-7 / degree-6 Taylor polynomials of it (truncation < 2e-20).
+// No quadrant logic, no float-to-int conversion: 12 FP64 instructions and one
+// 16-byte shared-memory load against ~24 + 11 integer ones for sincos2pi().
+// The table is filled on the host in long double (drtb_create) and staged into
+// shared memory per block (BlockScene).
+constexpr int kSinCosShift = 23;
+constexpr int kSinCosEntries = (1 << (31 - kSinCosShift)) + 1;      // 257 (index 256: k + 2^22 carries)
+__device__ double2 g_sincos_tab[kSinCosEntries];
+template <typename R> struct SinCosTab { };                          // float: sincospif
+template <> struct SinCosTab<double> { double2 t[kSinCosEntries]; };
 
 template <> struct Real<double> {
     static __device__ __forceinline__ double pi() { return kC64.pi; }           // constants.hpp:9
@@ -122,6 +139,23 @@ template <> struct Real<double> {
         *s = __hiloint2double(__double2hiint(a) ^ sflip, __double2loint(a));
         *c = __hiloint2double(__double2hiint(b) ^ cflip, __double2loint(b));
     }
+    static constexpr bool kTable = true;
+    static __device__ __forceinline__ void sincos_tab(const SinCosTab<double>& tab, uint32_t k, double* s, double* c)
+    {
+        const uint32_t i = (k + (1u << (kSinCosShift - 1))) >> kSinCosShift;
+        const int j = int(k - (i << kSinCosShift));              // [-2^22, 2^22)
+        const double2 sc = tab.t[i];
+        const double d = double(j) * kC64.tab_step;
+        const double d2 = d * d;
+        double ps = ::fma(d2, kC64.tab_s[0], kC64.tab_s[1]);
+        ps = ::fma(ps, d2, kC64.tab_s[2]);
+        const double sn = ::fma(ps * d2, d, d);                  // sin(delta)
+        double pc = ::fma(d2, kC64.tab_c[0], kC64.tab_c[1]);
+        pc = ::fma(pc, d2, -0.5);
+        const double cm1 = pc * d2;                              // cos(delta) - 1
+        *s = ::fma(sc.x, cm1, ::fma(sc.y, sn, sc.x));
+        *c = ::fma(sc.y, cm1, ::fma(-sc.x, sn, sc.y));
+    }
     // random::uniform(): double(k) / RAND_MAX (random.hpp:9), correctly rounded:
     // q0 = RN(k/M) up to 1 ulp, one FMA residual step makes it exact (Markstein).
     static __device__ __forceinline__ double uniform(uint32_t k)
@@ -159,6 +193,11 @@ template <> struct Real<float> {
     }
     static __device__ __forceinline__ float pow(float a, float b) { return ::powf(a, b); }
     static __device__ __forceinline__ void sincos2pi(float u, float* s, float* c) { ::sincospif(2.0f * u, s, c); }
+    static constexpr bool kTable = false;
+    static __device__ __forceinline__ void sincos_tab(const SinCosTab<float>&, uint32_t k, float* s, float* c)
+    {
+        sincos2pi(uniform(k), s, c);
+    }
     // Top 24 bits of the 31-bit draw: u in [0, 1 - 2^-24], never 1.0f
     // (float(k/2147483647.0) would round the top ~64 draws to 1 and make
     // pdf = cos(theta)/pi = 0).

@@ -105,6 +105,7 @@ __device__ __forceinline__ bool wf_begin_segment(const DevScene<R>& sc, const Wf
                                                  uint32_t& truncated)
 {
     if (depth >= a.min_bounces) {
+        if (a.absorb >= 1.0) return false;               // every draw is < 1
         const double u = Real<double>::uniform(stream_draw_base(base, slot++));
         if (u < a.absorb) return false;
     }
@@ -286,10 +287,10 @@ wf_traverse_brute(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
 // Out of line: the lobe code (three pow calls) must not raise the register count of the
 // all-diffuse shade stage, which runs at 4 blocks of 256 threads per SM.
 template <typename R>
-__device__ __noinline__ void wf_specular_sample(const V3<R>* in /* n, tg, bt, d */, R expo, R u_theta, R u_phi, R* out /* dout.xyz, w */)
+__device__ __noinline__ void wf_specular_sample(const V3<R>* in /* n, tg, bt, d */, R expo, R u_theta, R sp, R cp, R* out /* dout.xyz, w */)
 {
     R w;
-    const V3<R> dout = specular_sample(in[0], in[1], in[2], in[3], expo, u_theta, u_phi, w);
+    const V3<R> dout = specular_sample(in[0], in[1], in[2], in[3], expo, u_theta, sp, cp, w);
     out[0] = dout.x; out[1] = dout.y; out[2] = dout.z; out[3] = w;
 }
 
@@ -346,7 +347,8 @@ wf_shade(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArgs 
                     wf_pixel_of(sc, a, a.first_path + p, pix, i, x, y);
                     const uint64_t base = wf_base(sc, a, x, y, i);
                     const R u_theta = Real<R>::uniform_fast(stream_draw_base(base, slot));
-                    const R u_phi = Real<R>::uniform_fast(stream_draw_base(base, slot + 1));
+                    R sp, cp;                                     // phi = 2 * pi * uniform(), bxdf.hpp:74
+                    Real<R>::sincos_tab(bs.tab, stream_draw_base(base, slot + 1), &sp, &cp);
                     slot += 2;
                     R w;
                     V3<R> dout;
@@ -354,11 +356,11 @@ wf_shade(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArgs 
                     if (a.specular && k < a.mesh.n_prims && bs.mtype[k] == DRTB_SPECULAR) {
                         const V3<R> in[4] = {nrm, tg, bt, d};
                         R out[4];
-                        wf_specular_sample<R>(in, bs.expo[k], u_theta, u_phi, out);
+                        wf_specular_sample<R>(in, bs.expo[k], u_theta, sp, cp, out);
                         dout = {out[0], out[1], out[2]}; w = out[3];
                         lit |= !(Real<R>::abs(w) < Real<R>::inf());   // NaN * 0 = NaN upstream: see trace_path
                     } else
-                        dout = diffuse_sample(nrm, tg, bt, u_theta, u_phi, w);
+                        dout = diffuse_sample(nrm, tg, bt, u_theta, sp, cp, w);
                     b.rec_w[(size_t)n * a.batch + p] = w;
                     ++n;
                     const R eps = Real<R>::origin_eps();          // 1e-3, pathtracer.hpp:99

@@ -11,7 +11,7 @@ for line in out.splitlines():
     if m:
         cur = m.group(1); continue
     if cur and pat in cur:
-        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        m = re.match(r"\s+/\*[0-9a-f]{4,5}\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
         if m: ops[m.group(2)] += 1
 tot = sum(ops.values())
 fp64 = sum(v for k, v in ops.items() if k in ("DFMA", "DMUL", "DADD", "DSETP"))
