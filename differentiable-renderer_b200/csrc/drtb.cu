@@ -114,7 +114,6 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     using Id = typename PrimId<MESH>::type;
     extern __shared__ double s_dyn[];              // [acc: n_params*3*kBlock doubles][rings]
     __shared__ BlockScene<R> bs;
-    __shared__ double s_red[kSmallP * 3][kWarpsPerBlock];
 
     // gradient sink: per-thread columns (SMALLP), shared atomic columns (analytic scenes with
     // more parameters) or global atomics (mesh scenes with more parameters)
@@ -135,7 +134,6 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     const int ppw = spp >= 32 ? 1 : 32 / spp;
     const int passes = spp >= 32 ? (spp + 31) / 32 : 1;
     const long long n_tasks = (npix + ppw - 1) / ppw;
-    const long long n_warps = (long long)gridDim.x * kWarpsPerBlock;
     const R inv_p = a.absorb < 1.0 ? R(1.0 / (1.0 - a.absorb)) : R(0);
 
     // this warp's ring (QUEUE only)
@@ -157,127 +155,136 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     TraceCounters cnt;
     uint32_t n_lit = 0;
 
-    for (long long task = (long long)blockIdx.x * kWarpsPerBlock + warp; task < n_tasks; task += n_warps) {
-        const int sub = spp >= 32 ? 0 : lane / spp;           // pixel within the task
-        const int i0 = spp >= 32 ? lane : lane % spp;         // first sample of this lane
-        const long long pix = task * ppw + sub;
-        const bool lane_ok = sub < ppw && pix < npix;
-        int x = 0, y = 0;
-        R g0[3] = {R(0), R(0), R(0)};
-        if (lane_ok) {
-            const int r = int(pix / W);
-            x = int(pix - (long long)r * W);
-            y = a.shard_count > 1 ? ((r / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + r % a.band_rows
-                                  : r;
-            if (want_grad) {
+    // Dynamic distribution.  Warps that own equal shares of the image still finish up to ~20 % apart
+    // (the schedulers do not serve resident warps evenly), and an SM whose warps have started to
+    // retire issues less: with a static round-robin the last tenth of the kernel ran on a
+    // half-empty machine.  So a warp claims the next CHUNK of `chunk_tasks` consecutive tasks from
+    // a global counter until none are left.  A chunk's gradient partial is flushed by the warp
+    // that ran it (SMALLP), so the sums do not depend on who ran what: results stay bit-reproducible.
+    for (;;) {
+        unsigned long long claimed = 0;
+        if (lane == 0) claimed = atomicAdd(a.task_counter, 1ull);
+        const long long chunk = (long long)__shfl_sync(0xffffffffu, claimed, 0);
+        const long long task0 = chunk * a.chunk_tasks;
+        if (task0 >= n_tasks) break;
+        const long long task1 = task0 + a.chunk_tasks < n_tasks ? task0 + a.chunk_tasks : n_tasks;
+        for (long long task = task0; task < task1; ++task) {
+            const int sub = spp >= 32 ? 0 : lane / spp;           // pixel within the task
+            const int i0 = spp >= 32 ? lane : lane % spp;         // first sample of this lane
+            const long long pix = task * ppw + sub;
+            const bool lane_ok = sub < ppw && pix < npix;
+            int x = 0, y = 0;
+            R g0[3] = {R(0), R(0), R(0)};
+            if (lane_ok) {
+                const int r = int(pix / W);
+                x = int(pix - (long long)r * W);
+                y = a.shard_count > 1 ? ((r / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + r % a.band_rows
+                                      : r;
+                if (want_grad) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    g0[c] = R(a.seed_scale * (a.seed_img ? a.seed_img[pix * 3 + c] : 1.0));
+                    for (int c = 0; c < 3; ++c)
+                        g0[c] = R(a.seed_scale * (a.seed_img ? a.seed_img[pix * 3 + c] : 1.0));
+                }
             }
-        }
-        double acc[3] = {0.0, 0.0, 0.0};
-        double gacc[3] = {0.0, 0.0, 0.0};          // GEN: this lane's share of the pixel's gradient-image value
+            double acc[3] = {0.0, 0.0, 0.0};
+            double gacc[3] = {0.0, 0.0, 0.0};          // GEN: this lane's share of the pixel's gradient-image value
 
-        // sweeps over one record; accumulates this lane's share of the pixel and the gradients
-        auto sweep = [&](const auto& rec, int n) {
-            R L0[3];
-            auto run = [&](auto& sink) { radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, sink); };
-            if constexpr (GEN) {
-                if constexpr (SMALLP)             { PixelSink<SmemSink> s{ssink, a.gimg_param, gacc}; run(s); }
-                else if constexpr (kSharedAtomic) { PixelSink<SmemAtomicSink> s{msink, a.gimg_param, gacc}; run(s); }
-                else                              { PixelSink<AtomicSink> s{asink, a.gimg_param, gacc}; run(s); }
-            } else {
-                if constexpr (SMALLP)             run(ssink);
-                else if constexpr (kSharedAtomic) run(msink);
-                else                              run(asink);
-            }
-            acc[0] += double(L0[0]); acc[1] += double(L0[1]); acc[2] += double(L0[2]);       // render.cpp:78
-            n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
-        };
-        // run the sweeps on the first m queued records, one per lane
-        auto drain = [&](int m) {
-            __syncwarp();
-            if (lane < m) {
-                const int slot = (q_head + lane) & (kQueueSlots - 1);
-                QueueView<R, MESH> qv{ring_w + slot, ring_prim + slot};
-                sweep(qv, ring_n[slot]);
-            }
-            __syncwarp();
-            q_head = (q_head + m) & (kQueueSlots - 1);
-            q_count -= m;
-        };
+            // sweeps over one record; accumulates this lane's share of the pixel and the gradients
+            auto sweep = [&](const auto& rec, int n) {
+                R L0[3];
+                auto run = [&](auto& sink) { radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, sink); };
+                if constexpr (GEN) {
+                    if constexpr (SMALLP)             { PixelSink<SmemSink> s{ssink, a.gimg_param, gacc}; run(s); }
+                    else if constexpr (kSharedAtomic) { PixelSink<SmemAtomicSink> s{msink, a.gimg_param, gacc}; run(s); }
+                    else                              { PixelSink<AtomicSink> s{asink, a.gimg_param, gacc}; run(s); }
+                } else {
+                    if constexpr (SMALLP)             run(ssink);
+                    else if constexpr (kSharedAtomic) run(msink);
+                    else                              run(asink);
+                }
+                acc[0] += double(L0[0]); acc[1] += double(L0[1]); acc[2] += double(L0[2]);       // render.cpp:78
+                n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
+            };
+            // run the sweeps on the first m queued records, one per lane
+            auto drain = [&](int m) {
+                __syncwarp();
+                if (lane < m) {
+                    const int slot = (q_head + lane) & (kQueueSlots - 1);
+                    QueueView<R, MESH> qv{ring_w + slot, ring_prim + slot};
+                    sweep(qv, ring_n[slot]);
+                }
+                __syncwarp();
+                q_head = (q_head + m) & (kQueueSlots - 1);
+                q_count -= m;
+            };
 
-        for (int pass = 0; pass < passes; ++pass) {
-            const int i = i0 + pass * 32;
-            bool lit = false;
-            int n = 0;
-            PathRecord<R, MESH, QUEUE ? kQueueDepth : kMaxDepth> rec;
-            if (lane_ok && i < spp) {
-                const uint64_t key = a.key0 + ((uint64_t)y * W + x) * (uint64_t)spp + (uint64_t)i;
-                const uint64_t base = key * kKeyMul;
-                V3<R> o = {sc.eye[0], sc.eye[1], sc.eye[2]};
-                V3<R> d = camera_ray(sc, x, y, base);
-                n = trace_path<R, MESH, QUEUE ? kQueueDepth : kMaxDepth, GEN>(sc, bs, mat, no_bvh, base, 2u, o, d, a.min_bounces,
-                                                                              a.absorb, a.max_depth, rec, lit, cnt);
-                if (!QUEUE && lit) sweep(rec, n);
-            }
-            if (QUEUE) {
-                const unsigned m = __ballot_sync(0xffffffffu, lit);
-                if (lit) {
-                    const int slot = (q_head + q_count + __popc(m & ((1u << lane) - 1u))) & (kQueueSlots - 1);
-                    for (int v = 0; v < n; ++v) {
-                        ring_w[v * kQueueSlots + slot] = rec.w_[v];
-                        ring_prim[v * kQueueSlots + slot] = rec.prim_[v];
+            for (int pass = 0; pass < passes; ++pass) {
+                const int i = i0 + pass * 32;
+                bool lit = false;
+                int n = 0;
+                PathRecord<R, MESH, QUEUE ? kQueueDepth : kMaxDepth> rec;
+                if (lane_ok && i < spp) {
+                    const uint64_t key = a.key0 + ((uint64_t)y * W + x) * (uint64_t)spp + (uint64_t)i;
+                    const uint64_t base = key * kKeyMul;
+                    V3<R> o = {sc.eye[0], sc.eye[1], sc.eye[2]};
+                    V3<R> d = camera_ray(sc, x, y, base);
+                    n = trace_path<R, MESH, QUEUE ? kQueueDepth : kMaxDepth, GEN>(sc, bs, mat, no_bvh, base, 2u, o, d, a.min_bounces,
+                                                                                  a.absorb, a.max_depth, rec, lit, cnt);
+                    if (!QUEUE && lit) sweep(rec, n);
+                }
+                if (QUEUE) {
+                    const unsigned m = __ballot_sync(0xffffffffu, lit);
+                    if (lit) {
+                        const int slot = (q_head + q_count + __popc(m & ((1u << lane) - 1u))) & (kQueueSlots - 1);
+                        for (int v = 0; v < n; ++v) {
+                            ring_w[v * kQueueSlots + slot] = rec.w_[v];
+                            ring_prim[v * kQueueSlots + slot] = rec.prim_[v];
+                        }
+                        ring_n[slot] = uint8_t(n);
                     }
-                    ring_n[slot] = uint8_t(n);
+                    q_count += __popc(m);
+                    if (q_count >= 32) drain(32);
                 }
-                q_count += __popc(m);
-                if (q_count >= 32) drain(32);
             }
-        }
-        // every queued record belongs to this task's pixel: finish them before the pixel is written
-        if (QUEUE && q_count > 0) drain(q_count);
+            // every queued record belongs to this task's pixel: finish them before the pixel is written
+            if (QUEUE && q_count > 0) drain(q_count);
 
-        // pixel_radiance / samples (render.cpp:82): sum the lanes of each pixel
-        auto write_pixel = [&](double* dst, double* v, bool mean) {
-            if (spp >= 32) {
+            // pixel_radiance / samples (render.cpp:82): sum the lanes of each pixel
+            auto write_pixel = [&](double* dst, double* v, bool mean) {
+                if (spp >= 32) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[c] = warp_sum(v[c]);
-                if (lane == 0 && lane_ok) {
+                    for (int c = 0; c < 3; ++c) v[c] = warp_sum(v[c]);
+                    if (lane == 0 && lane_ok) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) dst[pix * 3 + c] = mean ? v[c] / double(spp) : v[c];
-                }
-            } else {
-                double tot[3] = {v[0], v[1], v[2]};
-                for (int j = 1; j < spp; ++j) {
+                        for (int c = 0; c < 3; ++c) dst[pix * 3 + c] = mean ? v[c] / double(spp) : v[c];
+                    }
+                } else {
+                    double tot[3] = {v[0], v[1], v[2]};
+                    for (int j = 1; j < spp; ++j) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        double o = __shfl_down_sync(0xffffffffu, v[c], j);
-                        if (i0 + j < spp) tot[c] += o;
+                        for (int c = 0; c < 3; ++c) {
+                            double o = __shfl_down_sync(0xffffffffu, v[c], j);
+                            if (i0 + j < spp) tot[c] += o;
+                        }
+                    }
+                    if (lane_ok && i0 == 0) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) dst[pix * 3 + c] = mean ? tot[c] / double(spp) : tot[c];
                     }
                 }
-                if (lane_ok && i0 == 0) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) dst[pix * 3 + c] = mean ? tot[c] / double(spp) : tot[c];
-                }
-            }
-        };
-        if (a.img) write_pixel(a.img, acc, true);
-        if constexpr (GEN) { if (a.gimg) write_pixel(a.gimg, gacc, false); }
-    }
-
-    if (SMALLP && want_grad) {
-        // block reduction in a fixed order: lanes (xor tree) -> warps (0..3)
-        for (int j = 0; j < P3; ++j) {
-            double v = warp_sum(s_acc[j * kBlock + threadIdx.x]);
-            if (lane == 0) s_red[j][warp] = v;
+            };
+            if (a.img) write_pixel(a.img, acc, true);
+            if constexpr (GEN) { if (a.gimg) write_pixel(a.gimg, gacc, false); }
         }
-        __syncthreads();
-        if (threadIdx.x < P3) {
-            double v = 0.0;
-#pragma unroll
-            for (int w = 0; w < kWarpsPerBlock; ++w) v += s_red[threadIdx.x][w];
-            a.grad_partial[(size_t)blockIdx.x * P3 + threadIdx.x] = v;
+        if (SMALLP && want_grad) {
+            // this chunk's gradient: the lanes' columns summed by an xor tree, one row per chunk
+            double mine = 0.0;
+            for (int j = 0; j < P3; ++j) {
+                const double v = warp_sum(s_acc[j * kBlock + threadIdx.x]);
+                s_acc[j * kBlock + threadIdx.x] = 0.0;
+                if (lane == j) mine = v;
+            }
+            if (lane < P3) a.grad_partial[(size_t)chunk * P3 + lane] = mine;
         }
     }
     if (kSharedAtomic && want_grad) {
@@ -316,21 +323,26 @@ __global__ void iota_kernel(int* __restrict__ v, int n)
     if (i < n) v[i] = i;
 }
 
-// grad[j] = sum_b partial[b][j], b ascending inside each thread, then a fixed tree.
+// out[blockIdx.x][j] = sum of partial[r][j] over this block's rows
+// [blockIdx.x * rows_per_block, ...): r ascending inside each thread, then a fixed
+// tree.  One block over all rows gives grad[j]; many rows take two passes
+// (reduce_partials below).
 __global__ void __launch_bounds__(256)
-reduce_grad_kernel(const double* __restrict__ partial, int n_blocks, int P3, double* __restrict__ grad)
+reduce_grad_kernel(const double* __restrict__ partial, int n_rows, int rows_per_block, int P3, double* __restrict__ out)
 {
     __shared__ double s[256];
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(n_rows, r0 + rows_per_block);
     for (int j = 0; j < P3; ++j) {
         double v = 0.0;
-        for (int b = threadIdx.x; b < n_blocks; b += 256) v += partial[(size_t)b * P3 + j];
+        for (int r = r0 + threadIdx.x; r < r1; r += 256) v += partial[(size_t)r * P3 + j];
         s[threadIdx.x] = v;
         __syncthreads();
         for (int o = 128; o > 0; o >>= 1) {
             if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
             __syncthreads();
         }
-        if (threadIdx.x == 0) grad[j] = s[0];
+        if (threadIdx.x == 0) out[(size_t)blockIdx.x * P3 + j] = s[0];
         __syncthreads();
     }
 }
@@ -532,6 +544,7 @@ struct drtb_ctx {
     // wavefront buffers (mesh scenes), grown on demand
     void* wf_mem = nullptr;       size_t wf_cap = 0;
     bool mesh_megakernel = false; // DRTB_MESH_PIPELINE=megakernel: trace meshes inside render_kernel (A/B aid)
+    unsigned long long* d_task_counter = nullptr;
 };
 
 namespace {
@@ -674,34 +687,72 @@ int occupancy(drtb_ctx* ctx, K kernel, size_t smem, int& out)
     return DRTB_OK;
 }
 
+// grad[j] = sum over `rows` partial rows, in an order fixed by `rows` alone.  Up to 4096 rows:
+// one block.  More (a large render leaves one row per chunk of warp tasks): a first pass of
+// 256-row blocks into the scratch rows behind the partials, then one block over those.
+constexpr int kReduceDirectRows = 4096;
+inline size_t reduce_scratch_rows(size_t rows) { return rows > kReduceDirectRows ? (rows + 255) / 256 : 0; }
+int reduce_partials(drtb_ctx* ctx, double* partial, size_t rows, int P3, double* d_grad, cudaStream_t stream)
+{
+    if (rows <= kReduceDirectRows) {
+        reduce_grad_kernel<<<1, 256, 0, stream>>>(partial, int(rows), int(rows), P3, d_grad);
+        ctx->launches++;
+    } else {
+        double* scratch = partial + rows * P3;
+        const int nb = int(reduce_scratch_rows(rows));
+        reduce_grad_kernel<<<nb, 256, 0, stream>>>(partial, int(rows), 256, P3, scratch);
+        reduce_grad_kernel<<<1, 256, 0, stream>>>(scratch, nb, nb, P3, d_grad);
+        ctx->launches += 2;
+    }
+    CK(ctx, cudaGetLastError());
+    return DRTB_OK;
+}
+
 template <typename R, bool SMALLP, bool QUEUE, bool MESH, bool GEN>
-int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t smem, long long need_blocks,
-                   int P3, bool want_grad, cudaStream_t stream, int& grid_out)
+int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t smem, long long n_tasks,
+                   int P3, bool want_grad, cudaStream_t stream, size_t& rows_out)
 {
     int per_sm = 0;
     int rc = occupancy(ctx, render_kernel<R, SMALLP, QUEUE, MESH, GEN>, smem, per_sm);
     if (rc != DRTB_OK) return rc;
+    const long long need_blocks = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > need_blocks) grid = need_blocks;
     if (grid < 1) grid = 1;
-    if (want_grad && (SMALLP || !MESH)) {
-        rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, size_t(grid) * P3);
+    // Chunks of warp tasks (render_kernel): about 1024 paths each, so that claiming one and flushing
+    // its gradient row cost nothing, but never so large that a warp gets fewer than ~8 of them.
+    const long long paths_per_task = a.spp >= 32 ? a.spp : 32;
+    long long chunk = std::max<long long>(1, 1024 / paths_per_task);
+    chunk = std::max<long long>(1, std::min(chunk, n_tasks / (8 * grid * kWarpsPerBlock)));
+    if (const char* e = std::getenv("DRTB_CHUNK_TASKS")) chunk = std::max(1, std::atoi(e));     // A/B aid
+    a.chunk_tasks = int(chunk);
+    const long long n_chunks = (n_tasks + chunk - 1) / chunk;
+    if (!ctx->d_task_counter) CK(ctx, cudaMalloc(&ctx->d_task_counter, sizeof(unsigned long long)));
+    CK(ctx, cudaMemsetAsync(ctx->d_task_counter, 0, sizeof(unsigned long long), stream));
+    a.task_counter = ctx->d_task_counter;
+    // gradient partials: one row per chunk (SMALLP, summed in chunk order whoever ran the chunk) or
+    // per block (shared atomic columns)
+    size_t rows = 0;
+    if (want_grad && SMALLP) rows = size_t(n_chunks);
+    else if (want_grad && !MESH) rows = size_t(grid);
+    if (rows) {
+        rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (rows + reduce_scratch_rows(rows)) * P3);
         if (rc != DRTB_OK) return rc;
         a.grad_partial = ctx->d_partial;
     }
     render_kernel<R, SMALLP, QUEUE, MESH, GEN><<<int(grid), kBlock, smem, stream>>>(sc, a);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
-    grid_out = int(grid);
+    rows_out = rows;
     return DRTB_OK;
 }
 
 template <typename R>
 int launch_precision(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, bool smallp, bool queue, bool mesh, bool gen,
-                     size_t smem, long long need_blocks, int P3, bool want_grad, cudaStream_t stream, int& grid)
+                     size_t smem, long long n_tasks, int P3, bool want_grad, cudaStream_t stream, size_t& rows)
 {
-#define DRTB_LAUNCH(SP, Q, M) launch_variant<R, SP, Q, M, false>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid)
-#define DRTB_LAUNCH_GEN(SP, Q) launch_variant<R, SP, Q, false, true>(ctx, sc, a, smem, need_blocks, P3, want_grad, stream, grid)
+#define DRTB_LAUNCH(SP, Q, M) launch_variant<R, SP, Q, M, false>(ctx, sc, a, smem, n_tasks, P3, want_grad, stream, rows)
+#define DRTB_LAUNCH_GEN(SP, Q) launch_variant<R, SP, Q, false, true>(ctx, sc, a, smem, n_tasks, P3, want_grad, stream, rows)
     if (gen) {
         // SpecularBxDF materials and/or a gradient image (analytic scenes; mesh scenes take the wavefront)
         if (mesh) return fail(ctx, DRTB_ERR_UNSUPPORTED, "specular materials / gradient images on a mesh scene need the wavefront pipeline");
@@ -825,7 +876,6 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     const long long npix = (long long)rows * W;
     const int ppw = o->spp >= 32 ? 1 : 32 / o->spp;
     const long long n_tasks = (npix + ppw - 1) / ppw;
-    const long long need = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
 
     if (a.stats) {
         CK(ctx, cudaMemsetAsync(d_stats, 0, sizeof(drtb_stats), stream));
@@ -834,15 +884,11 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
         CK(ctx, cudaMemsetAsync(d_grad, 0, sizeof(double) * P3, stream));
         a.grad_atomic = d_grad;
     }
-    int grid = 0;
-    int rc = f32 ? launch_precision<float>(ctx, ctx->sc32, a, smallp, queue, mesh, gen, smem, need, P3, want_grad, stream, grid)
-                 : launch_precision<double>(ctx, ctx->sc64, a, smallp, queue, mesh, gen, smem, need, P3, want_grad, stream, grid);
+    size_t partial_rows = 0;
+    int rc = f32 ? launch_precision<float>(ctx, ctx->sc32, a, smallp, queue, mesh, gen, smem, n_tasks, P3, want_grad, stream, partial_rows)
+                 : launch_precision<double>(ctx, ctx->sc64, a, smallp, queue, mesh, gen, smem, n_tasks, P3, want_grad, stream, partial_rows);
     if (rc != DRTB_OK) return rc;
-    if (want_grad && (smallp || shared_atomic)) {
-        reduce_grad_kernel<<<1, 256, 0, stream>>>(ctx->d_partial, int(grid), P3, d_grad);
-        CK(ctx, cudaGetLastError());
-        ctx->launches++;
-    }
+    if (want_grad && (smallp || shared_atomic)) return reduce_partials(ctx, ctx->d_partial, partial_rows, P3, d_grad, stream);
     return DRTB_OK;
 }
 
@@ -944,7 +990,7 @@ int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opt
         ctx->launches += 2 + 2 * D;
     }
     if (want_grad && smallp) {
-        reduce_grad_kernel<<<1, 256, 0, stream>>>(ctx->d_partial, adj_grid * n_batches, P3, d_grad);
+        reduce_grad_kernel<<<1, 256, 0, stream>>>(ctx->d_partial, adj_grid * n_batches, adj_grid * n_batches, P3, d_grad);
         CK(ctx, cudaGetLastError());
         ctx->launches++;
     }
@@ -1060,7 +1106,7 @@ void drtb_destroy(drtb_ctx* ctx)
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    cudaFree(ctx->d_params); cudaFree(ctx->d_partial); cudaFree(ctx->d_img);
+    cudaFree(ctx->d_params); cudaFree(ctx->d_partial); cudaFree(ctx->d_img); cudaFree(ctx->d_task_counter);
     cudaFree(ctx->d_seed); cudaFree(ctx->d_grad); cudaFree(ctx->d_gimg); cudaFree(ctx->d_stats); cudaFree(ctx->wf_mem);
     free_mesh(ctx);
     delete ctx;

@@ -23,7 +23,10 @@ constexpr int kSlots      = 2 * kFast + kMaxPrims;
 #ifndef DRTB_PACK_HIT
 #define DRTB_PACK_HIT 1
 #endif
-constexpr bool kPackHit   = DRTB_PACK_HIT;   // double analytic kernels: closest hit on integer keys (Closest<double, true>)
+constexpr bool kPackHit   = DRTB_PACK_HIT;
+#ifndef DRTB_SKIP_LAST
+#define DRTB_SKIP_LAST 1           // 0: sample the BxDF at a vertex whose continuation is certainly absorbed (A/B aid)
+#endif   // double analytic kernels: closest hit on integer keys (Closest<double, true>)
 
 // Scene as the kernels see it.  Passed BY VALUE as a __grid_constant__ kernel
 // parameter: the closest-hit scan indexes prim[] with a warp-uniform i, so
@@ -107,6 +110,8 @@ struct RenderArgs {
     int32_t  gimg_param;                 // -1 = none
     int32_t  sink_cols;                  // shared atomic gradient columns (9 .. 64 parameters), a power of two
     MeshView mesh;                       // n_tris == 0: analytic scene only
+    unsigned long long* task_counter;    // zeroed before the launch: next unclaimed chunk of warp tasks
+    int32_t  chunk_tasks;                // consecutive warp tasks per chunk
 };
 
 // Per-block shared copy of what is looked up with a PER-LANE index (the prim a
@@ -469,13 +474,14 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
     constexpr bool kSync = MESH || DRTB_SYNC_DEPTH;         // mesh kernels: the lanes must enter the BVH traversal together
     unsigned live = kSync ? __activemask() : 0u;
     bool alive = true;
+    uint64_t ctr = base + kGolden + slot;                  // splitmix64's increment folded in (rng.cuh)
     for (int depth = 0;; ++depth) {
         if constexpr (kSync) live = __ballot_sync(live, alive);
         if (!alive) break;
         if (depth >= min_bounces) {                         // Russian roulette, :128-130
             // every draw is < 1 (k <= M - 1), so absorb >= 1 ends the path whatever the draw says
             if (absorb >= 1.0) { alive = false; continue; }
-            double u = Real<double>::uniform(stream_draw_base(base, slot++));
+            double u = Real<double>::uniform(stream_draw_ctr(ctr++));
             if (u < absorb) { alive = false; continue; }
         }
         if (n >= max_depth) { ++cnt.truncated; alive = false; continue; }
@@ -494,7 +500,13 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
         const int em = mat.em(k), col = mat.col(k);
         lit |= em >= 0;
         rec.prim_[n] = Id(k);
-        if (col < 0) {                                      // null BxDF, :25-26, 38-39
+        // absorb >= 1: the next trace() call returns 0 before it looks at the ray (:128-129), so this
+        // vertex's scattered term is brdf * 0 * cos / pdf and its w meets only L_{v+1} = 0 in both
+        // sweeps.  For the diffuse BxDF w is always finite, hence unobservable: the two draws, the
+        // frame and the direction are skipped (warp-uniform test).  SpecularBxDF keeps them, its w can
+        // be NaN and NaN * 0 poisons the path upstream.
+        const bool last_vertex = DRTB_SKIP_LAST && !SPEC && absorb >= 1.0 && depth + 1 >= min_bounces;
+        if (col < 0 || last_vertex) {                       // null BxDF, :25-26, 38-39
             rec.w_[n++] = R(0);
             alive = false;
             continue;
@@ -519,10 +531,10 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
                 bt = {bs.frame[k][3], bs.frame[k][4], bs.frame[k][5]};
             }
         }
-        R u_theta = Real<R>::uniform_fast(stream_draw_base(base, slot));
+        R u_theta = Real<R>::uniform_fast(stream_draw_ctr(ctr));
         R sp, cp;                                           // phi = 2 * pi * uniform(), bxdf.hpp:74
-        Real<R>::sincos_tab(bs.tab, stream_draw_base(base, slot + 1), &sp, &cp);
-        slot += 2;
+        Real<R>::sincos_tab(bs.tab, stream_draw_ctr(ctr + 1), &sp, &cp);
+        ctr += 2;
         R w;
         V3<R> dout;
         bool spec = false;

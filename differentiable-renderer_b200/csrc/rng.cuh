@@ -21,11 +21,12 @@ namespace drtb {
 
 constexpr uint64_t kKeyMul   = 0x100000001B3ull;
 constexpr uint64_t kSeedMul  = 0x9E3779B97F4A7C15ull;
+constexpr uint64_t kGolden   = 0x9E3779B97F4A7C15ull;   // splitmix64's increment
 constexpr uint32_t kMersenne = 2147483647u;          // RAND_MAX on glibc
 
 DRTB_HD uint64_t splitmix64(uint64_t x)
 {
-    x += 0x9E3779B97F4A7C15ull;
+    x += kGolden;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
     return x ^ (x >> 31);
@@ -39,6 +40,17 @@ DRTB_HD uint32_t mod_mersenne31(uint64_t x)
     uint32_t y = uint32_t(x & kMersenne) + uint32_t(x >> 31);   // < 2^31 + 5
     return y >= kMersenne ? y - kMersenne : y;
 }
+
+// The same split in two: splitmix64(x) = splitmix64_mix(x + golden), so a path
+// can carry ctr = key * kKeyMul + golden + slot and pay one 64-bit add per draw
+// instead of two.
+DRTB_HD uint64_t splitmix64_mix(uint64_t x)
+{
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+DRTB_HD uint32_t stream_draw_ctr(uint64_t ctr) { return mod_mersenne31(splitmix64_mix(ctr)); }
 
 // base = key * kKeyMul, hoisted once per path.
 DRTB_HD uint32_t stream_draw_base(uint64_t base, uint32_t slot)
