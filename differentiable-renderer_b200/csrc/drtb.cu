@@ -3,8 +3,9 @@
 // Kernel inventory
 //   render_kernel<R, SMALLP>   persistent megakernel: one lane = one path
 //                              (camera sample -> trace -> radiance -> adjoint),
-//                              lanes of a warp = consecutive samples of one pixel
-//   reduce_grad_kernel         fixed-order sum of the per-block gradient partials
+//                              lanes of a warp = consecutive samples of one pixel;
+//                              warps claim chunks of pixels from a global counter
+//   reduce_grad_kernel         fixed-order sum of the per-chunk gradient partials
 //   trace_rays_kernel<R>       Pathtracer::trace on explicit rays (+ Jacobian)
 //   fma_peak_kernel<R>         FMA issue-rate micro-benchmark (roofline denominator)
 //
@@ -104,11 +105,14 @@ struct JacSink {
 #ifndef DRTB_MESH_MIN_BLOCKS
 #define DRTB_MESH_MIN_BLOCKS DRTB_MIN_BLOCKS
 #endif
+#ifndef DRTB_MIN_BLOCKS_F32
+#define DRTB_MIN_BLOCKS_F32 DRTB_MIN_BLOCKS
+#endif
 //   MESH  : a triangle mesh + BVH is attached (ids are 32-bit, parameters in global memory)
 //   GEN   : the general variant -- SpecularBxDF materials (bxdf.hpp:85-124) and the
 //           per-pixel gradient image; the all-diffuse kernels do not carry that code
 template <typename R, bool SMALLP, bool QUEUE, bool MESH, bool GEN>
-__global__ void __launch_bounds__(kBlock, MESH ? DRTB_MESH_MIN_BLOCKS : DRTB_MIN_BLOCKS)
+__global__ void __launch_bounds__(kBlock, MESH ? DRTB_MESH_MIN_BLOCKS : sizeof(R) == 4 ? DRTB_MIN_BLOCKS_F32 : DRTB_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ RenderArgs a)
 {
     using Id = typename PrimId<MESH>::type;
@@ -324,26 +328,29 @@ __global__ void iota_kernel(int* __restrict__ v, int n)
 }
 
 // out[blockIdx.x][j] = sum of partial[r][j] over this block's rows
-// [blockIdx.x * rows_per_block, ...): r ascending inside each thread, then a fixed
-// tree.  One block over all rows gives grad[j]; many rows take two passes
-// (reduce_partials below).
+// [blockIdx.x * rows_per_block, ...).  Thread t owns column t % P3 and every
+// (256 / P3)-th row, so a warp reads consecutive doubles of the row-major
+// partials; the row lanes of a column are then added in ascending order by one
+// thread.  The order depends on (n_rows, rows_per_block, P3) alone.  One block
+// over all rows gives grad[j]; many rows take two passes (reduce_partials).
+// P3 <= 256 (kMaxParams * 3 = 192).
 __global__ void __launch_bounds__(256)
 reduce_grad_kernel(const double* __restrict__ partial, int n_rows, int rows_per_block, int P3, double* __restrict__ out)
 {
     __shared__ double s[256];
+    const int lanes = 256 / P3;                      // row lanes per column
+    const int col = threadIdx.x % P3, rl = threadIdx.x / P3;
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(n_rows, r0 + rows_per_block);
-    for (int j = 0; j < P3; ++j) {
-        double v = 0.0;
-        for (int r = r0 + threadIdx.x; r < r1; r += 256) v += partial[(size_t)r * P3 + j];
-        s[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) out[(size_t)blockIdx.x * P3 + j] = s[0];
-        __syncthreads();
+    double v = 0.0;
+    if (rl < lanes)
+        for (int r = r0 + rl; r < r1; r += lanes) v += partial[(size_t)r * P3 + col];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.x < P3) {
+        double t = 0.0;
+        for (int l = 0; l < lanes; ++l) t += s[l * P3 + threadIdx.x];
+        out[(size_t)blockIdx.x * P3 + threadIdx.x] = t;
     }
 }
 
@@ -689,18 +696,19 @@ int occupancy(drtb_ctx* ctx, K kernel, size_t smem, int& out)
 
 // grad[j] = sum over `rows` partial rows, in an order fixed by `rows` alone.  Up to 4096 rows:
 // one block.  More (a large render leaves one row per chunk of warp tasks): a first pass of
-// 256-row blocks into the scratch rows behind the partials, then one block over those.
-constexpr int kReduceDirectRows = 4096;
-inline size_t reduce_scratch_rows(size_t rows) { return rows > kReduceDirectRows ? (rows + 255) / 256 : 0; }
+// 1024-row blocks into the scratch rows behind the partials, then one block over those.
+constexpr int kReduceDirectRows = 4096, kReduceBlockRows = 1024;
+inline size_t reduce_scratch_rows(size_t rows) { return rows > kReduceDirectRows ? (rows + kReduceBlockRows - 1) / kReduceBlockRows : 0; }
 int reduce_partials(drtb_ctx* ctx, double* partial, size_t rows, int P3, double* d_grad, cudaStream_t stream)
 {
+    if (P3 <= 0 || rows == 0) return DRTB_OK;
     if (rows <= kReduceDirectRows) {
         reduce_grad_kernel<<<1, 256, 0, stream>>>(partial, int(rows), int(rows), P3, d_grad);
         ctx->launches++;
     } else {
         double* scratch = partial + rows * P3;
         const int nb = int(reduce_scratch_rows(rows));
-        reduce_grad_kernel<<<nb, 256, 0, stream>>>(partial, int(rows), 256, P3, scratch);
+        reduce_grad_kernel<<<nb, 256, 0, stream>>>(partial, int(rows), kReduceBlockRows, P3, scratch);
         reduce_grad_kernel<<<1, 256, 0, stream>>>(scratch, nb, nb, P3, d_grad);
         ctx->launches += 2;
     }
