@@ -158,7 +158,7 @@ def run_reference_arm(a):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthr, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=_REAL_STDOUT, flush=True)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -199,11 +199,46 @@ def run_b200_arm(a):
     perm = sharding.deinterleave_index(H, world, band, dev) if (world > 1 and equal) else None
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
+    # ---- N > 1: the image gather is fused into the render kernel (peer stores over NVLink into every
+    # rank's full image, drtb_set_image_peers); checked once against NCCL all-gather + re-interleave.
+    # If the peers cannot be mapped the NCCL gather stays in the step, and the JSON line says which ran.
+    peer, gather = None, "none (1 GPU)"
+    if world > 1:
+        gather = "NCCL all-gather of the row bands"
+        try:
+            peer = sharding.PeerImage(ctx, H, W, dist)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:                                     # noqa: BLE001 -- reported, not hidden
+            print(f"[bench] rank {rank}: peer image unavailable ({e}); using the NCCL gather", file=sys.stderr)
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if (ok.item() == 0 or not equal) and peer is not None:     # ragged shards keep the NCCL-free compact path
+            peer.close(); peer = None
+        if peer is not None:
+            full_p = peer.tensor(dev)
+            full_p.fill_(float("nan"))
+            dist.barrier(); torch.cuda.synchronize()
+            ctx.render_device(opts, 0, 0, d_grad.data_ptr(), 0, stream.cuda_stream)       # peers on: no compact image
+            dist.all_reduce(d_grad, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize(); dist.barrier()
+            ctx.set_image_peers([])
+            ctx.render_device(opts, 0, d_img.data_ptr(), d_grad.data_ptr(), 0, stream.cuda_stream)
+            dist.all_gather_into_tensor(d_full.view(world, rows, W, 3), d_img)
+            ref = d_full.view(H, W, 3)[perm]
+            same = torch.tensor([1.0 if torch.equal(full_p, ref) else 0.0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            if same.item() != 1.0:
+                raise SystemExit("peer-filled image differs from the NCCL all-gather")
+            ctx.set_image_peers(peer.ptrs)
+            gather = "fused: render kernel stores every pixel into all ranks' full images (NVLink peer stores), verified bit-equal to an NCCL all-gather"
+    use_peer = peer is not None
+    img_arg = 0 if use_peer else d_img.data_ptr()
+
     def step_device():
-        ctx.render_device(opts, 0, d_img.data_ptr(), d_grad.data_ptr(), 0, stream.cuda_stream)
+        ctx.render_device(opts, 0, img_arg, d_grad.data_ptr(), 0, stream.cuda_stream)
         if world > 1:
             dist.all_reduce(d_grad, op=dist.ReduceOp.SUM)          # the one collective of the path
-            if equal:
+            if equal and not use_peer:
                 dist.all_gather_into_tensor(d_full.view(world, rows, W, 3), d_img)
 
     # ---- stats run (untimed): segments/path for the algorithmic FLOP count
@@ -238,11 +273,11 @@ def run_b200_arm(a):
     for s0, s1, s2 in ev:
         flush.zero_()                                  # evict L2 between timed iterations (untimed)
         s0.record(stream)
-        ctx.render_device(opts, 0, d_img.data_ptr(), d_grad.data_ptr(), 0, stream.cuda_stream)
+        ctx.render_device(opts, 0, img_arg, d_grad.data_ptr(), 0, stream.cuda_stream)
         s1.record(stream)                              # render + gradient reduction kernels only
         if world > 1:
             dist.all_reduce(d_grad, op=dist.ReduceOp.SUM)
-            if equal:
+            if equal and not use_peer:
                 dist.all_gather_into_tensor(d_full.view(world, rows, W, 3), d_img)
         s2.record(stream)
     sync_all()
@@ -263,6 +298,9 @@ def run_b200_arm(a):
     h_grad = torch.empty((P, 3), dtype=torch.float64).pin_memory()
     g_dev = torch.empty((P, 3), dtype=torch.float64, device=dev)
     pvals = scene.param_values()
+
+    if use_peer:
+        ctx.set_image_peers([])                                          # the host-buffer API returns this rank's rows
 
     def step_e2e():
         ctx.set_params(pvals)                                            # H2D: this step's inputs
@@ -286,6 +324,9 @@ def run_b200_arm(a):
     h2d = P * 3 * 8 * world
     d2h = (H * W * 3 * 8) + P * 3 * 8 * world
 
+    if peer is not None:
+        torch.cuda.synchronize()
+        peer.close()                                                     # collective
     if rank != 0:
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
@@ -331,8 +372,8 @@ def run_b200_arm(a):
         "config": {"workload": workload_name(a), "width": W, "height": H, "spp": spp, "bounces": B,
                    "paths_per_step": int(paths_total), "segments_per_path": segs_total / paths_total,
                    "lit_path_fraction": lit_total / paths_total,
-                   "parallelism": f"pixel-band dp{world} (bands of {band} rows), 1 NCCL all-reduce of {P * 3} doubles"
-                                  + (" + image all-gather" if world > 1 else ""),
+                   "parallelism": f"pixel-band dp{world} (bands of {band} rows), 1 NCCL all-reduce of {P * 3} doubles",
+                   "image_gather": gather,
                    "l2": "flushed between timed iterations (256 MiB memset, untimed)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "drtb_set_params + drtb_render (host buffers, pinned)"},
@@ -345,7 +386,7 @@ def run_b200_arm(a):
         kind, nthr, sample, step = cpu_render_rate(a, seconds_budget=12.0)
         p, dt = step()
         out["cpu_baseline"] = {"value": p / dt / 1e6, "unit": UNIT, "cores": nthr, "kind": kind, "sample": sample}
-    print(json.dumps(out))
+    print(json.dumps(out), file=_REAL_STDOUT, flush=True)
     ctx.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
@@ -353,6 +394,12 @@ def run_b200_arm(a):
 
 def main():
     a = parse_args()
+    # stdout carries the one JSON line and nothing else: libraries that print there (NCCL's version
+    # banner under NCCL_DEBUG=VERSION) are sent to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference_arm(a)
     else:

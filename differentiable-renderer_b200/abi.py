@@ -21,6 +21,8 @@ F64, F32, MIXED = 0, 1, 2
 FLAG_IMAGE, FLAG_GRAD, FLAG_STATS, FLAG_NO_BVH = 1, 2, 4, 8
 
 STREAM_KEY_MUL = 0x9E3779B97F4A7C15
+IPC_HANDLE_BYTES = 64
+MAX_PEERS = 8
 
 
 class Prim(C.Structure):
@@ -87,6 +89,11 @@ SYMBOLS = [
                                          C.POINTER(Stats)]),
     ("drtb_render_grad_image_device", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), C.c_int32, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("drtb_set_image_peers", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]),
+    ("drtb_ipc_alloc", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    ("drtb_ipc_open", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("drtb_ipc_close", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("drtb_ipc_free", C.c_int, [C.c_void_p, C.c_void_p]),
     ("drtb_trace_rays", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), C.c_int64, _dp, _dp,
                                   C.POINTER(C.c_uint64), _dp, _dp]),
     ("drtb_fma_peak", C.c_int, [C.c_void_p, C.c_int32, _dp]),

@@ -169,9 +169,12 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
         unsigned long long claimed = 0;
         if (lane == 0) claimed = atomicAdd(a.task_counter, 1ull);
         const long long chunk = (long long)__shfl_sync(0xffffffffu, claimed, 0);
-        const long long task0 = chunk * a.chunk_tasks;
-        if (task0 >= n_tasks) break;
-        const long long task1 = task0 + a.chunk_tasks < n_tasks ? task0 + a.chunk_tasks : n_tasks;
+        if (chunk >= a.n_chunks) break;
+        // the first n_big chunks hold chunk_tasks tasks each, the rest a single task: the tail of
+        // the kernel is then one task long, not one chunk
+        const long long task0 = chunk < a.n_big_chunks ? chunk * a.chunk_tasks
+                                                       : a.n_big_chunks * a.chunk_tasks + (chunk - a.n_big_chunks);
+        const long long task1 = chunk < a.n_big_chunks ? task0 + a.chunk_tasks : task0 + 1;
         for (long long task = task0; task < task1; ++task) {
             const int sub = spp >= 32 ? 0 : lane / spp;           // pixel within the task
             const int i0 = spp >= 32 ? lane : lane % spp;         // first sample of this lane
@@ -278,6 +281,37 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                 }
             };
             if (a.img) write_pixel(a.img, acc, true);
+            if (a.n_peer_img > 0) {
+                // Image all-gather fused into the render: the pixel goes straight into the full image
+                // of every GPU of the job (peer stores over NVLink, lane p -> peer p), at its image
+                // row.  ~24 B per pixel and peer against ~10^5 instructions of tracing: the exchange
+                // hides completely behind the compute and no gather step follows the kernel.
+                const size_t at = ((size_t)y * W + x) * 3;
+                if (spp >= 32) {
+                    if (!a.img) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) acc[c] = warp_sum(acc[c]);
+                    }
+                    if (lane < a.n_peer_img && lane_ok) {
+                        double* dst = a.peer_img[lane] + at;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) dst[c] = acc[c] / double(spp);
+                    }
+                } else {
+                    double tot[3] = {acc[0], acc[1], acc[2]};
+                    for (int j = 1; j < spp; ++j) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const double o = __shfl_down_sync(0xffffffffu, acc[c], j);
+                            if (i0 + j < spp) tot[c] += o;
+                        }
+                    }
+                    if (lane_ok && i0 == 0)
+                        for (int p = 0; p < a.n_peer_img; ++p)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) a.peer_img[p][at + c] = tot[c] / double(spp);
+                }
+            }
             if constexpr (GEN) { if (a.gimg) write_pixel(a.gimg, gacc, false); }
         }
         if (SMALLP && want_grad) {
@@ -552,6 +586,8 @@ struct drtb_ctx {
     void* wf_mem = nullptr;       size_t wf_cap = 0;
     bool mesh_megakernel = false; // DRTB_MESH_PIPELINE=megakernel: trace meshes inside render_kernel (A/B aid)
     unsigned long long* d_task_counter = nullptr;
+    double* img_peers[kMaxPeers] = {};   // drtb_set_image_peers: full images the render kernel fills directly
+    int n_img_peers = 0;
 };
 
 namespace {
@@ -734,7 +770,11 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
     chunk = std::max<long long>(1, std::min(chunk, n_tasks / (8 * grid * kWarpsPerBlock)));
     if (const char* e = std::getenv("DRTB_CHUNK_TASKS")) chunk = std::max(1, std::atoi(e));     // A/B aid
     a.chunk_tasks = int(chunk);
-    const long long n_chunks = (n_tasks + chunk - 1) / chunk;
+    // ... and the last round (one chunk's worth of tasks per resident warp) is handed out task by task
+    const long long small_tasks = chunk > 1 ? std::min(n_tasks, grid * kWarpsPerBlock * chunk) : 0;
+    a.n_big_chunks = (n_tasks - small_tasks) / chunk;
+    const long long n_chunks = a.n_big_chunks + (n_tasks - a.n_big_chunks * chunk);
+    a.n_chunks = n_chunks;
     if (!ctx->d_task_counter) CK(ctx, cudaMalloc(&ctx->d_task_counter, sizeof(unsigned long long)));
     CK(ctx, cudaMemsetAsync(ctx->d_task_counter, 0, sizeof(unsigned long long), stream));
     a.task_counter = ctx->d_task_counter;
@@ -841,7 +881,9 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     const bool want_grad = (o->flags & DRTB_FLAG_GRAD) != 0;
     const bool want_img = (o->flags & DRTB_FLAG_IMAGE) != 0;
     if (want_grad && !d_grad) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_GRAD set but grad is NULL");
-    if (want_img && !d_img) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_IMAGE set but img is NULL");
+    const bool peers = want_img && ctx->n_img_peers > 0;
+    if (want_img && !d_img && !peers) return fail(ctx, DRTB_ERR_INVALID, "DRTB_FLAG_IMAGE set but img is NULL");
+    if (peers && ctx->n_tris > 0) return fail(ctx, DRTB_ERR_UNSUPPORTED, "peer images are filled by the analytic-scene kernel only");
     if (ctx->n_tris > 0 && !ctx->mesh_megakernel)
         return o->precision == DRTB_F32 ? launch_wavefront<float>(ctx, ctx->sc32, o, d_seed, d_img, d_grad, d_stats, gi, stream)
                                         : launch_wavefront<double>(ctx, ctx->sc64, o, d_seed, d_img, d_grad, d_stats, gi, stream);
@@ -854,6 +896,8 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     a.shard_index = o->shard_index; a.shard_count = cnt; a.band_rows = o->band_rows > 0 ? o->band_rows : 1;
     a.shard_rows = rows; a.seed_scale = o->seed_scale;
     a.params = ctx->d_params; a.seed_img = d_seed; a.img = want_img ? d_img : nullptr;
+    a.n_peer_img = peers ? ctx->n_img_peers : 0;
+    for (int p = 0; p < a.n_peer_img; ++p) a.peer_img[p] = ctx->img_peers[p];
     a.stats = (o->flags & DRTB_FLAG_STATS) ? d_stats : nullptr;
     const bool want_gimg = want_grad && gi.d_out != nullptr;
     a.gimg = want_gimg ? gi.d_out : nullptr;
@@ -1424,6 +1468,61 @@ int drtb_render_grad_image_device(drtb_ctx* ctx, const drtb_render_opts* o, int3
     GradImage gi;
     gi.param = param; gi.d_out = d_grad_img;
     return render_device(ctx, o, gi, d_seed_img, d_img, d_grad, d_stats, stream);
+}
+
+int drtb_set_image_peers(drtb_ctx* ctx, double* const* full_images, int32_t n)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    if (n < 0 || n > kMaxPeers) return fail(ctx, DRTB_ERR_INVALID, "between 0 and 8 peer images");
+    if (n > 0 && !full_images) return fail(ctx, DRTB_ERR_INVALID, "full_images is NULL");
+    for (int p = 0; p < n; ++p)
+        if (!full_images[p]) return fail(ctx, DRTB_ERR_INVALID, "a peer image pointer is NULL");
+    for (int p = 0; p < kMaxPeers; ++p) ctx->img_peers[p] = p < n ? full_images[p] : nullptr;
+    ctx->n_img_peers = n;
+    return DRTB_OK;
+}
+
+int drtb_ipc_alloc(drtb_ctx* ctx, size_t bytes, void** d_ptr, void* handle)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    if (!d_ptr || !handle || bytes == 0) return fail(ctx, DRTB_ERR_INVALID, "drtb_ipc_alloc: NULL argument or zero size");
+    static_assert(sizeof(cudaIpcMemHandle_t) == DRTB_IPC_HANDLE_BYTES, "IPC handle size");
+    CK(ctx, cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CK(ctx, cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(ctx, DRTB_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    std::memcpy(handle, &h, sizeof(h));
+    *d_ptr = p;
+    return DRTB_OK;
+}
+
+int drtb_ipc_open(drtb_ctx* ctx, const void* handle, void** d_ptr)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    if (!d_ptr || !handle) return fail(ctx, DRTB_ERR_INVALID, "drtb_ipc_open: NULL argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    CK(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DRTB_OK;
+}
+
+int drtb_ipc_close(drtb_ctx* ctx, void* d_ptr)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return DRTB_OK;
+}
+
+int drtb_ipc_free(drtb_ctx* ctx, void* d_ptr)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaFree(d_ptr));
+    return DRTB_OK;
 }
 
 int drtb_trace_rays(drtb_ctx* ctx, const drtb_render_opts* o, int64_t n, const double* orig, const double* dir,

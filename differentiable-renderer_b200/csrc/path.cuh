@@ -20,6 +20,7 @@ constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr int kFast       = 8;     // planes / spheres scanned by straight-line code (compile-time slots)
 constexpr int kAxisFast   = 2;     // axis-aligned unit planes per axis scanned by straight-line code (a slab)
 constexpr int kSlots      = 2 * kFast + kMaxPrims;
+constexpr int kMaxPeers   = 8;     // GPUs of one NVSwitch box whose full images a render can fill
 #ifndef DRTB_PACK_HIT
 #define DRTB_PACK_HIT 1
 #endif
@@ -110,8 +111,11 @@ struct RenderArgs {
     int32_t  gimg_param;                 // -1 = none
     int32_t  sink_cols;                  // shared atomic gradient columns (9 .. 64 parameters), a power of two
     MeshView mesh;                       // n_tris == 0: analytic scene only
+    double*  peer_img[kMaxPeers];        // FULL images (H x W x 3, row = image row) on every GPU of the job,
+    int32_t  n_peer_img;                 // written pixel by pixel over NVLink (drtb_set_image_peers); 0 = off
     unsigned long long* task_counter;    // zeroed before the launch: next unclaimed chunk of warp tasks
-    int32_t  chunk_tasks;                // consecutive warp tasks per chunk
+    int32_t  chunk_tasks;                // consecutive warp tasks per big chunk
+    long long n_big_chunks, n_chunks;    // chunks [n_big_chunks, n_chunks) are single tasks
 };
 
 // Per-block shared copy of what is looked up with a PER-LANE index (the prim a

@@ -129,6 +129,34 @@ class Context:
                                                  d_img or None, d_grad or None, d_stats or None,
                                                  stream or None))
 
+    # -- multi-GPU: the image all-gather fused into the render ------------------------
+    def set_image_peers(self, full_images):
+        """drtb_set_image_peers: device addresses of the FULL image (H x W x 3 doubles) on
+        every GPU of the job; sharded renders then store their pixels into all of them.
+        An empty list switches it off."""
+        n = len(full_images)
+        arr = (C.c_void_p * max(n, 1))(*[int(p) for p in full_images])
+        self._check(self._lib.drtb_set_image_peers(self._h, arr, n))
+
+    def ipc_alloc(self, nbytes: int):
+        """(device address, 64-byte handle) of memory a peer process can map."""
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * abi.IPC_HANDLE_BYTES)()
+        self._check(self._lib.drtb_ipc_alloc(self._h, int(nbytes), C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def ipc_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * abi.IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        self._check(self._lib.drtb_ipc_open(self._h, buf, C.byref(ptr)))
+        return int(ptr.value)
+
+    def ipc_close(self, ptr: int):
+        self._check(self._lib.drtb_ipc_close(self._h, C.c_void_p(ptr)))
+
+    def ipc_free(self, ptr: int):
+        self._check(self._lib.drtb_ipc_free(self._h, C.c_void_p(ptr)))
+
     def trace_rays(self, opts: abi.RenderOpts, orig: np.ndarray, dirs: np.ndarray,
                    keys: np.ndarray, *, jac: bool = True) -> Tuple[np.ndarray, Optional[np.ndarray]]:
         """Pathtracer::trace on explicit rays (pathtracer.hpp:121-136)."""

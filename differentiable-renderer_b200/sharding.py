@@ -79,3 +79,48 @@ def deinterleave_index(height: int, count: int, band_rows: int, device=None):
     perm = np.empty(height, dtype=np.int64)
     perm[order] = np.arange(height)
     return torch.from_numpy(perm).to(device) if device is not None else torch.from_numpy(perm)
+
+
+class PeerImage:
+    """The full image (H x W x 3 doubles) replicated on every rank and filled by the
+    render kernels themselves: each rank's kernel stores its pixels into all ranks'
+    buffers over NVLink (drtb_set_image_peers), so no image gather follows the render.
+
+    Host-side plumbing only: every rank allocates its buffer with `ctx.ipc_alloc`,
+    the 64-byte CUDA IPC handles travel through `dist.all_gather_object`, peers are
+    mapped with `ctx.ipc_open`, and the rank-ordered pointer list goes to
+    `ctx.set_image_peers`.  `ctx` is a `render.Context` (or, in the CPU tests, any
+    object with the same four methods)."""
+
+    def __init__(self, ctx, height: int, width: int, dist):
+        self.ctx, self.height, self.width = ctx, height, width
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.nbytes = height * width * 3 * 8
+        self.local_ptr, handle = ctx.ipc_alloc(self.nbytes)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle)
+        self.ptrs = [self.local_ptr if r == self.rank else ctx.ipc_open(handles[r]) for r in range(self.world)]
+        ctx.set_image_peers(self.ptrs)
+        self._dist = dist
+
+    # numba-style interface so torch (or cupy) can wrap the local buffer without a copy
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.height, self.width, 3), "typestr": "<f8", "data": (self.local_ptr, False),
+                "version": 3, "strides": None}
+
+    def tensor(self, device):
+        import torch
+        return torch.as_tensor(self, device=device)
+
+    def close(self):
+        """Collective: every rank unmaps its peers before anyone frees."""
+        if self.ctx is None:
+            return
+        self.ctx.set_image_peers([])
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                self.ctx.ipc_close(p)
+        self._dist.barrier()
+        self.ctx.ipc_free(self.local_ptr)
+        self.ctx = None

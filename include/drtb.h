@@ -235,6 +235,33 @@ int drtb_render_device(drtb_ctx* ctx, const drtb_render_opts* opts,
                        const double* d_seed_img, double* d_img, double* d_grad,
                        drtb_stats* d_stats, void* stream);
 
+/* ---- multi-GPU: the image all-gather fused into the render ----------------
+ * The reference renders in one process (src/render.cpp:72-86 fills one img[]).
+ * With the image rows sharded over the GPUs of one NVSwitch box (shard_index /
+ * shard_count / band_rows), every GPU normally ends up with its own rows only
+ * and a gather has to follow.  Instead the render kernel can store each pixel,
+ * as it is finished, into the FULL image (H*W*3 doubles, row = image row, row
+ * 0 = top) of every GPU of the job: peer stores over NVLink, hidden behind the
+ * tracing.  full_images[p] are device pointers valid in this process -- this
+ * GPU's own buffer and the peers' buffers opened with drtb_ipc_open (or any
+ * peer-accessible allocation).  n = 0 switches it off.  While it is on,
+ * DRTB_FLAG_IMAGE renders (analytic scenes) fill the peers' images and d_img
+ * may be NULL.  The stores are complete when the kernel is; a rank may read
+ * its full image once every rank's render has finished (the gradient
+ * all-reduce that follows the render on each rank's stream orders that). */
+int drtb_set_image_peers(drtb_ctx* ctx, double* const* full_images, int32_t n);
+
+/* Device memory that another process on the same box can map (CUDA IPC, one
+ * process per GPU).  drtb_ipc_alloc: cudaMalloc on ctx's device + its
+ * DRTB_IPC_HANDLE_BYTES-byte handle, to be sent to the peers by the host's own
+ * means; drtb_ipc_open: map a peer's handle into this process (peer access is
+ * enabled on demand); drtb_ipc_close / drtb_ipc_free undo them. */
+#define DRTB_IPC_HANDLE_BYTES 64
+int drtb_ipc_alloc(drtb_ctx* ctx, size_t bytes, void** d_ptr, void* handle);
+int drtb_ipc_open(drtb_ctx* ctx, const void* handle, void** d_ptr);
+int drtb_ipc_close(drtb_ctx* ctx, void* d_ptr);
+int drtb_ipc_free(drtb_ctx* ctx, void* d_ptr);
+
 /* drtb_render plus the PER-PIXEL gradient image of ONE parameter (the figure of
  * README.md:138-145, "gradients of the pixel colors with respect to the
  * parameter controlling the color of the left wall"): the same adjoint sweep,

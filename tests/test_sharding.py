@@ -53,3 +53,63 @@ def test_deinterleave_index_inverts_the_band_layout():
     cat = np.concatenate([full[sharding.shard_row_indices(H, r, count, band)] for r in range(count)])
     perm = sharding.deinterleave_index(H, count, band).numpy()
     assert np.array_equal(cat[perm], full)
+
+
+class _FakeCtx:
+    """Stands in for render.Context in the handle exchange: `ipc_alloc` hands out a made-up
+    address and a handle that encodes it, `ipc_open` decodes a peer's handle."""
+    def __init__(self, rank):
+        self.rank, self.peers, self.opened, self.closed, self.freed = rank, None, [], [], []
+
+    def ipc_alloc(self, nbytes):
+        ptr = 0x7000_0000_0000 + self.rank * 0x1000_0000
+        return ptr, ptr.to_bytes(8, "little") + bytes([self.rank]) * 56
+
+    def ipc_open(self, handle):
+        assert len(handle) == 64
+        p = int.from_bytes(handle[:8], "little") + 1       # a peer mapping lives at another address
+        self.opened.append(p)
+        return p
+
+    def set_image_peers(self, ptrs):
+        self.peers = list(ptrs)
+
+    def ipc_close(self, ptr):
+        self.closed.append(ptr)
+
+    def ipc_free(self, ptr):
+        self.freed.append(ptr)
+
+
+def _peer_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from differentiable_renderer_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = _FakeCtx(rank)
+    pi = sharding.PeerImage(ctx, 16, 8, dist)
+    peers = list(ctx.peers)
+    iface = pi.__cuda_array_interface__
+    pi.close()
+    np.savez(out + f".{rank}.npz", peers=np.array(peers, dtype=np.uint64), local=pi.local_ptr, nbytes=pi.nbytes,
+             closed=np.array(ctx.closed, dtype=np.uint64), freed=np.array(ctx.freed, dtype=np.uint64),
+             after=len(ctx.peers), shape=np.array(iface["shape"]))
+    dist.destroy_process_group()
+
+
+def test_peer_image_handle_exchange_on_two_gloo_ranks(tmp_path):
+    """Host logic of the fused image gather: rank-ordered pointer list, own buffer by its
+    local address, peers by their mapped address, everything unmapped on close."""
+    import torch.multiprocessing as mp
+    world = 2
+    out = str(tmp_path / "p")
+    mp.spawn(_peer_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        z = np.load(out + f".{r}.npz")
+        base = [0x7000_0000_0000 + q * 0x1000_0000 for q in range(world)]
+        want = [base[q] if q == r else base[q] + 1 for q in range(world)]
+        assert z["peers"].tolist() == want and int(z["local"]) == base[r]
+        assert int(z["nbytes"]) == 16 * 8 * 3 * 8 and z["shape"].tolist() == [16, 8, 3]
+        assert z["closed"].tolist() == [w for q, w in enumerate(want) if q != r]
+        assert z["freed"].tolist() == [base[r]] and int(z["after"]) == 0
