@@ -97,8 +97,11 @@ struct JacSink {
 
 // The pixel loop of src/render.cpp:72-86.
 //   SMALLP: <= kSmallP parameters, gradients in per-thread shared columns
-//   QUEUE : spp >= 32 and max_depth <= kQueueDepth: lit paths are compacted
-//           through a per-warp shared-memory ring before the sweeps
+//   QUEUE : spp >= 32 and max_depth <= kQueueDepth: lit paths are compacted through a per-warp
+//           ring before the sweeps.  1: the ring lives in shared memory; 2: in a global scratch
+//           buffer (L1/L2 resident), chosen when the shared ring of a deep record (max_depth > 8
+//           in double) would cost resident blocks -- the ring carries only the ~16-21 % of the
+//           paths that are lit, so its latency does not matter, the occupancy does
 #ifndef DRTB_MIN_BLOCKS
 #define DRTB_MIN_BLOCKS 1
 #endif
@@ -111,7 +114,7 @@ struct JacSink {
 //   MESH  : a triangle mesh + BVH is attached (ids are 32-bit, parameters in global memory)
 //   GEN   : the general variant -- SpecularBxDF materials (bxdf.hpp:85-124) and the
 //           per-pixel gradient image; the all-diffuse kernels do not carry that code
-template <typename R, bool SMALLP, bool QUEUE, bool MESH, bool GEN>
+template <typename R, bool SMALLP, int QUEUE, bool MESH, bool GEN>
 __global__ void __launch_bounds__(kBlock, MESH ? DRTB_MESH_MIN_BLOCKS : sizeof(R) == 4 ? DRTB_MIN_BLOCKS_F32 : DRTB_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ RenderArgs a)
 {
@@ -144,6 +147,8 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     const int qdepth = a.max_depth;
     unsigned char* ring = reinterpret_cast<unsigned char*>(s_dyn + acc_doubles) +
                           (QUEUE ? size_t(warp) * queue_bytes_per_warp(qdepth, sizeof(R), sizeof(Id)) : 0);
+    if constexpr (QUEUE == 2)
+        ring = a.ring_scratch + (size_t(blockIdx.x) * kWarpsPerBlock + warp) * queue_bytes_per_warp(qdepth, sizeof(R), sizeof(Id));
     R* ring_w = reinterpret_cast<R*>(ring);
     Id* ring_prim = reinterpret_cast<Id*>(ring + size_t(qdepth) * kQueueSlots * sizeof(R));
     uint8_t* ring_n = reinterpret_cast<uint8_t*>(ring_prim + size_t(qdepth) * kQueueSlots);
@@ -567,6 +572,7 @@ struct drtb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double* d_params = nullptr;   size_t params_cap = 0;
     double* d_partial = nullptr;  size_t partial_cap = 0;
+    double* d_ring = nullptr;     size_t ring_cap = 0;      // lit-path rings of the QUEUE == 2 kernels
     double* d_img = nullptr;      size_t img_cap = 0;
     double* d_seed = nullptr;     size_t seed_cap = 0;
     double* d_grad = nullptr;     size_t grad_cap = 0;
@@ -752,7 +758,7 @@ int reduce_partials(drtb_ctx* ctx, double* partial, size_t rows, int P3, double*
     return DRTB_OK;
 }
 
-template <typename R, bool SMALLP, bool QUEUE, bool MESH, bool GEN>
+template <typename R, bool SMALLP, int QUEUE, bool MESH, bool GEN>
 int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t smem, long long n_tasks,
                    int P3, bool want_grad, cudaStream_t stream, size_t& rows_out)
 {
@@ -788,6 +794,12 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
         if (rc != DRTB_OK) return rc;
         a.grad_partial = ctx->d_partial;
     }
+    if (QUEUE == 2) {
+        const size_t per_warp = queue_bytes_per_warp(a.max_depth, sizeof(R), MESH ? sizeof(int32_t) : sizeof(uint8_t));
+        rc = ensure(ctx, ctx->d_ring, ctx->ring_cap, size_t(grid) * kWarpsPerBlock * per_warp / sizeof(double));
+        if (rc != DRTB_OK) return rc;
+        a.ring_scratch = reinterpret_cast<unsigned char*>(ctx->d_ring);
+    }
     render_kernel<R, SMALLP, QUEUE, MESH, GEN><<<int(grid), kBlock, smem, stream>>>(sc, a);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
@@ -796,24 +808,25 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
 }
 
 template <typename R>
-int launch_precision(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, bool smallp, bool queue, bool mesh, bool gen,
+int launch_precision(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, bool smallp, int queue, bool mesh, bool gen,
                      size_t smem, long long n_tasks, int P3, bool want_grad, cudaStream_t stream, size_t& rows)
 {
 #define DRTB_LAUNCH(SP, Q, M) launch_variant<R, SP, Q, M, false>(ctx, sc, a, smem, n_tasks, P3, want_grad, stream, rows)
 #define DRTB_LAUNCH_GEN(SP, Q) launch_variant<R, SP, Q, false, true>(ctx, sc, a, smem, n_tasks, P3, want_grad, stream, rows)
+#define DRTB_BY_QUEUE(L, SP, ...) (queue == 2 ? L(SP, 2, ##__VA_ARGS__) : queue == 1 ? L(SP, 1, ##__VA_ARGS__) : L(SP, 0, ##__VA_ARGS__))
     if (gen) {
         // SpecularBxDF materials and/or a gradient image (analytic scenes; mesh scenes take the wavefront)
         if (mesh) return fail(ctx, DRTB_ERR_UNSUPPORTED, "specular materials / gradient images on a mesh scene need the wavefront pipeline");
-        if (smallp) return queue ? DRTB_LAUNCH_GEN(true, true) : DRTB_LAUNCH_GEN(true, false);
-        return queue ? DRTB_LAUNCH_GEN(false, true) : DRTB_LAUNCH_GEN(false, false);
+        return smallp ? DRTB_BY_QUEUE(DRTB_LAUNCH_GEN, true) : DRTB_BY_QUEUE(DRTB_LAUNCH_GEN, false);
     }
     if (mesh) {
         // mesh scenes: parameters live in global memory; small sets still use the smem gradient columns
-        if (smallp) return queue ? DRTB_LAUNCH(true, true, true) : DRTB_LAUNCH(true, false, true);
-        return queue ? DRTB_LAUNCH(false, true, true) : DRTB_LAUNCH(false, false, true);
+        // (the megakernel on a mesh is an A/B aid: shared ring only)
+        if (smallp) return queue ? DRTB_LAUNCH(true, 1, true) : DRTB_LAUNCH(true, 0, true);
+        return queue ? DRTB_LAUNCH(false, 1, true) : DRTB_LAUNCH(false, 0, true);
     }
-    if (smallp) return queue ? DRTB_LAUNCH(true, true, false) : DRTB_LAUNCH(true, false, false);
-    return queue ? DRTB_LAUNCH(false, true, false) : DRTB_LAUNCH(false, false, false);
+    return smallp ? DRTB_BY_QUEUE(DRTB_LAUNCH, true, false) : DRTB_BY_QUEUE(DRTB_LAUNCH, false, false);
+#undef DRTB_BY_QUEUE
 #undef DRTB_LAUNCH
 #undef DRTB_LAUNCH_GEN
 }
@@ -917,13 +930,22 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     const bool shared_atomic = !smallp && !mesh;
     a.sink_cols = 1;
     if (shared_atomic && want_grad) {
-        const size_t budget = 44 * 1024 - 6 * 1024 - ring_bytes;          // 227 KB / 5 blocks, minus static smem
+        const size_t room = 44 * 1024 - 6 * 1024;                         // 227 KB / 5 blocks, minus static smem
+        const size_t budget = ring_bytes + 8 * 1024 < room ? room - ring_bytes : room;   // a large ring goes to global memory below
         int cols = kBlock;
         while (cols > 1 && size_t(P3) * cols * sizeof(double) > budget) cols >>= 1;
         a.sink_cols = cols;
         smem = size_t(P3) * cols * sizeof(double);
     }
-    smem += ring_bytes;
+    // The shared ring of a deep record costs resident blocks (double, max_depth 16: 37 KB of ring, 3 blocks instead
+    // of 5, -36 % throughput): past the budget the ring moves to a global scratch buffer (QUEUE == 2).
+    int queue_kind = queue ? 1 : 0;
+    if (queue && !mesh) {
+        const int want_blocks = f32 ? DRTB_MIN_BLOCKS_F32 : DRTB_MIN_BLOCKS;
+        const size_t static_smem = (f32 ? sizeof(BlockScene<float>) : sizeof(BlockScene<double>)) + 1024;   // + 1 KB the system reserves per block
+        if ((static_smem + smem + ring_bytes) * want_blocks > size_t(228) * 1024) queue_kind = 2;
+    }
+    if (queue_kind != 2) smem += ring_bytes;
     smem = (smem + 15) & ~size_t(15);
     const long long npix = (long long)rows * W;
     const int ppw = o->spp >= 32 ? 1 : 32 / o->spp;
@@ -937,8 +959,8 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
         a.grad_atomic = d_grad;
     }
     size_t partial_rows = 0;
-    int rc = f32 ? launch_precision<float>(ctx, ctx->sc32, a, smallp, queue, mesh, gen, smem, n_tasks, P3, want_grad, stream, partial_rows)
-                 : launch_precision<double>(ctx, ctx->sc64, a, smallp, queue, mesh, gen, smem, n_tasks, P3, want_grad, stream, partial_rows);
+    int rc = f32 ? launch_precision<float>(ctx, ctx->sc32, a, smallp, queue_kind, mesh, gen, smem, n_tasks, P3, want_grad, stream, partial_rows)
+                 : launch_precision<double>(ctx, ctx->sc64, a, smallp, queue_kind, mesh, gen, smem, n_tasks, P3, want_grad, stream, partial_rows);
     if (rc != DRTB_OK) return rc;
     if (want_grad && (smallp || shared_atomic)) return reduce_partials(ctx, ctx->d_partial, partial_rows, P3, d_grad, stream);
     return DRTB_OK;
@@ -1158,7 +1180,7 @@ void drtb_destroy(drtb_ctx* ctx)
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    cudaFree(ctx->d_params); cudaFree(ctx->d_partial); cudaFree(ctx->d_img); cudaFree(ctx->d_task_counter);
+    cudaFree(ctx->d_params); cudaFree(ctx->d_partial); cudaFree(ctx->d_img); cudaFree(ctx->d_task_counter); cudaFree(ctx->d_ring);
     cudaFree(ctx->d_seed); cudaFree(ctx->d_grad); cudaFree(ctx->d_gimg); cudaFree(ctx->d_stats); cudaFree(ctx->wf_mem);
     free_mesh(ctx);
     delete ctx;

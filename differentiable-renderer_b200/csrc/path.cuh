@@ -113,6 +113,7 @@ struct RenderArgs {
     MeshView mesh;                       // n_tris == 0: analytic scene only
     double*  peer_img[kMaxPeers];        // FULL images (H x W x 3, row = image row) on every GPU of the job,
     int32_t  n_peer_img;                 // written pixel by pixel over NVLink (drtb_set_image_peers); 0 = off
+    unsigned char* ring_scratch;         // QUEUE == 2: per-warp lit-path rings in global memory
     unsigned long long* task_counter;    // zeroed before the launch: next unclaimed chunk of warp tasks
     int32_t  chunk_tasks;                // consecutive warp tasks per big chunk
     long long n_big_chunks, n_chunks;    // chunks [n_big_chunks, n_chunks) are single tasks
