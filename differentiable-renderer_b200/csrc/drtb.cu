@@ -140,14 +140,13 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     // spp <  32: floor(32/spp) pixels per warp task, one pass.
     const int ppw = spp >= 32 ? 1 : 32 / spp;
     const int passes = spp >= 32 ? (spp + 31) / 32 : 1;
-    const long long n_tasks = (npix + ppw - 1) / ppw;
     const R inv_p = a.absorb < 1.0 ? R(1.0 / (1.0 - a.absorb)) : R(0);
 
     // this warp's ring (QUEUE only)
-    const int qdepth = a.max_depth;
+    const int qdepth = QUEUE == 3 ? kQueueDepth : a.max_depth;
     unsigned char* ring = reinterpret_cast<unsigned char*>(s_dyn + acc_doubles) +
                           (QUEUE ? size_t(warp) * queue_bytes_per_warp(qdepth, sizeof(R), sizeof(Id)) : 0);
-    if constexpr (QUEUE == 2)
+    if constexpr (QUEUE >= 2)
         ring = a.ring_scratch + (size_t(blockIdx.x) * kWarpsPerBlock + warp) * queue_bytes_per_warp(qdepth, sizeof(R), sizeof(Id));
     R* ring_w = reinterpret_cast<R*>(ring);
     Id* ring_prim = reinterpret_cast<Id*>(ring + size_t(qdepth) * kQueueSlots * sizeof(R));
@@ -230,6 +229,62 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                 q_count -= m;
             };
 
+            if constexpr (QUEUE == 3) {
+                // Path regeneration (Russian roulette, absorb < 1): path lengths are geometric, so a
+                // warp that traces 32 samples to the end idles most lanes (mean 1.9 segments, longest
+                // of 32 about 6.5 at the reference's defaults).  Here every lane steps ONE segment per
+                // iteration, and lanes whose path has ended take the pixel's next samples as soon as
+                // kRefillLanes of them are free (ballot order, hence deterministic).
+#ifndef DRTB_REFILL_LANES
+#define DRTB_REFILL_LANES 8
+#endif
+                constexpr int kRefillLanes = DRTB_REFILL_LANES;
+                int next_i = 0;                                   // warp-uniform: next unassigned sample
+                bool alive = false, lit = false;
+                int depth = 0, n = 0;
+                uint64_t ctr = 0;
+                V3<R> o = {R(0), R(0), R(0)}, d = o;
+                PathRecord<R, MESH, kMaxDepth> rec;
+                for (;;) {
+                    const unsigned dead = __ballot_sync(0xffffffffu, !alive);
+                    if (next_i < spp && (__popc(dead) >= kRefillLanes || dead == 0xffffffffu)) {
+                        const int mine = next_i + __popc(dead & ((1u << lane) - 1u));
+                        if (!alive && mine < spp) {
+                            const uint64_t key = a.key0 + ((uint64_t)y * W + x) * (uint64_t)spp + (uint64_t)mine;
+                            const uint64_t base = key * kKeyMul;
+                            o = {sc.eye[0], sc.eye[1], sc.eye[2]};
+                            d = camera_ray(sc, x, y, base);
+                            ctr = base + kGolden + 2u;
+                            depth = 0; n = 0; lit = false;
+                            alive = !roulette_absorbs(ctr, 0, a.min_bounces, a.absorb);     // min_bounces == 0: trace() may return 0 at once
+                        }
+                        next_i = min(spp, next_i + __popc(dead));
+                    }
+                    if (__ballot_sync(0xffffffffu, alive) == 0u) {
+                        if (next_i >= spp) break;
+                        continue;                                  // every fresh sample was absorbed at once (min_bounces == 0)
+                    }
+                    bool done = false;
+                    if constexpr (!MESH) {
+                        if (alive) done = trace_segment(sc, bs, mat, ctr, o, d, depth, n, lit, a.min_bounces, a.absorb,
+                                                        a.max_depth, rec, cnt);
+                    }
+                    if (done) alive = false;
+                    if (done && lit && n > kQueueDepth) sweep(rec, n);        // a record too deep for the ring (p ~ 1e-5)
+                    const bool queued = done && lit && n <= kQueueDepth;
+                    const unsigned m = __ballot_sync(0xffffffffu, queued);
+                    if (queued) {
+                        const int slot = (q_head + q_count + __popc(m & ((1u << lane) - 1u))) & (kQueueSlots - 1);
+                        for (int v = 0; v < n; ++v) {
+                            ring_w[v * kQueueSlots + slot] = rec.w_[v];
+                            ring_prim[v * kQueueSlots + slot] = rec.prim_[v];
+                        }
+                        ring_n[slot] = uint8_t(n);
+                    }
+                    q_count += __popc(m);
+                    if (q_count >= 32) drain(32);
+                }
+            } else
             for (int pass = 0; pass < passes; ++pass) {
                 const int i = i0 + pass * 32;
                 bool lit = false;
@@ -572,7 +627,8 @@ struct drtb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double* d_params = nullptr;   size_t params_cap = 0;
     double* d_partial = nullptr;  size_t partial_cap = 0;
-    double* d_ring = nullptr;     size_t ring_cap = 0;      // lit-path rings of the QUEUE == 2 kernels
+    double* d_ring = nullptr;     size_t ring_cap = 0;      // lit-path rings of the QUEUE >= 2 kernels
+    bool no_regen = false;        // DRTB_NO_REGEN=1: Russian-roulette renders without path regeneration (A/B aid)
     double* d_img = nullptr;      size_t img_cap = 0;
     double* d_seed = nullptr;     size_t seed_cap = 0;
     double* d_grad = nullptr;     size_t grad_cap = 0;
@@ -794,8 +850,8 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
         if (rc != DRTB_OK) return rc;
         a.grad_partial = ctx->d_partial;
     }
-    if (QUEUE == 2) {
-        const size_t per_warp = queue_bytes_per_warp(a.max_depth, sizeof(R), MESH ? sizeof(int32_t) : sizeof(uint8_t));
+    if (QUEUE >= 2) {
+        const size_t per_warp = queue_bytes_per_warp(QUEUE == 3 ? kQueueDepth : a.max_depth, sizeof(R), MESH ? sizeof(int32_t) : sizeof(uint8_t));
         rc = ensure(ctx, ctx->d_ring, ctx->ring_cap, size_t(grid) * kWarpsPerBlock * per_warp / sizeof(double));
         if (rc != DRTB_OK) return rc;
         a.ring_scratch = reinterpret_cast<unsigned char*>(ctx->d_ring);
@@ -814,6 +870,7 @@ int launch_precision(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, bool s
 #define DRTB_LAUNCH(SP, Q, M) launch_variant<R, SP, Q, M, false>(ctx, sc, a, smem, n_tasks, P3, want_grad, stream, rows)
 #define DRTB_LAUNCH_GEN(SP, Q) launch_variant<R, SP, Q, false, true>(ctx, sc, a, smem, n_tasks, P3, want_grad, stream, rows)
 #define DRTB_BY_QUEUE(L, SP, ...) (queue == 2 ? L(SP, 2, ##__VA_ARGS__) : queue == 1 ? L(SP, 1, ##__VA_ARGS__) : L(SP, 0, ##__VA_ARGS__))
+    if (queue == 3) return smallp ? DRTB_LAUNCH(true, 3, false) : DRTB_LAUNCH(false, 3, false);    // path regeneration
     if (gen) {
         // SpecularBxDF materials and/or a gradient image (analytic scenes; mesh scenes take the wavefront)
         if (mesh) return fail(ctx, DRTB_ERR_UNSUPPORTED, "specular materials / gradient images on a mesh scene need the wavefront pipeline");
@@ -945,7 +1002,9 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
         const size_t static_smem = (f32 ? sizeof(BlockScene<float>) : sizeof(BlockScene<double>)) + 1024;   // + 1 KB the system reserves per block
         if ((static_smem + smem + ring_bytes) * want_blocks > size_t(228) * 1024) queue_kind = 2;
     }
-    if (queue_kind != 2) smem += ring_bytes;
+    // Russian roulette on an all-diffuse analytic scene: the regenerating kernel (ring in global memory)
+    if (o->spp >= 32 && o->absorb < 1.0 && !mesh && !gen && !ctx->no_regen) queue_kind = 3;
+    if (queue_kind < 2) smem += ring_bytes;
     smem = (smem + 15) & ~size_t(15);
     const long long npix = (long long)rows * W;
     const int ppw = o->spp >= 32 ? 1 : 32 / o->spp;
@@ -1148,6 +1207,7 @@ int drtb_create(int device, drtb_ctx** out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = std::getenv("DRTB_MESH_PIPELINE")) ctx->mesh_megakernel = std::string(e) == "megakernel";
+    if (const char* e = std::getenv("DRTB_NO_REGEN")) ctx->no_regen = std::atoi(e) != 0;
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||

@@ -561,6 +561,66 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
 }
 
 // ---------------------------------------------------------------------------
+// ONE segment of trace_path for one lane whose path state lives in the caller
+// (analytic scenes, diffuse BxDFs): the regenerating kernel (render_kernel,
+// QUEUE == 3) steps every lane once per iteration and hands a fresh camera
+// sample to lanes whose path has ended.  Same arithmetic, same draws, same
+// record as trace_path; the roulette of the NEXT trace() call is decided here
+// as well.  Returns true when the path ends with this call.
+// ---------------------------------------------------------------------------
+// Russian roulette of the trace() call at `depth` (pathtracer.hpp:128-130).  The regenerating
+// kernel asks right after the segment that leads there (and once for the camera ray), so that a
+// lane never spends an iteration only to learn that its path was absorbed; the draw keeps its
+// place in the path's stream (after the two sampling draws of the previous vertex).
+__device__ __forceinline__ bool roulette_absorbs(uint64_t& ctr, int depth, int min_bounces, double absorb)
+{
+    if (depth < min_bounces) return false;
+    if (absorb >= 1.0) return true;
+    return Real<double>::uniform(stream_draw_ctr(ctr++)) < absorb;
+}
+
+template <typename R, int CAP>
+__device__ __forceinline__ bool trace_segment(const DevScene<R>& sc, const BlockScene<R>& bs,
+                                              const Materials<R, false>& mat, uint64_t& ctr, V3<R>& o, V3<R>& d,
+                                              int& depth, int& n, bool& lit, int min_bounces, double absorb,
+                                              int max_depth, PathRecord<R, false, CAP>& rec, TraceCounters& cnt)
+{
+    if (n >= max_depth) { ++cnt.truncated; return true; }
+    R t;
+    const int k = closest_hit<R, kPackHit>(sc, o, d, t);
+    ++cnt.segments;
+    if (k < 0) return true;                                 // miss, :134-135
+    const V3<R> pt = {o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
+    const int em = mat.em(k), col = mat.col(k);
+    lit |= em >= 0;
+    rec.prim_[n] = uint8_t(k);
+    if (col < 0) {                                          // null BxDF, :25-26, 38-39
+        rec.w_[n++] = R(0);
+        return true;
+    }
+    V3<R> nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]}, tg, bt;
+    if (bs.type[k] == DRTB_SPHERE) {                        // shape.hpp:105-106
+        nrm = normalize(V3<R>{pt.x - nrm.x, pt.y - nrm.y, pt.z - nrm.z});
+        unit_frame(nrm, tg, bt);
+    } else {                                                // plane: constant frame, bxdf.hpp:29-41 on the host
+        tg = {bs.frame[k][0], bs.frame[k][1], bs.frame[k][2]};
+        bt = {bs.frame[k][3], bs.frame[k][4], bs.frame[k][5]};
+    }
+    const R u_theta = Real<R>::uniform_fast(stream_draw_ctr(ctr));
+    R sp, cp;                                               // phi = 2 * pi * uniform(), bxdf.hpp:74
+    Real<R>::sincos_tab(bs.tab, stream_draw_ctr(ctr + 1), &sp, &cp);
+    ctr += 2;
+    R w;
+    const V3<R> dout = diffuse_sample(nrm, tg, bt, u_theta, sp, cp, w);
+    rec.w_[n++] = w;
+    const R eps = Real<R>::origin_eps();                    // 1e-3, pathtracer.hpp:99
+    o = {Real<R>::fma(eps, dout.x, pt.x), Real<R>::fma(eps, dout.y, pt.y), Real<R>::fma(eps, dout.z, pt.z)};
+    d = dout;
+    ++depth;
+    return roulette_absorbs(ctr, depth, min_bounces, absorb);
+}
+
+// ---------------------------------------------------------------------------
 // Radiance recurrence + adjoint: replaces the reverse tape (vector.hpp:120-318,
 // 418-557).  Backward sweep  L_v = (E_v + (rho_v/pi) L_{v+1} w_v) / p_v  gives
 // the path radiance L_0; forward sweep with g_0 = seed:
