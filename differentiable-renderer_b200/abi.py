@@ -81,6 +81,7 @@ SYMBOLS = [
     ("drtb_mesh_upload", C.c_int, [C.c_void_p, C.POINTER(Mesh)]),
     ("drtb_mesh_build_ms", C.c_double, [C.c_void_p]),
     ("drtb_set_params", C.c_int, [C.c_void_p, _dp, C.c_int32]),
+    ("drtb_set_params_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     ("drtb_shard_rows", C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("drtb_render", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), _dp, _dp, _dp, C.POINTER(Stats)]),
     ("drtb_render_device", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), C.c_void_p, C.c_void_p,

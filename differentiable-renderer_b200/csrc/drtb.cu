@@ -1455,6 +1455,17 @@ int drtb_set_params(drtb_ctx* ctx, const double* params, int32_t n_params)
     return DRTB_OK;
 }
 
+int drtb_set_params_device(drtb_ctx* ctx, const double* d_params, int32_t n_params, void* stream)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, DRTB_ERR_INVALID, "no scene uploaded");
+    if (!d_params || size_t(n_params) * 3 != ctx->params.size()) return fail(ctx, DRTB_ERR_INVALID, "n_params does not match the uploaded scene");
+    CK(ctx, cudaSetDevice(ctx->device));
+    // ordered on the caller's stream with the renders enqueued there; no host round trip
+    CK(ctx, cudaMemcpyAsync(ctx->d_params, d_params, sizeof(double) * ctx->params.size(), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return DRTB_OK;
+}
+
 int32_t drtb_shard_rows(int32_t height, int32_t shard_index, int32_t shard_count, int32_t band_rows)
 {
     if (shard_count > 1 && (shard_index < 0 || shard_index >= shard_count)) return 0;

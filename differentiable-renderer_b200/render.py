@@ -74,6 +74,10 @@ class Context:
         v = np.ascontiguousarray(values, dtype=np.float64).reshape(-1, 3)
         self._check(self._lib.drtb_set_params(self._h, _ptr(v), v.shape[0]))
 
+    def set_params_device(self, d_params: int, n_params: int, stream: int = 0):
+        """drtb_set_params_device: n_params x 3 doubles already on the device, copied on `stream`."""
+        self._check(self._lib.drtb_set_params_device(self._h, d_params, int(n_params), stream or None))
+
     # -- hot path, host buffers --------------------------------------------------
     def render(self, opts: abi.RenderOpts, seed_img: Optional[np.ndarray] = None,
                *, stats: bool = False):

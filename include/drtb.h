@@ -203,6 +203,10 @@ double drtb_mesh_build_ms(const drtb_ctx* ctx);
  * optimisation loop makes between renders. */
 int drtb_set_params(drtb_ctx* ctx, const double* params, int32_t n_params);
 
+/* Same from DEVICE memory, enqueued on `stream` (ordered with the renders the caller enqueues there;
+ * asynchronous): an optimisation loop whose update step runs on the GPU never returns to the host. */
+int drtb_set_params_device(drtb_ctx* ctx, const double* d_params, int32_t n_params, void* stream);
+
 /* Rows of the image that shard (index, count, band_rows) owns, for sizing the
  * compact shard buffers; callable without a GPU. */
 int32_t drtb_shard_rows(int32_t height, int32_t shard_index, int32_t shard_count,

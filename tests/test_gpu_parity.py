@@ -150,6 +150,25 @@ def test_set_params_is_what_an_optimisation_loop_needs(drt, ctx):
     assert rel_err(img, ref_img).max() <= 1e-9 and rel_err(grad, ref_grad).max() <= 1e-9
 
 
+def test_set_params_device_equals_the_host_call(drt, ctx):
+    """drtb_set_params_device: the update step of an optimisation loop that never leaves the GPU."""
+    import torch
+    scene = drt.cornell_box(32, 24)
+    ctx.upload(scene)
+    new = np.array([[0.3, 0.2, 0.1], [0.2, 0.7, 0.2], [0.6, 0.6, 0.5], [1.5, 1.0, 0.5]])
+    ctx.set_params(new)
+    a = ctx.render(drt.make_opts(8, 3, 0.3))
+    ctx.set_params(scene.param_values())
+    t = torch.tensor(new, dtype=torch.float64, device="cuda:0")
+    ctx.set_params_device(t.data_ptr(), 4, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    b = ctx.render(drt.make_opts(8, 3, 0.3))
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    with pytest.raises(drt.DrtbError):
+        ctx.set_params_device(t.data_ptr(), 3, 0)
+    ctx.set_params(scene.param_values())
+
+
 def test_flags_select_outputs(drt, ctx):
     ctx.upload(drt.cornell_box(32, 24))
     img, grad = ctx.render(drt.make_opts(8, 2, 0.5, flags=drt.FLAG_IMAGE))
