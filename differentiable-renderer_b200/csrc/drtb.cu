@@ -143,10 +143,10 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     const R inv_p = a.absorb < 1.0 ? R(1.0 / (1.0 - a.absorb)) : R(0);
 
     // this warp's ring (QUEUE only)
-    const int qdepth = QUEUE == 3 ? kQueueDepth : a.max_depth;
+    const int qdepth = a.max_depth;
     unsigned char* ring = reinterpret_cast<unsigned char*>(s_dyn + acc_doubles) +
                           (QUEUE ? size_t(warp) * queue_bytes_per_warp(qdepth, sizeof(R), sizeof(Id)) : 0);
-    if constexpr (QUEUE >= 2)
+    if constexpr (QUEUE == 2)
         ring = a.ring_scratch + (size_t(blockIdx.x) * kWarpsPerBlock + warp) * queue_bytes_per_warp(qdepth, sizeof(R), sizeof(Id));
     R* ring_w = reinterpret_cast<R*>(ring);
     Id* ring_prim = reinterpret_cast<Id*>(ring + size_t(qdepth) * kQueueSlots * sizeof(R));
@@ -229,62 +229,6 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                 q_count -= m;
             };
 
-            if constexpr (QUEUE == 3) {
-                // Path regeneration (Russian roulette, absorb < 1): path lengths are geometric, so a
-                // warp that traces 32 samples to the end idles most lanes (mean 1.9 segments, longest
-                // of 32 about 6.5 at the reference's defaults).  Here every lane steps ONE segment per
-                // iteration, and lanes whose path has ended take the pixel's next samples as soon as
-                // kRefillLanes of them are free (ballot order, hence deterministic).
-#ifndef DRTB_REFILL_LANES
-#define DRTB_REFILL_LANES 8
-#endif
-                constexpr int kRefillLanes = DRTB_REFILL_LANES;
-                int next_i = 0;                                   // warp-uniform: next unassigned sample
-                bool alive = false, lit = false;
-                int depth = 0, n = 0;
-                uint64_t ctr = 0;
-                V3<R> o = {R(0), R(0), R(0)}, d = o;
-                PathRecord<R, MESH, kMaxDepth> rec;
-                for (;;) {
-                    const unsigned dead = __ballot_sync(0xffffffffu, !alive);
-                    if (next_i < spp && (__popc(dead) >= kRefillLanes || dead == 0xffffffffu)) {
-                        const int mine = next_i + __popc(dead & ((1u << lane) - 1u));
-                        if (!alive && mine < spp) {
-                            const uint64_t key = a.key0 + ((uint64_t)y * W + x) * (uint64_t)spp + (uint64_t)mine;
-                            const uint64_t base = key * kKeyMul;
-                            o = {sc.eye[0], sc.eye[1], sc.eye[2]};
-                            d = camera_ray(sc, x, y, base);
-                            ctr = base + kGolden + 2u;
-                            depth = 0; n = 0; lit = false;
-                            alive = !roulette_absorbs(ctr, 0, a.min_bounces, a.absorb);     // min_bounces == 0: trace() may return 0 at once
-                        }
-                        next_i = min(spp, next_i + __popc(dead));
-                    }
-                    if (__ballot_sync(0xffffffffu, alive) == 0u) {
-                        if (next_i >= spp) break;
-                        continue;                                  // every fresh sample was absorbed at once (min_bounces == 0)
-                    }
-                    bool done = false;
-                    if constexpr (!MESH) {
-                        if (alive) done = trace_segment(sc, bs, mat, ctr, o, d, depth, n, lit, a.min_bounces, a.absorb,
-                                                        a.max_depth, rec, cnt);
-                    }
-                    if (done) alive = false;
-                    if (done && lit && n > kQueueDepth) sweep(rec, n);        // a record too deep for the ring (p ~ 1e-5)
-                    const bool queued = done && lit && n <= kQueueDepth;
-                    const unsigned m = __ballot_sync(0xffffffffu, queued);
-                    if (queued) {
-                        const int slot = (q_head + q_count + __popc(m & ((1u << lane) - 1u))) & (kQueueSlots - 1);
-                        for (int v = 0; v < n; ++v) {
-                            ring_w[v * kQueueSlots + slot] = rec.w_[v];
-                            ring_prim[v * kQueueSlots + slot] = rec.prim_[v];
-                        }
-                        ring_n[slot] = uint8_t(n);
-                    }
-                    q_count += __popc(m);
-                    if (q_count >= 32) drain(32);
-                }
-            } else
             for (int pass = 0; pass < passes; ++pass) {
                 const int i = i0 + pass * 32;
                 bool lit = false;
@@ -411,6 +355,221 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                 atomicAdd((unsigned long long*)&a.stats->bvh_nodes, nodes);
                 atomicAdd((unsigned long long*)&a.stats->tri_tests, tests);
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The pixel loop for Russian-roulette renders (absorb < 1) of all-diffuse analytic scenes, with
+// PATH REGENERATION.  Path lengths are geometric there (mean 1.9 segments at the reference's
+// defaults -b 1 -p 0.5, the longest of 32 about 6.5), so a warp that traces 32 samples to the
+// end keeps a third of its lanes busy.  Here a warp owns a CHUNK of pixels (<= kRegenPixels,
+// about 1024 samples) as one flat list of samples; every lane steps ONE segment per iteration
+// (trace_segment), and as soon as kRefillLanes lanes are free they take the next samples of the
+// list (ballot order, hence deterministic), whichever pixel those belong to -- only the last
+// iterations of a chunk run on thinning lanes.  Lit records go through the per-warp ring (in
+// global memory, kQueueDepth deep) tagged with their pixel; the sweeps add a pixel's radiance
+// into the warp's shared accumulators in ring order (match_any groups, rank by rank), so the
+// image is bit-reproducible.  Gradients, chunk distribution and reduction as in render_kernel.
+// ---------------------------------------------------------------------------
+constexpr int kRegenPixels = 64;
+#ifndef DRTB_REFILL_LANES
+#define DRTB_REFILL_LANES 8
+#endif
+__host__ __device__ constexpr size_t regen_smem_per_warp() { return size_t(kRegenPixels) * (3 * sizeof(double) + sizeof(int2)); }
+__host__ __device__ constexpr size_t regen_ring_per_warp(size_t real_size) { return queue_bytes_per_warp(kQueueDepth, real_size, 1) + kQueueSlots; }
+
+template <typename R, bool SMALLP>
+__global__ void __launch_bounds__(kBlock, sizeof(R) == 4 ? DRTB_MIN_BLOCKS_F32 : DRTB_MIN_BLOCKS)
+render_regen_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ RenderArgs a)
+{
+    extern __shared__ double s_dyn[];              // [acc][per warp: pxacc[kRegenPixels][3] | pxy[kRegenPixels]]
+    __shared__ BlockScene<R> bs;
+    const bool want_grad = (a.flags & DRTB_FLAG_GRAD) != 0;
+    const int P3 = sc.n_params * 3;
+    double* s_acc = s_dyn;
+    const int acc_doubles = !want_grad ? 0 : SMALLP ? P3 * kBlock : P3 * a.sink_cols;
+    load_block_scene(bs, sc, a.params);
+    for (int i = threadIdx.x; i < acc_doubles; i += kBlock) s_acc[i] = 0.0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int W = sc.width, spp = a.spp;
+    const long long npix = (long long)a.shard_rows * W;
+    const R inv_p = R(1.0 / (1.0 - a.absorb));
+    double* pxacc = s_dyn + acc_doubles + size_t(warp) * (regen_smem_per_warp() / sizeof(double));
+    int2* pxy = reinterpret_cast<int2*>(pxacc + kRegenPixels * 3);
+    unsigned char* ring = a.ring_scratch + (size_t(blockIdx.x) * kWarpsPerBlock + warp) * regen_ring_per_warp(sizeof(R));
+    R* ring_w = reinterpret_cast<R*>(ring);
+    uint8_t* ring_prim = ring + size_t(kQueueDepth) * kQueueSlots * sizeof(R);
+    uint8_t* ring_n = ring_prim + size_t(kQueueDepth) * kQueueSlots;
+    uint8_t* ring_px = ring_n + kQueueSlots;
+    int q_head = 0, q_count = 0;                   // warp-uniform
+
+    SmemSink ssink{s_acc + threadIdx.x};
+    SmemAtomicSink msink{s_acc + (threadIdx.x & (a.sink_cols - 1)), a.sink_cols};
+    Materials<R, false> mat;
+    mat.bs = &bs;
+    TraceCounters cnt;
+    uint32_t n_lit = 0;
+
+    for (;;) {
+        unsigned long long claimed = 0;
+        if (lane == 0) claimed = atomicAdd(a.task_counter, 1ull);
+        const long long chunk = (long long)__shfl_sync(0xffffffffu, claimed, 0);
+        if (chunk >= a.n_chunks) break;
+        // big chunks of chunk_tasks pixels, then a last round of small ones (render_kernel's tail rule)
+        const long long big_end = a.n_big_chunks * a.chunk_tasks;
+        const long long pix0 = chunk < a.n_big_chunks ? chunk * a.chunk_tasks : big_end + (chunk - a.n_big_chunks) * a.small_chunk;
+        const long long pix1 = min(npix, pix0 + (chunk < a.n_big_chunks ? a.chunk_tasks : a.small_chunk));
+        const int K = int(pix1 - pix0);
+        for (int k = lane; k < K; k += 32) {        // this chunk's pixels: image coordinates, cleared sums
+            const long long pix = pix0 + k;
+            const int r = int(pix / W);
+            const int x = int(pix - (long long)r * W);
+            const int y = a.shard_count > 1 ? ((r / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + r % a.band_rows : r;
+            pxy[k] = make_int2(x, y);
+            pxacc[3 * k] = 0.0; pxacc[3 * k + 1] = 0.0; pxacc[3 * k + 2] = 0.0;
+        }
+        __syncwarp();
+
+        // a pixel's radiance: lanes holding the same pixel add one after the other, in lane order
+        auto add_to_pixels = [&](int px, const R* L0) {       // px < 0: nothing to add
+            const unsigned grp = __match_any_sync(0xffffffffu, px);
+            const int rank = __popc(grp & lt_mask);
+            const int rounds = __reduce_max_sync(0xffffffffu, px < 0 ? 0 : __popc(grp));
+            for (int r = 0; r < rounds; ++r) {
+                if (px >= 0 && rank == r) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) pxacc[3 * px + c] += double(L0[c]);
+                }
+                __syncwarp();
+            }
+        };
+        // both sweeps over one record of pixel px (render.cpp:78-80)
+        auto sweep = [&](const auto& rec, int n, int px, R* L0) {
+            R g0[3] = {R(0), R(0), R(0)};
+            if (want_grad) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) g0[c] = R(a.seed_scale * (a.seed_img ? a.seed_img[(pix0 + px) * 3 + c] : 1.0));
+            }
+            if constexpr (SMALLP) radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ssink);
+            else                  radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, msink);
+            n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
+        };
+        auto drain = [&](int m) {
+            __syncwarp();
+            R L0[3] = {R(0), R(0), R(0)};
+            int px = -1;
+            if (lane < m) {
+                const int slot = (q_head + lane) & (kQueueSlots - 1);
+                QueueView<R, false> qv{ring_w + slot, ring_prim + slot};
+                px = ring_px[slot];
+                sweep(qv, ring_n[slot], px, L0);
+            }
+            add_to_pixels(px, L0);
+            q_head = (q_head + m) & (kQueueSlots - 1);
+            q_count -= m;
+        };
+
+        const int n_samples = K * spp;                        // <= kRegenPixels * spp
+        int next_s = 0;                                       // warp-uniform: next unassigned sample of the chunk
+        bool alive = false, lit = false;
+        int depth = 0, n = 0, my_px = 0;
+        uint64_t ctr = 0;
+        V3<R> o = {R(0), R(0), R(0)}, d = o;
+        PathRecord<R, false, kMaxDepth> rec;
+        for (;;) {
+            const unsigned dead = __ballot_sync(0xffffffffu, !alive);
+            if (next_s < n_samples && (__popc(dead) >= DRTB_REFILL_LANES || dead == 0xffffffffu)) {
+                const int mine = next_s + __popc(dead & lt_mask);
+                if (!alive && mine < n_samples) {
+                    my_px = mine / spp;
+                    const int i = mine - my_px * spp;
+                    const int2 xy = pxy[my_px];
+                    const uint64_t key = a.key0 + ((uint64_t)xy.y * W + xy.x) * (uint64_t)spp + (uint64_t)i;
+                    const uint64_t base = key * kKeyMul;
+                    o = {sc.eye[0], sc.eye[1], sc.eye[2]};
+                    d = camera_ray(sc, xy.x, xy.y, base);
+                    ctr = base + kGolden + 2u;
+                    depth = 0; n = 0; lit = false;
+                    alive = !roulette_absorbs(ctr, 0, a.min_bounces, a.absorb);     // min_bounces == 0: trace() may return 0 at once
+                }
+                next_s = min(n_samples, next_s + __popc(dead));
+            }
+            if (__ballot_sync(0xffffffffu, alive) == 0u) {
+                if (next_s >= n_samples) break;
+                continue;                                      // every fresh sample was absorbed at once (min_bounces == 0)
+            }
+            bool done = false;
+            if (alive) done = trace_segment(sc, bs, mat, ctr, o, d, depth, n, lit, a.min_bounces, a.absorb, a.max_depth, rec, cnt);
+            if (done) alive = false;
+            // a record too deep for the ring (p ~ 1e-5 at the reference's defaults) is swept by its own lane
+            const bool deep = done && lit && n > kQueueDepth;
+            if (__any_sync(0xffffffffu, deep)) {
+                R L0[3] = {R(0), R(0), R(0)};
+                if (deep) sweep(rec, n, my_px, L0);
+                add_to_pixels(deep ? my_px : -1, L0);
+            }
+            const bool queued = done && lit && n <= kQueueDepth;
+            const unsigned m = __ballot_sync(0xffffffffu, queued);
+            if (queued) {
+                const int slot = (q_head + q_count + __popc(m & lt_mask)) & (kQueueSlots - 1);
+                for (int v = 0; v < n; ++v) {
+                    ring_w[v * kQueueSlots + slot] = rec.w_[v];
+                    ring_prim[v * kQueueSlots + slot] = rec.prim_[v];
+                }
+                ring_n[slot] = uint8_t(n);
+                ring_px[slot] = uint8_t(my_px);
+            }
+            q_count += __popc(m);
+            if (q_count >= 32) drain(32);
+        }
+        if (q_count > 0) drain(q_count);
+        __syncwarp();
+
+        // pixel_radiance / samples (render.cpp:82), compact shard image and/or every peer's full image
+        for (int k = lane; k < K; k += 32) {
+            const int2 xy = pxy[k];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double v = pxacc[3 * k + c] / double(spp);
+                if (a.img) a.img[(pix0 + k) * 3 + c] = v;
+                for (int p = 0; p < a.n_peer_img; ++p) a.peer_img[p][((size_t)xy.y * W + xy.x) * 3 + c] = v;
+            }
+        }
+        __syncwarp();
+        if (SMALLP && want_grad) {                            // this chunk's gradient row (see render_kernel)
+            double mine = 0.0;
+            for (int j = 0; j < P3; ++j) {
+                const double v = warp_sum(s_acc[j * kBlock + threadIdx.x]);
+                s_acc[j * kBlock + threadIdx.x] = 0.0;
+                if (lane == j) mine = v;
+            }
+            if (lane < P3) a.grad_partial[(size_t)chunk * P3 + lane] = mine;
+        }
+    }
+    if (!SMALLP && want_grad) {
+        __syncthreads();                           // every warp's atomics have landed
+        for (int j = threadIdx.x; j < P3; j += kBlock) {
+            double v = 0.0;
+            for (int c = 0; c < a.sink_cols; ++c) v += s_acc[j * a.sink_cols + c];
+            a.grad_partial[(size_t)blockIdx.x * P3 + j] = v;
+        }
+    }
+    if (a.stats) {
+        auto total = [](uint32_t v) {
+            unsigned long long t = v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            return t;
+        };
+        const unsigned long long seg = total(cnt.segments), litp = total(n_lit), tr = total(cnt.truncated);
+        if (lane == 0) {
+            atomicAdd((unsigned long long*)&a.stats->segments, seg);
+            atomicAdd((unsigned long long*)&a.stats->lit_paths, litp);
+            if (tr) atomicAdd((unsigned long long*)&a.stats->truncated_paths, tr);
         }
     }
 }
@@ -850,13 +1009,57 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
         if (rc != DRTB_OK) return rc;
         a.grad_partial = ctx->d_partial;
     }
-    if (QUEUE >= 2) {
-        const size_t per_warp = queue_bytes_per_warp(QUEUE == 3 ? kQueueDepth : a.max_depth, sizeof(R), MESH ? sizeof(int32_t) : sizeof(uint8_t));
+    if (QUEUE == 2) {
+        const size_t per_warp = queue_bytes_per_warp(a.max_depth, sizeof(R), MESH ? sizeof(int32_t) : sizeof(uint8_t));
         rc = ensure(ctx, ctx->d_ring, ctx->ring_cap, size_t(grid) * kWarpsPerBlock * per_warp / sizeof(double));
         if (rc != DRTB_OK) return rc;
         a.ring_scratch = reinterpret_cast<unsigned char*>(ctx->d_ring);
     }
     render_kernel<R, SMALLP, QUEUE, MESH, GEN><<<int(grid), kBlock, smem, stream>>>(sc, a);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    rows_out = rows;
+    return DRTB_OK;
+}
+
+// Russian-roulette renders of all-diffuse analytic scenes: render_regen_kernel.
+template <typename R, bool SMALLP>
+int launch_regen(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, long long npix, int P3, bool want_grad,
+                 cudaStream_t stream, size_t& rows_out)
+{
+    size_t smem = kWarpsPerBlock * regen_smem_per_warp();
+    if (want_grad) smem += SMALLP ? size_t(P3) * kBlock * sizeof(double) : size_t(P3) * a.sink_cols * sizeof(double);
+    int per_sm = 0;
+    CK(ctx, cudaFuncSetAttribute(render_regen_kernel<R, SMALLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_regen_kernel<R, SMALLP>, kBlock, smem));
+    if (per_sm < 1) return fail(ctx, DRTB_ERR_CUDA, "regenerating render kernel does not fit on an SM");
+    // chunks of about 1024 samples, at most kRegenPixels pixels, at least ~8 chunks per resident warp; the last
+    // round in chunks of about 64 samples so that the tail of the kernel stays short
+    const long long n_warps_max = (long long)ctx->sm_count * per_sm * kWarpsPerBlock;
+    long long big = std::max<long long>(1, std::min<long long>(kRegenPixels, 1024 / a.spp));
+    big = std::max<long long>(1, std::min(big, npix / (8 * n_warps_max)));
+    const long long small = std::max<long long>(1, std::min<long long>(big, 64 / a.spp));
+    const long long small_pixels = big > small ? std::min(npix, n_warps_max * big) : 0;
+    a.chunk_tasks = int(big);
+    a.small_chunk = int(small);
+    a.n_big_chunks = (npix - small_pixels) / big;
+    const long long rest = npix - a.n_big_chunks * big;
+    a.n_chunks = a.n_big_chunks + (rest + small - 1) / small;
+    long long grid = std::min<long long>((long long)ctx->sm_count * per_sm, (a.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    if (grid < 1) grid = 1;
+    if (!ctx->d_task_counter) CK(ctx, cudaMalloc(&ctx->d_task_counter, sizeof(unsigned long long)));
+    CK(ctx, cudaMemsetAsync(ctx->d_task_counter, 0, sizeof(unsigned long long), stream));
+    a.task_counter = ctx->d_task_counter;
+    int rc = ensure(ctx, ctx->d_ring, ctx->ring_cap, size_t(grid) * kWarpsPerBlock * regen_ring_per_warp(sizeof(R)) / sizeof(double));
+    if (rc != DRTB_OK) return rc;
+    a.ring_scratch = reinterpret_cast<unsigned char*>(ctx->d_ring);
+    const size_t rows = !want_grad ? 0 : SMALLP ? size_t(a.n_chunks) : size_t(grid);
+    if (rows) {
+        rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (rows + reduce_scratch_rows(rows)) * P3);
+        if (rc != DRTB_OK) return rc;
+        a.grad_partial = ctx->d_partial;
+    }
+    render_regen_kernel<R, SMALLP><<<int(grid), kBlock, smem, stream>>>(sc, a);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     rows_out = rows;
@@ -870,7 +1073,6 @@ int launch_precision(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, bool s
 #define DRTB_LAUNCH(SP, Q, M) launch_variant<R, SP, Q, M, false>(ctx, sc, a, smem, n_tasks, P3, want_grad, stream, rows)
 #define DRTB_LAUNCH_GEN(SP, Q) launch_variant<R, SP, Q, false, true>(ctx, sc, a, smem, n_tasks, P3, want_grad, stream, rows)
 #define DRTB_BY_QUEUE(L, SP, ...) (queue == 2 ? L(SP, 2, ##__VA_ARGS__) : queue == 1 ? L(SP, 1, ##__VA_ARGS__) : L(SP, 0, ##__VA_ARGS__))
-    if (queue == 3) return smallp ? DRTB_LAUNCH(true, 3, false) : DRTB_LAUNCH(false, 3, false);    // path regeneration
     if (gen) {
         // SpecularBxDF materials and/or a gradient image (analytic scenes; mesh scenes take the wavefront)
         if (mesh) return fail(ctx, DRTB_ERR_UNSUPPORTED, "specular materials / gradient images on a mesh scene need the wavefront pipeline");
@@ -1002,8 +1204,6 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
         const size_t static_smem = (f32 ? sizeof(BlockScene<float>) : sizeof(BlockScene<double>)) + 1024;   // + 1 KB the system reserves per block
         if ((static_smem + smem + ring_bytes) * want_blocks > size_t(228) * 1024) queue_kind = 2;
     }
-    // Russian roulette on an all-diffuse analytic scene: the regenerating kernel (ring in global memory)
-    if (o->spp >= 32 && o->absorb < 1.0 && !mesh && !gen && !ctx->no_regen) queue_kind = 3;
     if (queue_kind < 2) smem += ring_bytes;
     smem = (smem + 15) & ~size_t(15);
     const long long npix = (long long)rows * W;
@@ -1018,8 +1218,18 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
         a.grad_atomic = d_grad;
     }
     size_t partial_rows = 0;
-    int rc = f32 ? launch_precision<float>(ctx, ctx->sc32, a, smallp, queue_kind, mesh, gen, smem, n_tasks, P3, want_grad, stream, partial_rows)
+    int rc;
+    // Russian roulette on an all-diffuse analytic scene: the path-regenerating kernel
+    const bool regen = o->absorb < 1.0 && !mesh && !gen && !ctx->no_regen;
+    if (regen) {
+        rc = f32 ? (smallp ? launch_regen<float, true>(ctx, ctx->sc32, a, npix, P3, want_grad, stream, partial_rows)
+                           : launch_regen<float, false>(ctx, ctx->sc32, a, npix, P3, want_grad, stream, partial_rows))
+                 : (smallp ? launch_regen<double, true>(ctx, ctx->sc64, a, npix, P3, want_grad, stream, partial_rows)
+                           : launch_regen<double, false>(ctx, ctx->sc64, a, npix, P3, want_grad, stream, partial_rows));
+    } else {
+        rc = f32 ? launch_precision<float>(ctx, ctx->sc32, a, smallp, queue_kind, mesh, gen, smem, n_tasks, P3, want_grad, stream, partial_rows)
                  : launch_precision<double>(ctx, ctx->sc64, a, smallp, queue_kind, mesh, gen, smem, n_tasks, P3, want_grad, stream, partial_rows);
+    }
     if (rc != DRTB_OK) return rc;
     if (want_grad && (smallp || shared_atomic)) return reduce_partials(ctx, ctx->d_partial, partial_rows, P3, d_grad, stream);
     return DRTB_OK;

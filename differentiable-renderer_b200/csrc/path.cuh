@@ -116,7 +116,8 @@ struct RenderArgs {
     unsigned char* ring_scratch;         // QUEUE == 2: per-warp lit-path rings in global memory
     unsigned long long* task_counter;    // zeroed before the launch: next unclaimed chunk of warp tasks
     int32_t  chunk_tasks;                // consecutive warp tasks per big chunk
-    long long n_big_chunks, n_chunks;    // chunks [n_big_chunks, n_chunks) are single tasks
+    long long n_big_chunks, n_chunks;    // chunks [n_big_chunks, n_chunks) are single tasks (render_kernel)
+    int32_t  small_chunk;                // ... or small_chunk pixels each (render_regen_kernel, whose tasks are pixels)
 };
 
 // Per-block shared copy of what is looked up with a PER-LANE index (the prim a
