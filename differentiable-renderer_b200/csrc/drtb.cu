@@ -5,6 +5,8 @@
 //                              (camera sample -> trace -> radiance -> adjoint),
 //                              lanes of a warp = consecutive samples of one pixel;
 //                              warps claim chunks of pixels from a global counter
+//   render_regen_kernel<R, SMALLP>  the same pixel loop for Russian-roulette renders, with path
+//                              regeneration over a chunk of pixels
 //   reduce_grad_kernel         fixed-order sum of the per-chunk gradient partials
 //   trace_rays_kernel<R>       Pathtracer::trace on explicit rays (+ Jacobian)
 //   fma_peak_kernel<R>         FMA issue-rate micro-benchmark (roofline denominator)
@@ -98,7 +100,7 @@ struct JacSink {
 // The pixel loop of src/render.cpp:72-86.
 //   SMALLP: <= kSmallP parameters, gradients in per-thread shared columns
 //   QUEUE : spp >= 32 and max_depth <= kQueueDepth: lit paths are compacted through a per-warp
-//           ring before the sweeps.  1: the ring lives in shared memory; 2: in a global scratch
+//           ring before the sweeps.  0: no ring; 1: the ring lives in shared memory; 2: in a global scratch
 //           buffer (L1/L2 resident), chosen when the shared ring of a deep record (max_depth > 8
 //           in double) would cost resident blocks -- the ring carries only the ~16-21 % of the
 //           paths that are lit, so its latency does not matter, the occupancy does

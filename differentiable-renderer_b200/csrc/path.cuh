@@ -563,8 +563,8 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
 
 // ---------------------------------------------------------------------------
 // ONE segment of trace_path for one lane whose path state lives in the caller
-// (analytic scenes, diffuse BxDFs): the regenerating kernel (render_kernel,
-// QUEUE == 3) steps every lane once per iteration and hands a fresh camera
+// (analytic scenes, diffuse BxDFs): the regenerating kernel
+// (render_regen_kernel) steps every lane once per iteration and hands a fresh camera
 // sample to lanes whose path has ended.  Same arithmetic, same draws, same
 // record as trace_path; the roulette of the NEXT trace() call is decided here
 // as well.  Returns true when the path ends with this call.

@@ -1,7 +1,7 @@
-"""The path-regenerating kernel (render_kernel, QUEUE == 3): Russian-roulette renders with
-spp >= 32 on all-diffuse analytic scenes.  Every lane steps one segment per iteration and free
-lanes take the pixel's next samples, so the pixel sums are taken in another order than in the
-pass-based kernel -- results agree to rounding, path statistics exactly."""
+"""The path-regenerating kernel (render_regen_kernel): Russian-roulette renders of all-diffuse
+analytic scenes.  Every lane steps one segment per iteration and free lanes take the next samples
+of the warp's chunk of pixels, so the pixel sums are taken in another order than in the pass-based
+kernel -- results agree to rounding, path statistics exactly."""
 import os
 
 import numpy as np
