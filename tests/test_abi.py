@@ -92,3 +92,26 @@ def test_scene_flattening_matches_src_render_cpp():
     assert mats == [2, 2, 0, 1, 2, 2, 2, 2]                          # white shared by six shapes
     assert np.allclose(list(sc.camera.forward), [0, 0, 1]) and np.allclose(list(sc.camera.right), [-1, 0, 0])
     assert np.allclose(list(sc.camera.up), [0, 1, 0]) and sc.camera.vfov == 1.3963
+
+
+def test_hot_kernels_keep_their_register_budget():
+    """The render kernels are issue bound and sized for 5 (double) / 6 (float) resident blocks of 128
+    threads per SM: a spill or a register count past the budget would silently cost occupancy.
+    Read from the ptxas report of the in-tree build (lib/build.log, written by build.py)."""
+    log = abi.LIB_PATH.parent / "build.log"
+    if not log.exists():
+        pytest.skip("libdrtb.so was not built by build.py in this tree")
+    text = log.read_text()
+    blocks = re.findall(r"Compiling entry function '(\S+)' for 'sm_100a'.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n"
+                        r"ptxas info\s+: Used (\d+) registers", text)
+    seen = 0
+    for name, _stack, st, ld, regs in blocks:
+        hot = ("render_kernelI" in name and name.split("render_kernelI")[1][1:].startswith("Lb1ELi")
+               and "Lb0ELb0EEE" in name) or "render_regen_kernelI" in name      # SMALLP, analytic, all-diffuse
+        if not hot:
+            continue
+        seen += 1
+        is_double = "render_kernelId" in name or "render_regen_kernelId" in name
+        assert int(st) == 0 and int(ld) == 0, f"{name}: spills"
+        assert int(regs) <= (102 if is_double else 85), f"{name}: {regs} registers"
+    assert seen >= 8, seen
