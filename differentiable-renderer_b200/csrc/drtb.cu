@@ -1038,9 +1038,10 @@ int launch_regen(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, long long 
     // chunks of about 1024 samples, at most kRegenPixels pixels, at least ~8 chunks per resident warp; the last
     // round in chunks of about 64 samples so that the tail of the kernel stays short
     const long long n_warps_max = (long long)ctx->sm_count * per_sm * kWarpsPerBlock;
+    const long long full_warp = std::min<long long>(kRegenPixels, (32 + a.spp - 1) / a.spp);     // pixels that fill 32 lanes once
     long long big = std::max<long long>(1, std::min<long long>(kRegenPixels, 1024 / a.spp));
-    big = std::max<long long>(1, std::min(big, npix / (8 * n_warps_max)));
-    const long long small = std::max<long long>(1, std::min<long long>(big, 64 / a.spp));
+    big = std::max(full_warp, std::min(big, npix / (8 * n_warps_max)));
+    const long long small = std::max(full_warp, std::min<long long>(big, 64 / a.spp));
     const long long small_pixels = big > small ? std::min(npix, n_warps_max * big) : 0;
     a.chunk_tasks = int(big);
     a.small_chunk = int(small);
