@@ -789,6 +789,7 @@ struct drtb_ctx {
     double* d_params = nullptr;   size_t params_cap = 0;
     double* d_partial = nullptr;  size_t partial_cap = 0;
     double* d_ring = nullptr;     size_t ring_cap = 0;      // lit-path rings of the QUEUE >= 2 kernels
+    int ring_policy = 0;          // DRTB_RING=global: lit-path ring in global memory at every depth (A/B aid)
     bool no_regen = false;        // DRTB_NO_REGEN=1: Russian-roulette renders without path regeneration (A/B aid)
     double* d_img = nullptr;      size_t img_cap = 0;
     double* d_seed = nullptr;     size_t seed_cap = 0;
@@ -1207,6 +1208,12 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
         const size_t static_smem = (f32 ? sizeof(BlockScene<float>) : sizeof(BlockScene<double>)) + 1024;   // + 1 KB the system reserves per block
         if ((static_smem + smem + ring_bytes) * want_blocks > size_t(228) * 1024) queue_kind = 2;
     }
+    // Measured and NOT adopted for records that fit (B <= 8, double): the global ring at every depth is 0.9 % faster
+    // (42.51 against 42.88 ms: the freed shared memory goes to the L1 that holds the local-memory records, hit rate
+    // 44 -> 81 %) but the L2 writes the constantly rewritten rings back to HBM, 0.9 GB per render against 0.15 GB --
+    // a per-launch persisting access-policy window over the rings did not change that -- and keeping the lanes' own
+    // records in the freed shared memory instead of local memory was slower (43.71 ms).  DRTB_RING forces either.
+    if (queue_kind == 1 && !mesh && ctx->ring_policy == 2) queue_kind = 2;
     if (queue_kind < 2) smem += ring_bytes;
     smem = (smem + 15) & ~size_t(15);
     const long long npix = (long long)rows * W;
@@ -1421,6 +1428,7 @@ int drtb_create(int device, drtb_ctx** out)
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = std::getenv("DRTB_MESH_PIPELINE")) ctx->mesh_megakernel = std::string(e) == "megakernel";
     if (const char* e = std::getenv("DRTB_NO_REGEN")) ctx->no_regen = std::atoi(e) != 0;
+    if (const char* e = std::getenv("DRTB_RING")) ctx->ring_policy = std::string(e) == "global" ? 2 : 0;
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
