@@ -10,9 +10,11 @@ traced to termination plus its gradient contribution (BASELINE.json `metric`).
 `e2e`    : the same through the C ABI call with HOST buffers (drtb_set_params +
            drtb_render), parameter H2D and image/gradient D2H inside the timing.
 N > 1    : launched under torchrun, one rank per GPU; image rows are sharded in
-           interleaved bands, gradients summed with one NCCL all-reduce, image
-           bands all-gathered; max over ranks; weak scaling is NOT used -- the
-           workload is fixed, so "scaling" is "strong".
+           interleaved bands, gradients summed with one NCCL all-reduce; the image
+           gather is fused into the render kernel (every rank's kernel stores its
+           pixels into all ranks' full images over NVLink, drtb_set_image_peers),
+           checked once against an NCCL all-gather before timing; max over ranks;
+           weak scaling is NOT used -- the workload is fixed, so "scaling" is "strong".
 """
 from __future__ import annotations
 

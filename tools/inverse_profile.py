@@ -1,5 +1,8 @@
+"""GPU time of the pieces of one inverse-rendering iteration (development aid): image-only render,
+adjoint render with a seed image, both in one call, and the tensor arithmetic between them."""
 import sys, time
-sys.path.insert(0, "/root/repo")
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch, numpy as np
 import drt_b200 as drt
 dev = torch.device("cuda", 0); stream = torch.cuda.current_stream().cuda_stream
