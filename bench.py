@@ -113,13 +113,19 @@ def cpu_render_rate(a, seconds_budget: float, threads: int | None = None):
     import oracle_lib
     import drt_b200 as drt
     kind = "reference" if oracle_lib.have_ref() else "port"
+    # every host core this process may run on: torchrun exports OMP_NUM_THREADS=1, which would turn the
+    # CPU arm into a single-thread run (the thread count is passed to the library explicitly)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     if kind == "reference":
         lib = oracle_lib.load_ref()
-        nthr = threads or lib.drt_ref_max_threads()
+        nthr = threads or max(cores, lib.drt_ref_max_threads())
         run = lambda sc, o: oracle_lib.ref_render(sc, o, threads=nthr)
     else:
         lib = oracle_lib.load_restate()
-        nthr = threads or lib.drt_oracle_max_threads()
+        nthr = threads or max(cores, lib.drt_oracle_max_threads())
         run = lambda sc, o: oracle_lib.restate_render(sc, o, threads=nthr)
     spp = min(a.spp, 16)
     # pilot to size the sample
