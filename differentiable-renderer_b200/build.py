@@ -30,8 +30,9 @@ NVCC_FLAGS = [
     # no spills; measured on B200: 69.4 ms vs 76.3 ms uncapped (141 registers),
     # and no further gain from 6/7/8 (the kernel is issue bound, not latency bound).
     "-DDRTB_MIN_BLOCKS=5",
-    # the float instantiation needs fewer registers: 6 blocks (85 registers) measured 4 % faster than 5
-    "-DDRTB_MIN_BLOCKS_F32=6",
+    # the float instantiation needs fewer registers: resident blocks 5 / 6 / 7 / 8 -> 34.6 / 33.1 / 31.2 / 31.1 ms;
+    # 7 (72 registers) is the most that stays free of spills in every all-diffuse variant
+    "-DDRTB_MIN_BLOCKS_F32=7",
     # mesh kernels are latency bound (BVH node fetches): more resident warps beat more registers
     "-DDRTB_MESH_MIN_BLOCKS=6",
 ]

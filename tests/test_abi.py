@@ -95,7 +95,7 @@ def test_scene_flattening_matches_src_render_cpp():
 
 
 def test_hot_kernels_keep_their_register_budget():
-    """The render kernels are issue bound and sized for 5 (double) / 6 (float) resident blocks of 128
+    """The render kernels are issue bound and sized for 5 (double) / 7 (float) resident blocks of 128
     threads per SM: a spill or a register count past the budget would silently cost occupancy.
     Read from the ptxas report of the in-tree build (lib/build.log, written by build.py)."""
     log = abi.LIB_PATH.parent / "build.log"
@@ -113,5 +113,5 @@ def test_hot_kernels_keep_their_register_budget():
         seen += 1
         is_double = "render_kernelId" in name or "render_regen_kernelId" in name
         assert int(st) == 0 and int(ld) == 0, f"{name}: spills"
-        assert int(regs) <= (102 if is_double else 85), f"{name}: {regs} registers"
+        assert int(regs) <= (102 if is_double else 73), f"{name}: {regs} registers"
     assert seen >= 8, seen
