@@ -629,12 +629,68 @@ __device__ __forceinline__ bool trace_segment(const DevScene<R>& sc, const Block
 //   g_{v+1} = gp w_v rho_v / pi.           (per channel; channels never mix)
 // Sink::add(param_index, channel, value) receives the contributions.
 // ---------------------------------------------------------------------------
+// The same for a record deeper than kQueueDepth, without the L_{v+1} array: the forward sweep
+// re-runs the backward recurrence from the end of the path down to v + 1 for every vertex
+// (O(n^2), n <= 64, rare) -- the same operations in the same order, hence the same bits.
+template <typename R, typename Mat, typename Rec, typename Sink>
+__device__ __noinline__ void radiance_and_adjoint_deep(const Mat& mat, const Rec& rec, int n, int min_bounces, R inv_p,
+                                                       bool want_grad, const R g0[3], R L0[3], Sink& sink)
+{
+    auto radiance_from = [&](int first, R L[3]) {           // L_first, sweeping v = n - 1 .. first
+        L[0] = L[1] = L[2] = R(0);
+        for (int v = n - 1; v >= first; --v) {
+            const int k = rec.prim(v);
+            const int em = mat.em(k), col = mat.col(k);
+            const R ip = v >= min_bounces ? inv_p : R(1);
+            const R f = rec.w(v) * Real<R>::inv_pi();
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                R E = em >= 0 ? mat.param(3 * em + c) : R(0);
+                R rho = col >= 0 ? mat.param(3 * col + c) : R(0);
+                L[c] = (E + rho * f * L[c]) * ip;
+            }
+        }
+    };
+    radiance_from(0, L0);
+    if (!want_grad) return;
+    R g[3] = {g0[0], g0[1], g0[2]};
+    for (int v = 0; v < n; ++v) {
+        const int k = rec.prim(v);
+        const int em = mat.em(k), col = mat.col(k);
+        const R ip = v >= min_bounces ? inv_p : R(1);
+        const R f = rec.w(v) * Real<R>::inv_pi();
+        R Ln[3];
+        radiance_from(v + 1, Ln);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            R gp = g[c] * ip;
+            if (em >= 0) sink.add(em, c, gp);
+            if (col >= 0) {
+                sink.add(col, c, gp * f * Ln[c]);
+                g[c] = gp * f * mat.param(3 * col + c);
+            } else {
+                g[c] = R(0);
+            }
+        }
+    }
+}
+
 template <typename R, typename Mat, typename Rec, typename Sink>
 __device__ __forceinline__ void radiance_and_adjoint(const Mat& mat, const Rec& rec,
                                                      int n, int min_bounces, R inv_p,
                                                      bool want_grad, const R g0[3], R L0[3], Sink& sink)
 {
-    R Ls[Rec::kCap + 1][3];
+    // L_{v+1} of every vertex is kept for the forward sweep -- for up to kQueueDepth vertices.  Deeper records
+    // (capacity kMaxDepth; p ~ 1e-5 at the reference's defaults) recompute it instead, see below: a 65 x 3 array
+    // per thread would triple the local memory the driver has to reserve for every resident thread.
+    constexpr int kKeep = Rec::kCap < kQueueDepth ? Rec::kCap : kQueueDepth;
+    if constexpr (Rec::kCap > kQueueDepth) {
+        if (n > kQueueDepth) {
+            radiance_and_adjoint_deep(mat, rec, n, min_bounces, inv_p, want_grad, g0, L0, sink);
+            return;
+        }
+    }
+    R Ls[kKeep + 1][3];
     R L[3] = {R(0), R(0), R(0)};
     for (int v = n - 1; v >= 0; --v) {
         const int k = rec.prim(v);
