@@ -98,6 +98,7 @@ SYMBOLS = [
     ("drtb_trace_rays", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), C.c_int64, _dp, _dp,
                                   C.POINTER(C.c_uint64), _dp, _dp]),
     ("drtb_fma_peak", C.c_int, [C.c_void_p, C.c_int32, _dp]),
+    ("drtb_chunk_plan", C.c_int, [C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]),
     ("drtb_launch_count", C.c_uint64, [C.c_void_p]),
     ("drtb_stream_draw", C.c_uint32, [C.c_uint64, C.c_uint32]),
 ]

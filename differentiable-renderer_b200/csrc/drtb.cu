@@ -954,6 +954,46 @@ int occupancy(drtb_ctx* ctx, K kernel, size_t smem, int& out)
     return DRTB_OK;
 }
 
+// How a render's units of work are cut into the chunks that warps claim from the global counter
+// (render_kernel: units = warp tasks; render_regen_kernel: units = pixels).  The first n_big chunks hold
+// `big` units each, the rest `small` units each (the last one possibly fewer): big chunks keep the claim and
+// the per-chunk gradient row cheap, the small ones of the last round keep the tail of the kernel short.
+// Pure host arithmetic, exported as drtb_chunk_plan so that the CPU tests can check that every unit is
+// covered exactly once for any size.
+struct ChunkPlan { long long big, small, n_big, n_chunks; };
+
+ChunkPlan plan_chunks(long long n_units, int spp, long long resident_warps, bool regen, long long forced_big)
+{
+    ChunkPlan p{1, 1, 0, 0};
+    if (n_units <= 0) return p;
+    if (resident_warps < 1) resident_warps = 1;
+    if (!regen) {
+        // about 1024 paths per chunk, but never so large that a warp gets fewer than ~8 chunks; then single tasks
+        const long long paths_per_task = spp >= 32 ? spp : 32;
+        long long big = std::max<long long>(1, 1024 / paths_per_task);
+        big = std::max<long long>(1, std::min(big, n_units / (8 * resident_warps)));
+        if (forced_big > 0) big = forced_big;
+        const long long small_units = big > 1 ? std::min(n_units, resident_warps * big) : 0;
+        p.big = big; p.small = 1;
+        p.n_big = (n_units - small_units) / big;
+        p.n_chunks = p.n_big + (n_units - p.n_big * big);
+    } else {
+        // about 1024 samples per chunk, at most kRegenPixels pixels, at least one warp of samples; the last round
+        // in chunks of about 64 samples
+        const long long full_warp = std::min<long long>(kRegenPixels, (32 + spp - 1) / spp);   // pixels that fill 32 lanes once
+        long long big = std::max<long long>(1, std::min<long long>(kRegenPixels, 1024 / spp));
+        big = std::max(full_warp, std::min(big, n_units / (8 * resident_warps)));
+        if (forced_big > 0) big = std::max(full_warp, std::min<long long>(kRegenPixels, forced_big));
+        const long long small = std::max(full_warp, std::min<long long>(big, 64 / spp));
+        const long long small_units = big > small ? std::min(n_units, resident_warps * big) : 0;
+        p.big = big; p.small = small;
+        p.n_big = (n_units - small_units) / big;
+        const long long rest = n_units - p.n_big * big;
+        p.n_chunks = p.n_big + (rest + small - 1) / small;
+    }
+    return p;
+}
+
 // grad[j] = sum over `rows` partial rows, in an order fixed by `rows` alone.  Up to 4096 rows:
 // one block.  More (a large render leaves one row per chunk of warp tasks): a first pass of
 // 1024-row blocks into the scratch rows behind the partials, then one block over those.
@@ -987,17 +1027,13 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > need_blocks) grid = need_blocks;
     if (grid < 1) grid = 1;
-    // Chunks of warp tasks (render_kernel): about 1024 paths each, so that claiming one and flushing
-    // its gradient row cost nothing, but never so large that a warp gets fewer than ~8 of them.
-    const long long paths_per_task = a.spp >= 32 ? a.spp : 32;
-    long long chunk = std::max<long long>(1, 1024 / paths_per_task);
-    chunk = std::max<long long>(1, std::min(chunk, n_tasks / (8 * grid * kWarpsPerBlock)));
-    if (const char* e = std::getenv("DRTB_CHUNK_TASKS")) chunk = std::max(1, std::atoi(e));     // A/B aid
-    a.chunk_tasks = int(chunk);
-    // ... and the last round (one chunk's worth of tasks per resident warp) is handed out task by task
-    const long long small_tasks = chunk > 1 ? std::min(n_tasks, grid * kWarpsPerBlock * chunk) : 0;
-    a.n_big_chunks = (n_tasks - small_tasks) / chunk;
-    const long long n_chunks = a.n_big_chunks + (n_tasks - a.n_big_chunks * chunk);
+    long long forced = 0;
+    if (const char* e = std::getenv("DRTB_CHUNK_TASKS")) forced = std::max(1, std::atoi(e));     // A/B aid
+    const ChunkPlan plan = plan_chunks(n_tasks, a.spp, grid * kWarpsPerBlock, false, forced);
+    a.chunk_tasks = int(plan.big);
+    a.small_chunk = 1;
+    a.n_big_chunks = plan.n_big;
+    const long long n_chunks = plan.n_chunks;
     a.n_chunks = n_chunks;
     if (!ctx->d_task_counter) CK(ctx, cudaMalloc(&ctx->d_task_counter, sizeof(unsigned long long)));
     CK(ctx, cudaMemsetAsync(ctx->d_task_counter, 0, sizeof(unsigned long long), stream));
@@ -1036,19 +1072,11 @@ int launch_regen(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, long long 
     CK(ctx, cudaFuncSetAttribute(render_regen_kernel<R, SMALLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_regen_kernel<R, SMALLP>, kBlock, smem));
     if (per_sm < 1) return fail(ctx, DRTB_ERR_CUDA, "regenerating render kernel does not fit on an SM");
-    // chunks of about 1024 samples, at most kRegenPixels pixels, at least ~8 chunks per resident warp; the last
-    // round in chunks of about 64 samples so that the tail of the kernel stays short
-    const long long n_warps_max = (long long)ctx->sm_count * per_sm * kWarpsPerBlock;
-    const long long full_warp = std::min<long long>(kRegenPixels, (32 + a.spp - 1) / a.spp);     // pixels that fill 32 lanes once
-    long long big = std::max<long long>(1, std::min<long long>(kRegenPixels, 1024 / a.spp));
-    big = std::max(full_warp, std::min(big, npix / (8 * n_warps_max)));
-    const long long small = std::max(full_warp, std::min<long long>(big, 64 / a.spp));
-    const long long small_pixels = big > small ? std::min(npix, n_warps_max * big) : 0;
-    a.chunk_tasks = int(big);
-    a.small_chunk = int(small);
-    a.n_big_chunks = (npix - small_pixels) / big;
-    const long long rest = npix - a.n_big_chunks * big;
-    a.n_chunks = a.n_big_chunks + (rest + small - 1) / small;
+    const ChunkPlan plan = plan_chunks(npix, a.spp, (long long)ctx->sm_count * per_sm * kWarpsPerBlock, true, 0);
+    a.chunk_tasks = int(plan.big);
+    a.small_chunk = int(plan.small);
+    a.n_big_chunks = plan.n_big;
+    a.n_chunks = plan.n_chunks;
     long long grid = std::min<long long>((long long)ctx->sm_count * per_sm, (a.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock);
     if (grid < 1) grid = 1;
     if (!ctx->d_task_counter) CK(ctx, cudaMalloc(&ctx->d_task_counter, sizeof(unsigned long long)));
@@ -1684,6 +1712,14 @@ int drtb_set_params_device(drtb_ctx* ctx, const double* d_params, int32_t n_para
     CK(ctx, cudaSetDevice(ctx->device));
     // ordered on the caller's stream with the renders enqueued there; no host round trip
     CK(ctx, cudaMemcpyAsync(ctx->d_params, d_params, sizeof(double) * ctx->params.size(), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return DRTB_OK;
+}
+
+int drtb_chunk_plan(int64_t n_units, int32_t spp, int64_t resident_warps, int32_t regen, int64_t out[4])
+{
+    if (!out || n_units < 0 || spp < 1) return DRTB_ERR_INVALID;
+    const ChunkPlan p = plan_chunks(n_units, spp, resident_warps, regen != 0, 0);
+    out[0] = p.big; out[1] = p.small; out[2] = p.n_big; out[3] = p.n_chunks;
     return DRTB_OK;
 }
 

@@ -307,6 +307,13 @@ int drtb_trace_rays(drtb_ctx* ctx, const drtb_render_opts* opts, int64_t n,
  * (FMA = 2 FLOP). */
 int drtb_fma_peak(drtb_ctx* ctx, int32_t precision, double* tflops);
 
+/* How the render kernels cut n_units units of work (warp tasks, or pixels when regen != 0: the path-regenerating
+ * kernel of Russian-roulette renders) into the chunks that resident warps claim from a global counter:
+ * out = { units per big chunk, units per small chunk, number of big chunks, number of chunks }.  Chunk c covers
+ * units [c * big, (c + 1) * big) for c < n_big and [n_big * big + (c - n_big) * small, ... + small) clipped to
+ * n_units after that.  Host arithmetic, callable without a GPU (the tests check the cover). */
+int drtb_chunk_plan(int64_t n_units, int32_t spp, int64_t resident_warps, int32_t regen, int64_t out[4]);
+
 /* Number of kernels this context has launched so far (bench `gpu_launches`). */
 uint64_t drtb_launch_count(const drtb_ctx* ctx);
 

@@ -115,3 +115,43 @@ def test_hot_kernels_keep_their_register_budget():
         assert int(st) == 0 and int(ld) == 0, f"{name}: spills"
         assert int(regs) <= (102 if is_double else 73), f"{name}: {regs} registers"
     assert seen >= 8, seen
+
+
+def _chunk_cover(n_units, big, small, n_big, n_chunks):
+    """Units each chunk covers, as render_kernel / render_regen_kernel compute them from the plan."""
+    spans = []
+    for c in range(n_chunks):
+        if c < n_big:
+            lo, hi = c * big, (c + 1) * big
+        else:
+            lo = n_big * big + (c - n_big) * small
+            hi = lo + small
+        spans.append((lo, min(hi, n_units)))
+    return spans
+
+
+@pytest.mark.parametrize("regen", [0, 1])
+def test_chunk_plan_covers_every_unit_exactly_once(regen):
+    """The dynamic distribution's host arithmetic (drtb_chunk_plan): for any image size, spp and number of
+    resident warps the chunks tile [0, n_units) without gaps or overlaps, none is empty, big chunks come
+    first, and the regenerating kernel's chunks never exceed its 64-pixel accumulators."""
+    lib = drt.load_library()
+    rng = np.random.default_rng(7 + regen)
+    cases = [(1, 1, 2960), (31, 7, 2960), (2960 * 4, 256, 2960), (1 << 20, 256, 2960), (1 << 22, 128, 2960),
+             (131072, 256, 2960), (65536, 64, 2960), (65536, 16, 2960), (3072, 8, 2960), (5, 1000, 4), (100000, 1, 3552)]
+    cases += [(int(rng.integers(1, 300000)), int(rng.choice([1, 2, 3, 5, 8, 16, 31, 32, 33, 40, 64, 100, 256, 1024, 5000])),
+               int(rng.choice([1, 4, 64, 592, 2960, 3552, 4736]))) for _ in range(300)]
+    out = (C.c_int64 * 4)()
+    for n_units, spp, warps in cases:
+        assert lib.drtb_chunk_plan(n_units, spp, warps, regen, out) == abi.OK
+        big, small, n_big, n_chunks = (int(v) for v in out)
+        assert 1 <= small <= big and 0 <= n_big <= n_chunks, (n_units, spp, warps, list(out))
+        if regen:
+            assert big <= 64
+        spans = _chunk_cover(n_units, big, small, n_big, n_chunks)
+        assert spans[0][0] == 0 and spans[-1][1] == n_units
+        assert all(lo < hi for lo, hi in spans)                                  # no empty chunk
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))  # contiguous, disjoint
+    assert lib.drtb_chunk_plan(0, 16, 100, 0, out) == abi.OK and int(out[3]) == 0
+    assert lib.drtb_chunk_plan(10, 0, 100, 0, out) == abi.ERR_INVALID
+    assert lib.drtb_chunk_plan(10, 4, 100, 0, None) == abi.ERR_INVALID
