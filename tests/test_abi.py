@@ -139,8 +139,8 @@ def test_chunk_plan_covers_every_unit_exactly_once(regen):
     rng = np.random.default_rng(7 + regen)
     cases = [(1, 1, 2960), (31, 7, 2960), (2960 * 4, 256, 2960), (1 << 20, 256, 2960), (1 << 22, 128, 2960),
              (131072, 256, 2960), (65536, 64, 2960), (65536, 16, 2960), (3072, 8, 2960), (5, 1000, 4), (100000, 1, 3552)]
-    cases += [(int(rng.integers(1, 300000)), int(rng.choice([1, 2, 3, 5, 8, 16, 31, 32, 33, 40, 64, 100, 256, 1024, 5000])),
-               int(rng.choice([1, 4, 64, 592, 2960, 3552, 4736]))) for _ in range(300)]
+    cases += [(int(rng.integers(1, 60000)), int(rng.choice([1, 2, 3, 5, 8, 16, 31, 32, 33, 40, 64, 100, 256, 1024, 5000])),
+               int(rng.choice([1, 4, 64, 592, 2960, 3552, 4736]))) for _ in range(200)]
     out = (C.c_int64 * 4)()
     for n_units, spp, warps in cases:
         assert lib.drtb_chunk_plan(n_units, spp, warps, regen, out) == abi.OK
