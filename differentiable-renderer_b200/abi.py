@@ -12,7 +12,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "lib" / "libdrtb.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 SPHERE, PLANE = 0, 1
@@ -84,6 +84,7 @@ SYMBOLS = [
     ("drtb_set_params_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     ("drtb_shard_rows", C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("drtb_render", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), _dp, _dp, _dp, C.POINTER(Stats)]),
+    ("drtb_reserve", C.c_int, [C.c_void_p, C.POINTER(RenderOpts)]),
     ("drtb_render_device", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     ("drtb_render_grad_image", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), C.c_int32, _dp, _dp, _dp, _dp,

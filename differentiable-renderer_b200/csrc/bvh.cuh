@@ -57,6 +57,7 @@ struct MeshView {
 // ---------------------------------------------------------------------------
 // build kernels
 // ---------------------------------------------------------------------------
+#ifdef DRTB_BVH_BUILD_KERNELS        // mesh.cu only: the other translation units need the traversal below, not the build
 
 // order-preserving float <-> uint map for atomicMin/atomicMax on floats
 __device__ __forceinline__ uint32_t float_to_ordered(float f)
@@ -70,7 +71,7 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u)
 }
 
 // per triangle: edge form in double, outward-rounded float AABB; scene bounds
-__global__ void mesh_prepare_kernel(const double* __restrict__ vertices, const int32_t* __restrict__ indices, int n,
+static __global__ void mesh_prepare_kernel(const double* __restrict__ vertices, const int32_t* __restrict__ indices, int n,
                                     double* __restrict__ tri64, float4* __restrict__ leaf_lo, float4* __restrict__ leaf_hi,
                                     uint32_t* __restrict__ bounds /* [6] ordered: lo xyz, hi xyz */)
 {
@@ -116,7 +117,7 @@ __device__ __forceinline__ uint64_t spread21(uint32_t v)      // 21 bits -> ever
     return x;
 }
 
-__global__ void mesh_morton_kernel(const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+static __global__ void mesh_morton_kernel(const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                                    const uint32_t* __restrict__ bounds, int n, uint64_t* __restrict__ keys,
                                    uint32_t* __restrict__ vals)
 {
@@ -154,7 +155,7 @@ __device__ __forceinline__ float box_area(float4 lo, float4 hi)
 }
 
 // leaves of the binary tree, in Morton order, boxes padded for the float slab test
-__global__ void bin_leaves_kernel(const uint32_t* __restrict__ sorted_tri, const float4* __restrict__ leaf_lo,
+static __global__ void bin_leaves_kernel(const uint32_t* __restrict__ sorted_tri, const float4* __restrict__ leaf_lo,
                                   const float4* __restrict__ leaf_hi, const uint32_t* __restrict__ bounds, int n,
                                   BinTree t)
 {
@@ -178,7 +179,7 @@ __device__ __forceinline__ int lbvh_delta(const uint64_t* __restrict__ keys, int
     return a == b ? 64 + __clz(uint32_t(i) ^ uint32_t(j)) : __clzll((long long)(a ^ b));
 }
 
-__global__ void lbvh_hierarchy_kernel(const uint64_t* __restrict__ keys, int n, int2* __restrict__ children,
+static __global__ void lbvh_hierarchy_kernel(const uint64_t* __restrict__ keys, int n, int2* __restrict__ children,
                                       int* __restrict__ parent /* [2n-1] by node id */)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,7 +209,7 @@ __global__ void lbvh_hierarchy_kernel(const uint64_t* __restrict__ keys, int n, 
 }
 
 // one thread per leaf climbs; the second arrival at a node owns it
-__global__ void lbvh_refit_kernel(int n, const int* __restrict__ parent, int* __restrict__ arrivals, BinTree t)
+static __global__ void lbvh_refit_kernel(int n, const int* __restrict__ parent, int* __restrict__ arrivals, BinTree t)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -232,7 +233,7 @@ __global__ void lbvh_refit_kernel(int n, const int* __restrict__ parent, int* __
 // ---- PLOC -------------------------------------------------------------------
 // clusters[i] = node id of the i-th live cluster, in Morton order.
 // nearest[i] = the j in [i - R, i + R] \ {i} minimising area(box_i U box_j); ties -> smaller j.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 ploc_nearest_kernel(const int* __restrict__ clusters, int m, BinTree t, int* __restrict__ nearest)
 {
     constexpr int R = kPlocRadius, T = 256;
@@ -261,7 +262,7 @@ ploc_nearest_kernel(const int* __restrict__ clusters, int m, BinTree t, int* __r
 
 // flags[i]: low 32 bits = 1 if cluster i survives (alone or as the merged pair's
 // left member), high 32 bits = 1 if i leads a merge (allocates a node)
-__global__ void ploc_flag_kernel(const int* __restrict__ nearest, int m, uint64_t* __restrict__ flags)
+static __global__ void ploc_flag_kernel(const int* __restrict__ nearest, int m, uint64_t* __restrict__ flags)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
@@ -273,7 +274,7 @@ __global__ void ploc_flag_kernel(const int* __restrict__ nearest, int m, uint64_
 }
 
 // scan[i] = exclusive prefix sums of flags; merged leaders create node n + first_node + (#leaders before i)
-__global__ void ploc_merge_kernel(const int* __restrict__ clusters, const int* __restrict__ nearest,
+static __global__ void ploc_merge_kernel(const int* __restrict__ clusters, const int* __restrict__ nearest,
                                   const uint64_t* __restrict__ flags, const uint64_t* __restrict__ scan, int m, int n,
                                   int first_node, BinTree t, int* __restrict__ out)
 {
@@ -302,7 +303,7 @@ struct CollapseCounters { int nodes, tris, next; int pad; };
 __device__ __forceinline__ int bin_count(const BinTree& t, int id) { return __float_as_int(t.lo[id].w); }
 
 // One thread per (binary node -> wide node slot) task of this level.
-__global__ void collapse_kernel(const int2* __restrict__ tasks, int n_tasks, int n, BinTree t,
+static __global__ void collapse_kernel(const int2* __restrict__ tasks, int n_tasks, int n, BinTree t,
                                 const uint32_t* __restrict__ sorted_tri, float4* __restrict__ nodes,
                                 int32_t* __restrict__ leaf_order, CollapseCounters* __restrict__ cnt,
                                 int2* __restrict__ next_tasks)
@@ -366,7 +367,7 @@ __global__ void collapse_kernel(const int2* __restrict__ tasks, int n_tasks, int
 }
 
 // leaf-ordered float triangles: (v0.xyz, e1.x) (e1.yz, e2.xy) (e2.z, max|e1|, max|e2|, original index)
-__global__ void leaf_triangles_kernel(const int32_t* __restrict__ leaf_order, const double* __restrict__ tri64, int n,
+static __global__ void leaf_triangles_kernel(const int32_t* __restrict__ leaf_order, const double* __restrict__ tri64, int n,
                                       float4* __restrict__ tri32)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,6 +384,8 @@ __global__ void leaf_triangles_kernel(const int32_t* __restrict__ leaf_order, co
     tri32[(size_t)s * kTri32Stride + 2] = make_float4(f[8], c1, c2, __int_as_float(tri));
     tri32[(size_t)s * kTri32Stride + 3] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
+
+#endif  // DRTB_BVH_BUILD_KERNELS
 
 // ---------------------------------------------------------------------------
 // ray-triangle and traversal

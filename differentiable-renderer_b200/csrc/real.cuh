@@ -8,6 +8,7 @@
 //                 cos(2 pi u) via sincospi) -- all ~1e-15 relative.
 //   Real<float> : the throughput instantiation (MUFU-based rcp/rsqrt/sqrt).
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -24,7 +25,8 @@ struct ConstF64 {
     double half_pi, pi, inv_pi, inv_m, m, origin_eps;
     double tab_s[3], tab_c[2], tab_step;         // sincos_tab: -1/7!, 1/5!, -1/3! ; -1/6!, 1/4! ; 2 pi / M
 };
-__constant__ ConstF64 kC64 = {
+// (static: every translation unit of the library carries its own copy -- no relocatable device code)
+static __constant__ ConstF64 kC64 = {
     {2.8114572543455206e-15, -7.6471637318198164e-13, 1.6059043836821613e-10, -2.5052108385441720e-08,
      2.7557319223985893e-06, -1.9841269841269841e-04, 8.3333333333333332e-03, -1.6666666666666666e-01},
     {-1.5619206968586225e-16, 4.7794773323873853e-14, -1.1470745597729725e-11, 2.0876756987868100e-09,
@@ -43,7 +45,18 @@ __constant__ ConstF64 kC64 = {
 // shared memory per block (BlockScene).
 constexpr int kSinCosShift = 23;
 constexpr int kSinCosEntries = (1 << (31 - kSinCosShift)) + 1;      // 257 (index 256: k + 2^22 carries)
-__device__ double2 g_sincos_tab[kSinCosEntries];
+static __device__ double2 g_sincos_tab[kSinCosEntries];
+// Fills THIS translation unit's copy of the table: (sin, cos)(2 pi i 2^23 / M) in long double on the host.
+static inline cudaError_t upload_sincos_tab()
+{
+    static double2 tab[kSinCosEntries];
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int i = 0; i < kSinCosEntries; ++i) {
+        const long double ang = two_pi * ((long double)i * (long double)(1u << kSinCosShift)) / 2147483647.0L;
+        tab[i] = make_double2(double(sinl(ang)), double(cosl(ang)));
+    }
+    return cudaMemcpyToSymbol(g_sincos_tab, tab, sizeof(tab));
+}
 template <typename R> struct SinCosTab { };                          // float: sincospif
 template <> struct SinCosTab<double> { double2 t[kSinCosEntries]; };
 

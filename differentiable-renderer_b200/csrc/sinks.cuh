@@ -1,0 +1,70 @@
+// sinks.cuh — where the adjoint's contributions go: the gradient sinks of the render, wavefront and
+// explicit-ray kernels (what VariableNode::backward's `m_grad += g` is upstream, vector.hpp:185-188).
+#pragma once
+#include "path.cuh"
+
+namespace drtb {
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Gradient sinks ------------------------------------------------------------
+// Small parameter sets (the Cornell box has 4): every thread owns one column of
+// a [n_params*3][kBlock] shared array -- no atomics, no bank conflicts, and a
+// fixed summation order, so gradients are bit-reproducible run to run.
+struct SmemSink {
+    double* col;                                   // &acc[threadIdx.x]
+    template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
+    {
+        col[(3 * p + c) * kBlock] += double(v);
+    }
+};
+// Medium parameter sets (9 .. kMaxParams, analytic scenes): the columns no longer fit per
+// thread, so `cols` (a power of two, chosen by the launcher to fit shared memory) columns are
+// shared by the threads with equal (threadIdx.x mod cols) and updated with shared-memory
+// atomics (a CAS loop, ATOMS.CAST.SPIN.64).  Contention stays inside the block and is spread
+// over P3 x cols words; the block reduction and reduce_grad_kernel are the small-set ones.
+// (Global atomics here cost 8x the whole render at 9 parameters: every lit path of the grid
+// hammers the same 27 words.)
+struct SmemAtomicSink {
+    double* col;                                   // &acc[threadIdx.x & (cols - 1)]
+    int cols;
+    template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
+    {
+        atomicAdd(col + (3 * p + c) * cols, double(v));
+    }
+};
+// Large parameter sets (mesh scenes, per-triangle albedos): one red.global.add.f64 per contribution.
+struct AtomicSink {
+    double* grad;
+    template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
+    {
+        atomicAdd(grad + 3 * p + c, double(v));
+    }
+};
+// Gradient image (drtb_render_grad_image): parameter kp's contributions are
+// additionally summed into the lane's per-pixel accumulator g[3].
+template <typename Inner>
+struct PixelSink {
+    Inner inner;
+    int kp;
+    double* g;
+    template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
+    {
+        inner.add(p, c, v);
+        if (p == kp) g[c] += double(v);
+    }
+};
+struct JacSink {
+    double* row;                                   // this ray's n_params x 3 block
+    template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
+    {
+        row[3 * p + c] += double(v);
+    }
+};
+
+} // namespace drtb

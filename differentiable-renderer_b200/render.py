@@ -91,11 +91,9 @@ class Context:
         if seed_img is not None:
             seed_img = np.ascontiguousarray(seed_img, dtype=np.float64)
             assert seed_img.shape == (rows, cam.width, 3)
-        st = abi.Stats()
-        if stats:
-            opts.flags |= abi.FLAG_STATS
+        st = abi.Stats() if stats else None     # drtb_render turns the statistics on when it gets a drtb_stats
         self._check(self._lib.drtb_render(self._h, C.byref(opts), _ptr(seed_img), _ptr(img),
-                                          _ptr(grad), C.byref(st)))
+                                          _ptr(grad), C.byref(st) if stats else None))
         return (img, grad, st) if stats else (img, grad)
 
     def render_grad_image(self, opts: abi.RenderOpts, param, seed_img: Optional[np.ndarray] = None):
@@ -123,6 +121,10 @@ class Context:
             self._h, C.byref(opts), C.cast(seed_ptr, _dp) if seed_ptr else None,
             C.cast(img_ptr, _dp) if img_ptr else None, C.cast(grad_ptr, _dp) if grad_ptr else None,
             C.byref(st) if st is not None else None))
+
+    def reserve(self, opts: abi.RenderOpts):
+        """drtb_reserve: size scratch and load kernels for renders with these options."""
+        self._check(self._lib.drtb_reserve(self._h, C.byref(opts)))
 
     # -- hot path, device buffers ------------------------------------------------
     def render_device(self, opts: abi.RenderOpts, d_seed_img: int, d_img: int, d_grad: int,

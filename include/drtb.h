@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DRTB_ABI_VERSION 2
+#define DRTB_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------- */
 #define DRTB_OK                 0
@@ -190,8 +190,10 @@ int drtb_scene_upload(drtb_ctx* ctx, const drtb_scene* scene);
 
 /* Attach a triangle mesh to the uploaded scene (call after drtb_scene_upload;
  * parameter indices refer to that scene's params[]).  Copies the mesh, builds
- * an LBVH on the GPU (Morton codes -> radix sort -> Karras hierarchy ->
- * bottom-up refit).  mesh == NULL or n_triangles == 0 detaches the mesh.
+ * the BVH on the GPU: Morton codes -> radix sort -> binary tree by PLOC
+ * (parallel locally-ordered clustering; DRTB_BVH=lbvh selects Karras' radix
+ * tree + bottom-up refit instead) -> collapse to a 4-wide BVH with <= 4
+ * triangles per leaf.  mesh == NULL or n_triangles == 0 detaches the mesh.
  * A later drtb_scene_upload detaches it as well. */
 int drtb_mesh_upload(drtb_ctx* ctx, const drtb_mesh* mesh);
 
@@ -234,10 +236,27 @@ int drtb_render(drtb_ctx* ctx, const drtb_render_opts* opts,
 /* Same, DEVICE buffers on ctx's device, enqueued on `stream` (a cudaStream_t
  * passed as void*; NULL = the legacy default stream).  Asynchronous: returns
  * after the launches; the caller synchronises the stream.  d_stats is NULL or
- * a device drtb_stats (kernel_ms is not filled). */
+ * a device drtb_stats, of which the kernels fill segments, lit_paths,
+ * truncated_paths, bvh_nodes and tri_tests (paths, retraced_paths and
+ * kernel_ms are host-side figures that only drtb_render fills).
+ * ONE STREAM AT A TIME PER CONTEXT: every render of a ctx shares the ctx's
+ * scratch (task counter, gradient partials, lit-path rings, wavefront
+ * buffers), so two renders of the same ctx must not be in flight on different
+ * streams at once -- enqueue them on one stream, or order the streams with an
+ * event.  drtb_render / drtb_set_params run on the ctx's own private stream
+ * and block until done, so they are always ordered with each other; mixing
+ * them with *_device calls still in flight on another stream is the caller's
+ * to order (synchronise that stream first). */
 int drtb_render_device(drtb_ctx* ctx, const drtb_render_opts* opts,
                        const double* d_seed_img, double* d_img, double* d_grad,
                        drtb_stats* d_stats, void* stream);
+
+/* Size every scratch buffer a render with these options needs, set the kernel
+ * attributes and load the kernels it will launch, so that the first
+ * drtb_render_device with them is as fast as the second (drtb_render does the
+ * same by itself before it starts the timer behind drtb_stats.kernel_ms).
+ * Optional; blocking. */
+int drtb_reserve(drtb_ctx* ctx, const drtb_render_opts* opts);
 
 /* ---- multi-GPU: the image all-gather fused into the render ----------------
  * The reference renders in one process (src/render.cpp:72-86 fills one img[]).
@@ -252,7 +271,12 @@ int drtb_render_device(drtb_ctx* ctx, const drtb_render_opts* opts,
  * DRTB_FLAG_IMAGE renders (analytic scenes) fill the peers' images and d_img
  * may be NULL.  The stores are complete when the kernel is; a rank may read
  * its full image once every rank's render has finished (the gradient
- * all-reduce that follows the render on each rank's stream orders that). */
+ * all-reduce that follows the render on each rank's stream orders that).
+ * The opposite hazard is the caller's as well: a rank's NEXT peer-filling
+ * render stores straight into the other ranks' full images, so a cross-rank
+ * barrier or collective must separate every rank's last read of its full
+ * image from the next such render on any rank (or the caller double-buffers
+ * the full images and alternates drtb_set_image_peers). */
 int drtb_set_image_peers(drtb_ctx* ctx, double* const* full_images, int32_t n);
 
 /* Device memory that another process on the same box can map (CUDA IPC, one

@@ -145,3 +145,38 @@ def test_exact_ties_keep_the_lower_scene_index(drt, ctx, order, precision):
     assert np.array_equal(ref_img, np.broadcast_to(colour, ref_img.shape))       # the oracle keeps scene-order shape 0
     assert np.array_equal(img, ref_img)
     assert np.array_equal(grad, ref_grad)
+
+
+@pytest.mark.parametrize("mesh", [False, True])
+def test_shard_that_owns_no_rows_reports_zeros(drt, ctx, mesh):
+    """More shards than bands (H = 32, bands of 8 rows, 8 shards): shards 4..7 own nothing.  Their gradients
+    must be OVERWRITTEN with zeros (drtb.h), not left stale, and a mesh scene must not divide by zero
+    (drtb.cu reduce_partials / launch_wavefront)."""
+    scene = drt.tessellated_room(2, 4, width=16, height=32) if mesh else drt.cornell_box(16, 32)
+    ctx.upload(scene)
+    whole_img, whole_grad = ctx.render(drt.make_opts(4, 2, 0.5))           # leaves non-zero gradients behind
+    assert np.abs(whole_grad).max() > 0
+    total = np.zeros_like(whole_grad)
+    for s in range(8):
+        o = drt.make_opts(4, 2, 0.5, shard_index=s, shard_count=8, band_rows=8)
+        img, grad, st = ctx.render(o, stats=True)
+        if s >= 4:
+            assert img.shape[0] == 0 and st.segments == 0 and st.lit_paths == 0 and st.paths == 0
+            assert np.array_equal(grad, np.zeros_like(grad))
+        else:
+            assert np.array_equal(img, whole_img[8 * s:8 * s + 8])
+        total += grad
+    assert np.abs(total - whole_grad).max() <= 1e-12 * np.abs(whole_grad).max()
+
+
+def test_reserve_makes_the_first_render_as_fast_as_the_second(drt, ctx):
+    """drtb_reserve / the preparation pass inside drtb_render: no allocation, attribute call or first-use
+    kernel load lands between the events behind drtb_stats.kernel_ms."""
+    with drt.Context(0) as fresh:
+        fresh.upload(drt.cornell_box(96, 64))
+        times = {}
+        for spp, mb, ab in ((8, 8, 1.0), (8, 1, 0.5), (32, 8, 1.0), (32, 1, 0.5), (40, 16, 1.0)):
+            first = fresh.render(drt.make_opts(spp, mb, ab), stats=True)[2].kernel_ms
+            second = fresh.render(drt.make_opts(spp, mb, ab), stats=True)[2].kernel_ms
+            times[(spp, mb, ab)] = (first, second)
+            assert first <= 3.0 * second + 0.25, times
