@@ -139,14 +139,18 @@ def test_bvh_equals_linear_scan_on_65536_rays_at_1m_triangles(drt, ctx, million)
 
 
 def test_million_triangle_independent_seeds_agree_within_three_sigma(drt, ctx, million):
+    """Independent streams on the 1 M-triangle scene: 8 x 8 pixel block means (2 048 samples each, close to
+    Gaussian; single pixels at 32 spp are dominated by rare bright paths) agree within 3 sigma, sigma estimated
+    from eight further independent renders."""
     ctx.upload(million)
     spp, mb = 32, 4
-    runs = [ctx.render(drt.make_opts(spp, mb, 1.0, seed=s)) for s in range(1, 9)]
+    runs = [ctx.render(drt.make_opts(spp, mb, 1.0, seed=s)) for s in range(1, 11)]
     imgs = np.stack([r[0] for r in runs])
-    a, b = imgs[0], imgs[1]
-    var = imgs[2:].var(axis=0, ddof=1)
+    blocks = imgs.reshape(len(runs), 16, 8, 16, 8, 3).mean(axis=(2, 4))
+    a, b = blocks[0], blocks[1]
+    var = blocks[2:].var(axis=0, ddof=1)
     ok = np.abs(a - b) <= 3.0 * np.sqrt(2.0 * var) + 1e-12
-    assert ok.mean() >= 0.95
+    assert ok.mean() >= 0.95, ok.mean()
     m = imgs.reshape(len(runs), -1, 3).mean(1)
     assert (np.abs(m[0] - m[1:].mean(0)) <= 4.0 * m[1:].std(0, ddof=1) + 1e-5).all()
     # total per-triangle gradient mass (sum over triangles) agrees across seeds
