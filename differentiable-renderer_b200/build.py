@@ -36,6 +36,8 @@ NVCC_FLAGS = [
     "-DDRTB_MIN_BLOCKS_F32=7",
     # mesh kernels are latency bound (BVH node fetches): more resident warps beat more registers
     "-DDRTB_MESH_MIN_BLOCKS=6",
+    # the wavefront traversal: 7 resident blocks (72 registers) over 6: +1.5 % (profiles/README.md, round 2)
+    "-DDRTB_WF_MIN_BLOCKS=7",
 ]
 
 

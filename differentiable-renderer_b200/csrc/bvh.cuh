@@ -16,14 +16,23 @@
 //              agglomerative build whose SAH cost is far below LBVH's; or
 //        LBVH  (Karras 2012): binary radix tree over the codes + bottom-up refit
 //              (kept as the fast-build option, DRTB_BVH=lbvh)
-//   3. collapse to a 4-wide BVH, top-down and level-synchronous: a wide node
-//      adopts the grandchildren with the largest surface area first; subtrees
-//      of <= kLeafMax triangles become leaves and their triangles are stored
-//      contiguously in leaf order.
-// Wide node = 128 B (one cache line): the 4 child boxes as SoA float4 rows
-// (lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4]) + 4 child links.  Boxes
-// are float, rounded outward and padded, and the slab test is conservative, so
-// float culling can never reject a triangle the exact test would accept.
+//   3. collapse to an 8-wide COMPRESSED BVH (after Ylitie, Karras, Laine 2017, "Efficient
+//      incoherent ray traversal on GPUs through compressed wide BVHs"), top-down and
+//      level-synchronous: a wide node adopts the descendants with the largest surface
+//      area first until it has 8 children; subtrees of <= kLeafMax triangles become
+//      leaves.  A node's internal children are stored contiguously (child base + rank in
+//      the internal mask) and so are the triangles of its leaf children, in leaf order.
+// Wide node = 128 B (one cache line): the node's box origin (3 floats), a power-of-two scale
+// per axis (3 exponent bytes), the internal-child mask, two base indices, 8 meta bytes and
+// the 8 child boxes quantised to 15 bits per plane relative to the origin (the paper's 8-bit
+// planes make an 80-byte node; a 16-bit field drops into a float's mantissa with ONE byte
+// permute, so a plane costs PRMT + FFMA instead of PRMT + FADD + FFMA, and an aligned
+// 128-byte node touches no more 32-byte sectors than an unaligned 80-byte one).
+// Quantisation rounds outward, the leaf boxes are padded and the slab test is widened, so
+// float culling can never reject a triangle the exact test would accept.  Against the
+// 4-wide float nodes of round 1: 8 children per 128 B instead of 4, no sorting network, and
+// at most ONE 8-byte stack entry per visited node (a child GROUP: base, hit mask, and a
+// lower bound on the entry distance of what is left in it) instead of up to three.
 #pragma once
 #include <cfloat>
 #include <cstdint>
@@ -35,17 +44,16 @@ namespace drtb {
 
 constexpr int kBvhStack   = 64;           // traversal stack entries per lane (overflow falls back to a linear scan)
 #ifndef DRTB_LEAF_MAX
-#define DRTB_LEAF_MAX 4
+#define DRTB_LEAF_MAX 3
 #endif
-constexpr int kLeafMax    = DRTB_LEAF_MAX; // triangles per leaf, <= 4 (2 bits of the leaf link)
+constexpr int kLeafMax    = DRTB_LEAF_MAX; // triangles per leaf, <= 3 (3 unary bits of the child's meta byte)
 constexpr int kPlocRadius = 16;           // PLOC neighbour search radius along the Morton order
 constexpr int kTri64Stride = 10;          // doubles per triangle: v0, e1, e2, pad (16-byte aligned rows)
 constexpr int kTri32Stride = 4;           // float4 per triangle (64 B: two 256-bit loads)
-constexpr int kNodeStride  = 8;           // float4 per wide node
-constexpr int kEmptyLink   = 0x7fffffff;
+constexpr int kNodeStride  = 8;           // 16-byte words per wide node (128 B)
 
 struct MeshView {
-    const float4*  nodes;                 // kNodeStride float4 per wide node; node 0 is the root
+    const float4*  nodes;                 // kNodeStride 16-byte words per wide node (raw bits); node 0 is the root
     const double*  tri64;                 // ORIGINAL order: v0.xyz e1.xyz e2.xyz pad
     const float4*  tri32;                 // LEAF order: (v0.xyz,e1.x) (e1.yz,e2.xy) (e2.z, max|e1|, max|e2|, original index)
     const int32_t* color;                 // per triangle (original order): param index of the albedo, -1 = null BxDF
@@ -297,26 +305,38 @@ static __global__ void ploc_merge_kernel(const int* __restrict__ clusters, const
     out[pos] = id;
 }
 
-// ---- collapse to the 4-wide BVH ----------------------------------------------
+// ---- collapse to the 8-wide compressed BVH ------------------------------------
 struct CollapseCounters { int nodes, tris, next; int pad; };
 
 __device__ __forceinline__ int bin_count(const BinTree& t, int id) { return __float_as_int(t.lo[id].w); }
 
-// One thread per (binary node -> wide node slot) task of this level.
-static __global__ void collapse_kernel(const int2* __restrict__ tasks, int n_tasks, int n, BinTree t,
-                                const uint32_t* __restrict__ sorted_tri, float4* __restrict__ nodes,
-                                int32_t* __restrict__ leaf_order, CollapseCounters* __restrict__ cnt,
-                                int2* __restrict__ next_tasks)
+// Node layout (8 x 16 bytes):
+//   w0 = origin.x, origin.y, origin.z (float bits), ex | ey << 8 | ez << 16 | imask << 24
+//   w1 = child base, triangle base, meta[0..3], meta[4..7]
+//   w2 = qlo.x[0..7]   w3 = qlo.y[0..7]   w4 = qlo.z[0..7]      (8 x 16 bits each, child s in half-word s)
+//   w5 = qhi.x[0..7]   w6 = qhi.y[0..7]   w7 = qhi.z[0..7]
+// child box plane = origin + q * 2^(e - 127 - 8), q in [0, 32767]; the exponent byte is stored with the + 8
+// the traversal's mantissa trick needs (see node8_step).  imask bit s = slot s holds an internal child, stored at
+// node index child base + popc(imask & ((1 << s) - 1)); meta[s] = 0 (empty), 1 << 5 | (24 + s) (internal) or
+// unary(n_tris) << 5 | offset (leaf whose triangles sit at triangle base + offset, leaf order).
+// Children are assigned to slots so that slot bit a says on which side of the node's centre (axis a) the child
+// lies; a ray then visits the slots of a popped group in the order of (slot ^ its direction octant), near side
+// first, without sorting anything.
+// One thread per (binary node -> wide node index) task of this level.
+static __global__ void collapse8_kernel(const int2* __restrict__ tasks, int n_tasks, int n, BinTree t,
+                                        const uint32_t* __restrict__ sorted_tri, uint4* __restrict__ nodes,
+                                        int32_t* __restrict__ leaf_order, CollapseCounters* __restrict__ cnt,
+                                        int2* __restrict__ next_tasks)
 {
     const int ti = blockIdx.x * blockDim.x + threadIdx.x;
     if (ti >= n_tasks) return;
-    const int b = tasks[ti].x, slot = tasks[ti].y;
-    int cand[4]; int nc;
+    const int b = tasks[ti].x, self = tasks[ti].y;
+    int cand[8]; int nc;
     if (b < n || bin_count(t, b) <= kLeafMax) { cand[0] = b; nc = 1; }        // tiny mesh: the root is a leaf
     else {
         const int2 ch = t.children[b - n];
         cand[0] = ch.x; cand[1] = ch.y; nc = 2;
-        while (nc < 4) {                                  // open the largest child that is not a leaf yet
+        while (nc < 8) {                                  // open the largest child that is not a leaf yet
             int pick = -1; float pa = -1.f;
             for (int k = 0; k < nc; ++k) {
                 const int id = cand[k];
@@ -329,41 +349,86 @@ static __global__ void collapse_kernel(const int2* __restrict__ tasks, int n_tas
             cand[pick] = c2.x; cand[nc++] = c2.y;
         }
     }
-    float lo[3][4], hi[3][4]; int link[4];
-    for (int k = 0; k < 4; ++k) {
-        if (k >= nc) {
-            // NaN planes: every slab compare fails, the empty slot can never be entered
-            for (int a = 0; a < 3; ++a) { lo[a][k] = __int_as_float(0x7fc00000); hi[a][k] = __int_as_float(0x7fc00000); }
-            link[k] = kEmptyLink;
-            continue;
+    // quantisation frame of this node
+    const float4 nlo = t.lo[b], nhi = t.hi[b];
+    const float org[3] = {nlo.x, nlo.y, nlo.z}, top[3] = {nhi.x, nhi.y, nhi.z};
+    int ebits[3]; double inv_scale[3];
+    for (int a = 0; a < 3; ++a) {
+        const float ext = top[a] - org[a];
+        int e = ext > 0.f ? ilogbf(ext * (1.0f / 32767.0f)) + 1 : -126;     // 2^e > ext / 32767
+        e = max(-126, min(110, e));
+        ebits[a] = e + 127 + 8;                           // stored with the + 8 of node8_step's a' = 256 * 2^e / d
+        inv_scale[a] = exp2(double(-e));
+    }
+    // slot assignment: greedy on cost(child, slot) = sum_a (slot bit a ? + : -) (child centre - node centre)_a
+    float cv[8][3];
+    for (int k = 0; k < nc; ++k) {
+        const float4 l = t.lo[cand[k]], h = t.hi[cand[k]];
+        cv[k][0] = (l.x + h.x) - (nlo.x + nhi.x); cv[k][1] = (l.y + h.y) - (nlo.y + nhi.y); cv[k][2] = (l.z + h.z) - (nlo.z + nhi.z);
+    }
+    int slot_of[8], child_in[8];
+    for (int k = 0; k < 8; ++k) { slot_of[k] = -1; child_in[k] = -1; }
+    for (int round = 0; round < nc; ++round) {
+        float bestc = -FLT_MAX; int bk = -1, bs = -1;
+        for (int k = 0; k < nc; ++k) {
+            if (slot_of[k] >= 0) continue;
+            for (int sl = 0; sl < 8; ++sl) {
+                if (child_in[sl] >= 0) continue;
+                const float c = ((sl & 1) ? cv[k][0] : -cv[k][0]) + ((sl & 2) ? cv[k][1] : -cv[k][1]) + ((sl & 4) ? cv[k][2] : -cv[k][2]);
+                if (c > bestc) { bestc = c; bk = k; bs = sl; }
+            }
         }
-        const int id = cand[k];
+        slot_of[bk] = bs; child_in[bs] = bk;
+    }
+    // allocation: internal children contiguous, triangles of the leaf children contiguous
+    int n_int = 0, n_tri = 0;
+    for (int sl = 0; sl < 8; ++sl) {
+        if (child_in[sl] < 0) continue;
+        const int c = bin_count(t, cand[child_in[sl]]);
+        if (c <= kLeafMax) n_tri += c; else ++n_int;
+    }
+    const int child_base = n_int ? atomicAdd(&cnt->nodes, n_int) : 0;
+    const int task_base = n_int ? atomicAdd(&cnt->next, n_int) : 0;
+    const int tri_base = n_tri ? atomicAdd(&cnt->tris, n_tri) : 0;
+    uint32_t imask = 0, meta[2] = {0u, 0u}, q[6][4] = {};
+    int ri = 0, off = 0;
+    for (int sl = 0; sl < 8; ++sl) {
+        if (child_in[sl] < 0) continue;
+        const int id = cand[child_in[sl]];
         const float4 l = t.lo[id], h = t.hi[id];
-        lo[0][k] = l.x; lo[1][k] = l.y; lo[2][k] = l.z; hi[0][k] = h.x; hi[1][k] = h.y; hi[2][k] = h.z;
+        const float cl[3] = {l.x, l.y, l.z}, chh[3] = {h.x, h.y, h.z};
+        for (int a = 0; a < 3; ++a) {
+            const int lo_q = max(0, min(32767, int(floor((double(cl[a]) - double(org[a])) * inv_scale[a]))));
+            const int hi_q = max(0, min(32767, int(ceil((double(chh[a]) - double(org[a])) * inv_scale[a]))));
+            q[a][sl >> 1] |= uint32_t(lo_q) << (16 * (sl & 1));
+            q[3 + a][sl >> 1] |= uint32_t(hi_q) << (16 * (sl & 1));
+        }
         const int c = __float_as_int(l.w);
-        if (c <= kLeafMax) {                              // leaf: triangles stored contiguously in leaf order
-            const int first = atomicAdd(&cnt->tris, c);
+        uint32_t mb;
+        if (c <= kLeafMax) {                              // leaf: its triangles at tri_base + off, in leaf order
             int st[kLeafMax], sp = 0, w = 0;
             st[sp++] = id;
             while (sp > 0) {
                 const int x = st[--sp];
-                if (x < n) leaf_order[first + w++] = int32_t(sorted_tri[x]);
+                if (x < n) leaf_order[tri_base + off + w++] = int32_t(sorted_tri[x]);
                 else { const int2 c2 = t.children[x - n]; st[sp++] = c2.y; st[sp++] = c2.x; }
             }
-            link[k] = ~((first << 2) | (c - 1));
+            mb = (((1u << c) - 1u) << 5) | uint32_t(off);
+            off += c;
         } else {
-            const int s = atomicAdd(&cnt->nodes, 1);
-            next_tasks[atomicAdd(&cnt->next, 1)] = make_int2(id, s);
-            link[k] = s;
+            imask |= 1u << sl;
+            next_tasks[task_base + ri] = make_int2(id, child_base + ri);
+            ++ri;
+            mb = (1u << 5) | uint32_t(24 + sl);
         }
+        meta[sl >> 2] |= mb << (8 * (sl & 3));
     }
-    float4* out = nodes + (size_t)slot * kNodeStride;
-    for (int a = 0; a < 3; ++a) {
-        out[a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
-        out[3 + a] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
-    }
-    out[6] = make_float4(__int_as_float(link[0]), __int_as_float(link[1]), __int_as_float(link[2]), __int_as_float(link[3]));
-    out[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4* out = nodes + (size_t)self * kNodeStride;
+    out[0] = make_uint4(__float_as_uint(org[0]), __float_as_uint(org[1]), __float_as_uint(org[2]),
+                        uint32_t(ebits[0]) | uint32_t(ebits[1]) << 8 | uint32_t(ebits[2]) << 16 | imask << 24);
+    out[1] = make_uint4(uint32_t(child_base), uint32_t(tri_base), meta[0], meta[1]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) out[2 + k] = make_uint4(q[k][0], q[k][1], q[k][2], q[k][3]);
 }
 
 // leaf-ordered float triangles: (v0.xyz, e1.x) (e1.yz, e2.xy) (e2.z, max|e1|, max|e2|, original index)
@@ -439,6 +504,7 @@ struct RayF {
     float ox, oy, oz, dx, dy, dz;
     float ix, iy, iz, oix, oiy, oiz;      // 1/d and o/d for the slab test  t = plane * (1/d) - o/d
     float om, dm;                         // max-norms of o and d (error bound of the float cull)
+    uint32_t octinv4;                     // (7 - direction octant) in every byte: slot visiting order of the wide nodes
 };
 
 template <typename R>
@@ -455,6 +521,9 @@ __device__ __forceinline__ RayF make_rayf(V3<R> o, V3<R> d)
     r.oix = r.ox * r.ix; r.oiy = r.oy * r.iy; r.oiz = r.oz * r.iz;
     r.om = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
     r.dm = fmaxf(fabsf(r.dx), fmaxf(fabsf(r.dy), fabsf(r.dz)));
+    // near slot = the child octant the ray enters first: bit a set where d_a < 0 (it comes from the high side)
+    const uint32_t near_slot = (r.ix < 0.f ? 1u : 0u) | (r.iy < 0.f ? 2u : 0u) | (r.iz < 0.f ? 4u : 0u);
+    r.octinv4 = (near_slot ^ 7u) * 0x01010101u;
     return r;
 }
 
@@ -521,130 +590,189 @@ __device__ __forceinline__ void brute_closest(const MeshView& m, V3<R> o, V3<R> 
     for (int i = 0; i < m.n_tris; ++i) { ++n_tests; tri_test_exact<R>(load_tri<R>(m, i), i, o, d, tmin, best); }
 }
 
-// sort key of a slab hit: entry distance (non-negative float, so its bits order
-// like an int) with the child slot in the two low mantissa bits; clearing them
-// only lowers the distance, which keeps the pop-time cull conservative
-__device__ __forceinline__ int hit_key(float tn, float tf, float tmax, int j)
-{
-    return (tn <= tf && tn <= tmax) ? ((__float_as_int(tn) & ~3) | j) : 0x7fffffff;
-}
-__device__ __forceinline__ void cswap(int& a, int& b) { const int lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
-__device__ __forceinline__ int pick_link(float4 lk, int j)
-{
-    const float a = (j & 1) ? lk.y : lk.x, b = (j & 1) ? lk.w : lk.z;
-    return __float_as_int((j & 2) ? b : a);
-}
-
-// Traversal stacks.  Entries are (sort key, link).  LocalStack lives in local memory:
-// lanes sit at different depths, so one push touches up to 32 different cache lines.
-// SmemStack keeps the first kSmemStack entries in shared memory as [entry][thread]
-// (every lane owns a bank column: conflict-free whatever its depth) and spills deeper
+// Traversal stacks.  An entry is a child GROUP of one visited node: (child base, hit mask << 24 | internal mask),
+// the siblings still to be visited.  LocalStack lives in local memory: lanes sit at different depths, so one
+// push touches up to 32 different cache lines.  SmemStack keeps the first kSmemStack entries in shared memory
+// as [entry][thread] (every lane owns a bank column: conflict-free whatever its depth) and spills deeper
 // entries to local memory.
 struct LocalStack {
-    int2 e[kBvhStack];
-    __device__ __forceinline__ void put(int i, int2 v, bool pred) { if (pred) e[i] = v; }
-    __device__ __forceinline__ int2 get(int i) const { return e[i]; }
+    uint2 e[kBvhStack];
+    __device__ __forceinline__ void put(int i, uint2 v, bool pred) { if (pred) e[i] = v; }
+    __device__ __forceinline__ uint2 get(int i) const { return e[i]; }
 };
 #ifndef DRTB_SMEM_STACK
-#define DRTB_SMEM_STACK 16
+#define DRTB_SMEM_STACK 12
 #endif
 constexpr int kSmemStack = DRTB_SMEM_STACK;
 template <int THREADS>
 struct SmemStack {
-    int2* col;                                   // &s_stack[0][threadIdx.x]; row kSmemStack is a write-only dummy
-    int2 spill[kBvhStack - kSmemStack];
+    uint2* col;                                  // &s_stack[0][threadIdx.x]; row kSmemStack is a write-only dummy
+    uint2 spill[kBvhStack - kSmemStack];
     // predicated push without a branch on the common path: a lane that does not push writes the dummy row
-    __device__ __forceinline__ void put(int i, int2 v, bool pred)
+    __device__ __forceinline__ void put(int i, uint2 v, bool pred)
     {
         if (pred && i >= kSmemStack) spill[i - kSmemStack] = v;
         else col[(pred ? i : kSmemStack) * THREADS] = v;
     }
-    __device__ __forceinline__ int2 get(int i) const { return i < kSmemStack ? col[i * THREADS] : spill[i - kSmemStack]; }
+    __device__ __forceinline__ uint2 get(int i) const { return i < kSmemStack ? col[i * THREADS] : spill[i - kSmemStack]; }
 };
 
-// One wide-node step of a lane: slab-test the 4 children, sort the hits by entry
-// distance, push the far ones (far first, so the nearest is popped first), descend
-// into the nearest.  Returns true when nothing was hit (the caller pops).
-template <typename Stack>
-__device__ __forceinline__ bool bvh_node_step(const MeshView& m, const RayF& r, float tmax, int& cur, Stack& stack, int& sp,
-                                              bool& overflow)
+// Half-word H (0 / 1) of w dropped into a float's mantissa: bits = 0x43 << 24 | q << 8, i.e. 128 + q / 256 for the
+// 15-bit q -- one PRMT, no conversion and no subtraction: the 128 is folded into the slab's offset (node8_step).
+// `k43` is 0x43000000 held in a REGISTER (node8_step makes it opaque to the compiler): PRMT takes one immediate, and
+// with the constant as the immediate the compiler re-materialised the selector before almost every one of the 48
+// permutes of a node (profiles/r02_wf_traverse_f64_cw3_summary.txt: 79 instructions per node on this line).
+template <int H> __device__ __forceinline__ float plane_to_float(uint32_t w, uint32_t k43)
 {
-    const float4* nd = m.nodes + (size_t)cur * kNodeStride;
-    float4 lx, ly, lz, hx, hy, hz;
-    ldg256(nd, lx, ly); ldg256(nd + 2, lz, hx); ldg256(nd + 4, hy, hz);
-    const float4 lk = __ldg(nd + 6);
-    int key[4];
-#define DRTB_SLAB(J, C)                                                                           \
-    {                                                                                             \
-        const float ax = fmaf(lx.C, r.ix, -r.oix), bx = fmaf(hx.C, r.ix, -r.oix);                 \
-        const float ay = fmaf(ly.C, r.iy, -r.oiy), by = fmaf(hy.C, r.iy, -r.oiy);                 \
-        const float az = fmaf(lz.C, r.iz, -r.oiz), bz = fmaf(hz.C, r.iz, -r.oiz);                 \
-        float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));                     \
-        float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));                     \
-        tn = fmaxf(tn - fabsf(tn) * 4e-7f, 0.0f);           /* conservative: widen by a few ulp */ \
-        tf += fabsf(tf) * 4e-7f;                                                                  \
-        key[J] = hit_key(tn, tf, tmax, J);                                                        \
-    }
-    DRTB_SLAB(0, x) DRTB_SLAB(1, y) DRTB_SLAB(2, z) DRTB_SLAB(3, w)
-#undef DRTB_SLAB
-    cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
-    // the stores are predicated, not branched
-#pragma unroll
-    for (int k = 3; k >= 1; --k) {
-        const bool hit = key[k] != 0x7fffffff;
-        stack.put(sp, make_int2(key[k], pick_link(lk, key[k] & 3)), hit && sp < kBvhStack);
-        overflow |= hit && sp >= kBvhStack;
-        sp += (hit && sp < kBvhStack) ? 1 : 0;
-    }
-    cur = pick_link(lk, key[0] & 3);
-    return key[0] == 0x7fffffff;
+    uint32_t f;
+    if (H) asm("prmt.b32 %0, %1, %2, 0x7324;" : "=r"(f) : "r"(w), "r"(k43));
+    else   asm("prmt.b32 %0, %1, %2, 0x7104;" : "=r"(f) : "r"(w), "r"(k43));
+    return __uint_as_float(f);
 }
 
-// Closest triangle along (o, d) that beats `tmin`; ordered traversal, nearest child first.
+// Slab test of child S of a wide node; ORs its hit bits into `hits` and keeps the two smallest entry
+// distances of the INTERNAL children hit as integer keys (distance bits, low 3 bits = slot).  Branch-free.
+//   wn*, wf* : the words holding child S's near / far plane per axis (swizzled by the ray's direction signs)
+//   an*, bn* : t_near = f an + bn ; af*, bf* : t_far = f af + bf      (f = plane_to_float, see node8_step)
+struct SlabCoef { float anx, any, anz, bnx, bny, bnz, afx, afy, afz, bfx, bfy, bfz; uint32_t k43; };
+template <int S>
+__device__ __forceinline__ void child_slab(uint32_t wnx, uint32_t wny, uint32_t wnz, uint32_t wfx, uint32_t wfy, uint32_t wfz,
+                                           const SlabCoef& c, float tmax, uint32_t meta4, uint32_t imask,
+                                           uint32_t& hits, int& m1, int& m2)
+{
+    constexpr int H = S & 1, J = S & 3;
+    const float tnx = fmaf(plane_to_float<H>(wnx, c.k43), c.anx, c.bnx), tny = fmaf(plane_to_float<H>(wny, c.k43), c.any, c.bny),
+                tnz = fmaf(plane_to_float<H>(wnz, c.k43), c.anz, c.bnz);
+    const float tfx = fmaf(plane_to_float<H>(wfx, c.k43), c.afx, c.bfx), tfy = fmaf(plane_to_float<H>(wfy, c.k43), c.afy, c.bfy),
+                tfz = fmaf(plane_to_float<H>(wfz, c.k43), c.afz, c.bfz);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+    // meta byte: internal child 1 << 5 | (24 + slot), leaf unary(n) << 5 | offset: its hit bits are (meta >> 5) << (meta & 31)
+    const uint32_t mb = (meta4 >> (8 * J)) & 0xffu;
+    const uint32_t sel = tn <= tf ? 0xffffffffu : 0u;
+    hits |= ((mb >> 5) << (mb & 31u)) & sel;
+    const bool inner_hit = (tn <= tf) & ((imask >> S) & 1u);
+    const int key = inner_hit ? int((__float_as_uint(tn) & ~7u) | uint32_t(S)) : 0x7fffffff;
+    m2 = min(m2, max(m1, key));
+    m1 = min(m1, key);
+}
+
+// One wide-node step of a lane: fetch node `node`, slab-test its 8 children.  Returns the child group
+// ng = (child base, internal hits BY SLOT << 24 | imask), the triangle group tg = (triangle base, hit bits of the
+// triangles of the leaf children) and the keys (m1, m2) of the nearest and second-nearest internal child hit.
+//
+// Plane a of child s is origin_a + q 2^E; with f = 128 + q / 256 (plane_to_float) the slab distance is
+//   t = (origin_a + q 2^E - o_a) / d_a = f A + B,   A = 256 2^E / d_a,   B = (origin_a - o_a) / d_a - 128 A.
+// Near planes use (A, B)(1 - 4e-7) and far planes (A, B)(1 + 4e-7): the test is widened by a few ulp.
+__device__ __forceinline__ void node8_step(const MeshView& m, const RayF& r, float tmax, uint32_t node, uint2& ng, uint2& tg,
+                                           int& m1, int& m2)
+{
+    const float4* nd = m.nodes + (size_t)node * kNodeStride;
+    float4 f0, f1, f2, f3, f4, f5, f6, f7;
+    ldg256(nd, f0, f1); ldg256(nd + 2, f2, f3); ldg256(nd + 4, f4, f5); ldg256(nd + 6, f6, f7);
+    const uint32_t ew = __float_as_uint(f0.w), imask = ew >> 24;
+    const float ax = __uint_as_float((ew & 0xffu) << 23) * r.ix, ay = __uint_as_float(((ew >> 8) & 0xffu) << 23) * r.iy,
+                az = __uint_as_float(((ew >> 16) & 0xffu) << 23) * r.iz;
+    const float bx = fmaf(-128.0f, ax, (f0.x - r.ox) * r.ix), by = fmaf(-128.0f, ay, (f0.y - r.oy) * r.iy),
+                bz = fmaf(-128.0f, az, (f0.z - r.oz) * r.iz);
+    constexpr float kLo = 0.9999996f, kHi = 1.0000004f;
+    // 0x43000000 as a run-time value (the triangle base is < 2^28, which the compiler cannot know), so that it is
+    // not folded back into the permutes as their one immediate
+    const uint32_t k43 = 0x43000000u | (__float_as_uint(f1.y) >> 31);
+    const SlabCoef c = {ax * kLo, ay * kLo, az * kLo, bx * kLo, by * kLo, bz * kLo, ax * kHi, ay * kHi, az * kHi, bx * kHi, by * kHi, bz * kHi, k43};
+    const bool sx = r.ix < 0.f, sy = r.iy < 0.f, sz = r.iz < 0.f;
+    // near / far plane words per axis: lo planes in w2..w4, hi planes in w5..w7
+    const float4 nX = sx ? f5 : f2, fX = sx ? f2 : f5, nY = sy ? f6 : f3, fY = sy ? f3 : f6, nZ = sz ? f7 : f4, fZ = sz ? f4 : f7;
+    uint32_t hits = 0;
+    m1 = 0x7fffffff; m2 = 0x7fffffff;
+    const uint32_t meta_lo = __float_as_uint(f1.z), meta_hi = __float_as_uint(f1.w);
+#define DRTB_W(V, C) __float_as_uint(V.C)
+    child_slab<0>(DRTB_W(nX, x), DRTB_W(nY, x), DRTB_W(nZ, x), DRTB_W(fX, x), DRTB_W(fY, x), DRTB_W(fZ, x), c, tmax, meta_lo, imask, hits, m1, m2);
+    child_slab<1>(DRTB_W(nX, x), DRTB_W(nY, x), DRTB_W(nZ, x), DRTB_W(fX, x), DRTB_W(fY, x), DRTB_W(fZ, x), c, tmax, meta_lo, imask, hits, m1, m2);
+    child_slab<2>(DRTB_W(nX, y), DRTB_W(nY, y), DRTB_W(nZ, y), DRTB_W(fX, y), DRTB_W(fY, y), DRTB_W(fZ, y), c, tmax, meta_lo, imask, hits, m1, m2);
+    child_slab<3>(DRTB_W(nX, y), DRTB_W(nY, y), DRTB_W(nZ, y), DRTB_W(fX, y), DRTB_W(fY, y), DRTB_W(fZ, y), c, tmax, meta_lo, imask, hits, m1, m2);
+    child_slab<4>(DRTB_W(nX, z), DRTB_W(nY, z), DRTB_W(nZ, z), DRTB_W(fX, z), DRTB_W(fY, z), DRTB_W(fZ, z), c, tmax, meta_hi, imask, hits, m1, m2);
+    child_slab<5>(DRTB_W(nX, z), DRTB_W(nY, z), DRTB_W(nZ, z), DRTB_W(fX, z), DRTB_W(fY, z), DRTB_W(fZ, z), c, tmax, meta_hi, imask, hits, m1, m2);
+    child_slab<6>(DRTB_W(nX, w), DRTB_W(nY, w), DRTB_W(nZ, w), DRTB_W(fX, w), DRTB_W(fY, w), DRTB_W(fZ, w), c, tmax, meta_hi, imask, hits, m1, m2);
+    child_slab<7>(DRTB_W(nX, w), DRTB_W(nY, w), DRTB_W(nZ, w), DRTB_W(fX, w), DRTB_W(fY, w), DRTB_W(fZ, w), c, tmax, meta_hi, imask, hits, m1, m2);
+#undef DRTB_W
+    ng = make_uint2(__float_as_uint(f1.x), (hits & 0xff000000u) | imask);
+    tg = make_uint2(__float_as_uint(f1.y), hits & 0x00ffffffu);
+}
+
+// Child groups on the stack: x = child base, y = hits << 24 | bound << 8 | imask, hit bit 24 + s = the internal child
+// in slot s, and `bound` = the upper 16 bits of a float that is <= the entry distance of every child left in the
+// group (a conservative cull at pop time).
+constexpr uint32_t kHitBits = 0xff000000u;
+// Index of the child node in slot `slot` of group g.
+__device__ __forceinline__ uint32_t child_index(uint2 g, uint32_t slot)
+{
+    return g.x + __popc(g.y & 0xffu & ((1u << slot) - 1u));       // rank among the internal children
+}
+// After node8_step: take the NEAREST internal child hit (key m1) out of ng; what is left goes to `rest` with the
+// second-nearest distance as its bound (rest.y & kHitBits == 0: nothing left).  Returns the child's node index.
+__device__ __forceinline__ uint32_t take_nearest(uint2 ng, int m1, int m2, uint2& rest)
+{
+    const uint32_t slot = uint32_t(m1) & 7u;
+    rest = make_uint2(ng.x, (ng.y & ~(0x01000000u << slot)) | ((uint32_t(m2) >> 8) & 0x00ffff00u));
+    return child_index(ng, slot);
+}
+// A popped group: false if its bound is beyond tmax (every child left is culled); else takes the child on the
+// ray's near side -- the slot s with the smallest s ^ near_slot, where slot bit a says on which side of the node's
+// centre the child lies -- and returns its node index, leaving the others in g.
+__device__ __forceinline__ bool take_from_popped(uint2& g, float tmax, uint32_t octinv4, uint32_t& node)
+{
+    if (__uint_as_float((g.y << 8) & 0xffff0000u) > tmax) return false;
+    const uint32_t oi = octinv4 & 7u, h = g.y >> 24;
+    // permute the hit bits by s -> s ^ octinv (three conditional swaps); the highest bit is then the nearest slot
+    uint32_t v = h;
+    v = (oi & 1u) ? ((v & 0x55u) << 1) | ((v >> 1) & 0x55u) : v;
+    v = (oi & 2u) ? ((v & 0x33u) << 2) | ((v >> 2) & 0x33u) : v;
+    v = (oi & 4u) ? ((v & 0x0fu) << 4) | ((v >> 4) & 0x0fu) : v;
+    const uint32_t slot = (31u - __clz(v)) ^ oi;
+    g.y &= ~(0x01000000u << slot);
+    node = child_index(g, slot);
+    return true;
+}
+
+// Closest triangle along (o, d) that beats `tmin`: the per-lane form of the traversal (explicit rays,
+// drtb_trace_rays); the wavefront's wf_traverse runs the same steps warp-synchronously.
 template <typename R>
 __device__ __forceinline__ void bvh_closest(const MeshView& m, V3<R> o, V3<R> d, R& tmin, int& best,
                                             uint32_t& n_nodes, uint32_t& n_tests)
 {
     const RayF r = make_rayf(o, d);
     float tmax = upper_float<R>(tmin);
-    LocalStack stack;                                    // (key, link)
-    int sp = 0, cur = 0;
-    bool overflow = false, alive = true;
-    // Warp-synchronous stepping with a majority vote.  Left to the compiler's own
-    // reconvergence this loop ran with 4.3 of 32 lanes active; converged but executing
-    // the node code and the leaf code in every iteration, the leaf code still ran at
-    // 2.9 of 32 (profiles/r01_mesh_f64_v2_bvh4_summary.txt, ..._v3_sync_summary.txt).
-    // So each iteration issues ONE kind of step -- the one more lanes are waiting for --
-    // and the minority keeps its state: lanes that reached a leaf wait until the leaf
-    // lanes outnumber the lanes still descending, then all leaves are tested together.
-    const unsigned live = __activemask();
-#ifndef DRTB_LEAF_WEIGHT
-#define DRTB_LEAF_WEIGHT 1
-#endif
+    LocalStack stack;
+    int sp = 0;
+    bool overflow = false;
+    uint32_t node = 0;                                           // the root
     for (;;) {
-        const bool at_node = alive && cur >= 0, at_leaf = alive && cur < 0;
-        const unsigned node_m = __ballot_sync(live, at_node), leaf_m = __ballot_sync(live, at_leaf);
-        if ((node_m | leaf_m) == 0u) break;
-        const bool leaf_step = node_m == 0u || DRTB_LEAF_WEIGHT * __popc(leaf_m) >= __popc(node_m);
-        bool pop = false;
-        if (!leaf_step) {
-            if (at_node) {                               // wide node
-                ++n_nodes;
-                pop = bvh_node_step(m, r, tmax, cur, stack, sp, overflow);
-            }
-        } else if (at_leaf) {                            // leaf: ~((first << 2) | (count - 1))
-            const int code = ~cur, first = code >> 2, count = (code & 3) + 1;
-            for (int k = 0; k < count; ++k) { ++n_tests; leaf_tri_test<R>(m, first + k, r, o, d, tmin, best); }
-            tmax = upper_float<R>(tmin);
-            pop = true;
+        uint2 ng, tg, rest;
+        int m1, m2;
+        ++n_nodes;
+        node8_step(m, r, tmax, node, ng, tg, m1, m2);
+        bool have = false;
+        if (ng.y & kHitBits) {
+            node = take_nearest(ng, m1, m2, rest);
+            have = true;
+            if (rest.y & kHitBits) { if (sp < kBvhStack) stack.e[sp++] = rest; else overflow = true; }
         }
-        if (pop) {
-            alive = false;
-            while (sp > 0) {
-                const int2 e = stack.get(--sp);
-                if (__int_as_float(e.x & ~3) <= tmax) { cur = e.y; alive = true; break; }
+        while (tg.y) {
+            const int bit = __ffs(tg.y) - 1;
+            tg.y &= tg.y - 1u;
+            ++n_tests;
+            leaf_tri_test<R>(m, int(tg.x) + bit, r, o, d, tmin, best);
+        }
+        tmax = upper_float<R>(tmin);
+        while (!have && sp > 0) {
+            uint2 g = stack.e[--sp];
+            if (take_from_popped(g, tmax, r.octinv4, node)) {
+                have = true;
+                if (g.y & kHitBits) stack.e[sp++] = g;
             }
         }
+        if (!have) break;
     }
     if (overflow) brute_closest<R>(m, o, d, tmin, best, n_tests);   // never seen on a PLOC tree; correctness first
 }

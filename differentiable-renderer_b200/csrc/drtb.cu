@@ -451,6 +451,7 @@ int drtb_create(int device, drtb_ctx** out)
     if (!ctx) return fail(nullptr, DRTB_ERR_NOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_window_max = size_t(std::max(0, prop.accessPolicyMaxWindowSize));
     if (const char* e = std::getenv("DRTB_NO_REGEN")) ctx->no_regen = std::atoi(e) != 0;
     if (const char* e = std::getenv("DRTB_RING")) ctx->ring_policy = std::string(e) == "global" ? 2 : 0;
     if (cudaSetDevice(device) != cudaSuccess ||
@@ -461,6 +462,11 @@ int drtb_create(int device, drtb_ctx** out)
         delete ctx;
         return fail(nullptr, DRTB_ERR_CUDA, "context setup failed: " + m);
     }
+    // L2 set-aside for the mesh geometry's persisting window (mesh.cu); costs nothing while no window is active
+    if (prop.persistingL2CacheMaxSize > 0 &&
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(prop.persistingL2CacheMaxSize)) == cudaSuccess)
+        ctx->l2_persist_max = size_t(prop.persistingL2CacheMaxSize);
+    else cudaGetLastError();
     // (sin, cos)(2 pi i 2^23 / M) for Real<double>::sincos_tab: one copy per translation unit that samples in double
     if (drtb::upload_sincos_tab() != cudaSuccess || init_tables_render_f64() != cudaSuccess || init_tables_mesh() != cudaSuccess) {
         std::string m = cudaGetErrorString(cudaGetLastError());
@@ -620,8 +626,10 @@ int render_host(drtb_ctx* ctx, const drtb_render_opts* o, int32_t gparam, const 
         float ms = 0.f;
         CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         stats->kernel_ms = ms;
+#ifndef DRTB_TRAV_DEBUG                               // (the debug build of the traversal borrows these two fields)
         stats->paths = uint64_t(rows) * W * o->spp;
         stats->retraced_paths = 0;
+#endif
     }
     return DRTB_OK;
 }

@@ -59,7 +59,9 @@ struct drtb_ctx {
     unsigned long long launches = 0;
     // triangle mesh + BVH (device)
     int64_t n_tris = 0;
-    float4* d_nodes = nullptr;
+    float4* d_nodes = nullptr;    // raw 16-byte words of the wide nodes (bvh.cuh); lives in d_geom behind the triangles
+    size_t geom_bytes = 0;        // d_tri32 (= the base of the one allocation) .. end of the nodes: what the traversal reads,
+                                  // kept L2-resident by an access-policy window while the wavefront streams rays through
     double* d_tri64 = nullptr;
     float4* d_tri32 = nullptr;
     int32_t* d_tri_color = nullptr;
@@ -71,6 +73,8 @@ struct drtb_ctx {
     unsigned long long* d_task_counter = nullptr;
     double* img_peers[drtb::kMaxPeers] = {};   // drtb_set_image_peers: full images the render kernel fills directly
     int n_img_peers = 0;
+    size_t l2_persist_max = 0;    // cudaDevAttrMaxPersistingL2CacheSize, reserved at create (0: not supported)
+    size_t l2_window_max = 0;     // cudaDevAttrMaxAccessPolicyWindowSize
     // Preparation pass (drtb_reserve, and drtb_render before it starts its timer): every scratch buffer is
     // sized, every kernel attribute set and every kernel instantiation launched once on zero work (module load,
     // local-memory reservation), so that none of it lands between the events that drtb_stats.kernel_ms reports.
@@ -137,7 +141,8 @@ inline drtb::MeshView mesh_view(const drtb_ctx* ctx)
 
 inline void free_mesh(drtb_ctx* ctx)
 {
-    cudaFree(ctx->d_nodes); cudaFree(ctx->d_tri64); cudaFree(ctx->d_tri32);
+    cudaFree(ctx->d_tri64); cudaFree(ctx->d_tri32);           // d_nodes points into d_tri32's allocation
+    ctx->geom_bytes = 0;
     cudaFree(ctx->d_tri_color); cudaFree(ctx->d_tri_emis);
     ctx->d_nodes = nullptr; ctx->d_tri64 = nullptr; ctx->d_tri32 = nullptr;
     ctx->d_tri_color = nullptr; ctx->d_tri_emis = nullptr;

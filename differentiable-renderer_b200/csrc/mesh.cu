@@ -218,6 +218,19 @@ int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opt
         CK(ctx, cudaFuncGetAttributes(&fa, wf_shade<R>));
         return DRTB_OK;
     }
+    // "Scene geometry and the BVH staged in L2" (north_star): the rays of a batch stream through L2 once per depth
+    // (4 M x 72 B), which evicts the 85 MB of triangles and nodes that EVERY ray reads.  A persisting access-policy
+    // window over the geometry keeps it resident; ray traffic is left to the normal (evict-first for misses) policy.
+    const bool l2_window = ctx->l2_persist_max > 0 && ctx->geom_bytes > 0 && !no_bvh && std::getenv("DRTB_NO_L2_WINDOW") == nullptr;
+    if (l2_window) {
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr = ctx->d_tri32;
+        av.accessPolicyWindow.num_bytes = std::min(ctx->geom_bytes, ctx->l2_window_max);
+        av.accessPolicyWindow.hitRatio = float(std::min(1.0, double(ctx->l2_persist_max) / double(av.accessPolicyWindow.num_bytes)));
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CK(ctx, cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     for (int bi = 0; bi < n_batches; ++bi) {
         const long long p0 = (long long)bi * pix_per_batch;
         a.first_path = p0 * o->spp;
@@ -241,6 +254,10 @@ int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opt
         }
         CK(ctx, cudaGetLastError());
         ctx->launches += 2 + 2 * D;
+    }
+    if (l2_window) {
+        cudaStreamAttrValue av{};                            // num_bytes = 0: window off for whatever the caller enqueues next
+        CK(ctx, cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
     }
     if (want_grad && smallp) {
         // at most 148 * 8 * n_batches rows: the fixed-order reduction of drtb.cu (one block up to 4096 rows)
@@ -271,7 +288,7 @@ int mesh_upload_impl(drtb_ctx* ctx, const drtb_mesh* mesh)
     // ---- device buffers: persistent mesh data + build temporaries
     const bool use_lbvh = [] { const char* e = std::getenv("DRTB_BVH"); return e && std::string(e) == "lbvh"; }();
     double* d_vert = nullptr; int32_t* d_idx = nullptr;
-    float4 *d_lo = nullptr, *d_hi = nullptr, *d_blo = nullptr, *d_bhi = nullptr, *d_wide = nullptr; uint32_t* d_bounds = nullptr;
+    float4 *d_lo = nullptr, *d_hi = nullptr, *d_blo = nullptr, *d_bhi = nullptr; uint4* d_wide = nullptr; uint32_t* d_bounds = nullptr;
     uint64_t *d_keys = nullptr, *d_keys2 = nullptr, *d_flags = nullptr, *d_scan = nullptr;
     uint32_t *d_vals = nullptr, *d_vals2 = nullptr;
     int2 *d_children = nullptr, *d_tasks = nullptr, *d_tasks2 = nullptr;
@@ -288,14 +305,13 @@ int mesh_upload_impl(drtb_ctx* ctx, const drtb_mesh* mesh)
     cudaStream_t st = ctx->stream;
     const size_t nn = size_t(n), n_int = nn > 1 ? nn - 1 : 1;
     CKM(cudaMalloc((void**)&ctx->d_tri64, nn * kTri64Stride * sizeof(double)));
-    CKM(cudaMalloc((void**)&ctx->d_tri32, nn * kTri32Stride * sizeof(float4)));
     CKM(cudaMalloc((void**)&ctx->d_tri_color, nn * sizeof(int32_t)));
     CKM(cudaMalloc((void**)&ctx->d_tri_emis, nn * sizeof(int32_t)));
     CKM(cudaMalloc((void**)&d_vert, size_t(nv) * 3 * sizeof(double)));
     CKM(cudaMalloc((void**)&d_idx, nn * 3 * sizeof(int32_t)));
     CKM(cudaMalloc((void**)&d_lo, nn * sizeof(float4)));      CKM(cudaMalloc((void**)&d_hi, nn * sizeof(float4)));
     CKM(cudaMalloc((void**)&d_blo, 2 * nn * sizeof(float4))); CKM(cudaMalloc((void**)&d_bhi, 2 * nn * sizeof(float4)));
-    CKM(cudaMalloc((void**)&d_wide, nn * kNodeStride * sizeof(float4)));      // a wide node has >= 2 children: < n nodes
+    CKM(cudaMalloc((void**)&d_wide, nn * kNodeStride * sizeof(uint4)));       // a wide node has >= 2 children: < n nodes
     CKM(cudaMalloc((void**)&d_bounds, 6 * sizeof(uint32_t)));
     CKM(cudaMalloc((void**)&d_keys, nn * sizeof(uint64_t)));  CKM(cudaMalloc((void**)&d_keys2, nn * sizeof(uint64_t)));
     CKM(cudaMalloc((void**)&d_vals, nn * sizeof(uint32_t)));  CKM(cudaMalloc((void**)&d_vals2, nn * sizeof(uint32_t)));
@@ -369,14 +385,14 @@ int mesh_upload_impl(drtb_ctx* ctx, const drtb_mesh* mesh)
         }
         root = int(n) + made - 1;                            // the last node created
     }
-    // 3. collapse to the 4-wide BVH, one level per launch
+    // 3. collapse to the 8-wide compressed BVH, one level per launch
     const CollapseCounters init_cnt{1, 0, 0, 0};
     const int2 root_task = make_int2(root, 0);
     CKM(cudaMemcpyAsync(d_cnt, &init_cnt, sizeof init_cnt, cudaMemcpyHostToDevice, st));
     CKM(cudaMemcpyAsync(d_tasks, &root_task, sizeof root_task, cudaMemcpyHostToDevice, st));
     CollapseCounters h_cnt = init_cnt;
     for (int n_tasks = 1; n_tasks > 0;) {
-        collapse_kernel<<<(n_tasks + T - 1) / T, T, 0, st>>>(d_tasks, n_tasks, int(n), bt, d_vals2, d_wide, d_leaf_order, d_cnt, d_tasks2);
+        collapse8_kernel<<<(n_tasks + T - 1) / T, T, 0, st>>>(d_tasks, n_tasks, int(n), bt, d_vals2, d_wide, d_leaf_order, d_cnt, d_tasks2);
         CKM(cudaGetLastError());
         CKM(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
         CKM(cudaStreamSynchronize(st));
@@ -386,8 +402,14 @@ int mesh_upload_impl(drtb_ctx* ctx, const drtb_mesh* mesh)
         ctx->launches++;
     }
     if (h_cnt.tris != int(n)) { cleanup(); free_mesh(ctx); return fail(ctx, DRTB_ERR_CUDA, "BVH collapse lost triangles"); }
-    CKM(cudaMalloc((void**)&ctx->d_nodes, size_t(h_cnt.nodes) * kNodeStride * sizeof(float4)));
-    CKM(cudaMemcpyAsync(ctx->d_nodes, d_wide, size_t(h_cnt.nodes) * kNodeStride * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    // what the traversal reads -- float triangles (leaf order), then the wide nodes -- in ONE allocation, so that a
+    // single L2 access-policy window can keep it resident (launch_wavefront)
+    const size_t tri_bytes = (nn * kTri32Stride * sizeof(float4) + 255) & ~size_t(255);
+    const size_t node_bytes = size_t(h_cnt.nodes) * kNodeStride * sizeof(uint4);
+    CKM(cudaMalloc((void**)&ctx->d_tri32, tri_bytes + node_bytes));
+    ctx->d_nodes = reinterpret_cast<float4*>(reinterpret_cast<char*>(ctx->d_tri32) + tri_bytes);
+    ctx->geom_bytes = tri_bytes + node_bytes;
+    CKM(cudaMemcpyAsync(ctx->d_nodes, d_wide, node_bytes, cudaMemcpyDeviceToDevice, st));
     leaf_triangles_kernel<<<G, T, 0, st>>>(d_leaf_order, ctx->d_tri64, int(n), ctx->d_tri32);
     CKM(cudaGetLastError());
     ctx->launches++;

@@ -35,10 +35,9 @@ namespace drtb {
 
 constexpr int kBatchPaths = 1 << 22;          // camera samples per wavefront batch
 #ifndef DRTB_FETCH_BELOW
-#define DRTB_FETCH_BELOW 20
+#define DRTB_FETCH_BELOW 26
 #endif
 constexpr int kFetchBelow = DRTB_FETCH_BELOW; // traversal: refill the warp when fewer lanes than this hold a ray
-constexpr int kExactTag = 1 << 30;            // stack link ~(kExactTag | tri): exact test of triangle tri pending
 
 template <typename R> struct alignas(4 * sizeof(R)) R4 { R x, y, z, w; };
 
@@ -152,6 +151,32 @@ template <typename R> __device__ __forceinline__ void wf_reload_ray(const WfBuff
 #ifndef DRTB_WF_MIN_BLOCKS
 #define DRTB_WF_MIN_BLOCKS 6
 #endif
+
+// Per lane: the ray in float (RayF), the closest hit so far, and the traversal state of bvh.cuh -- the node to
+// open next (`next`), up to TWO pending triangle groups (tg0 being tested, tg1 waiting; .y = triangles still to cull
+// or test), `eg` = triangles of tg0 that survived the float cull and await the exact double test, and a stack of
+// child groups.  Each iteration the warp votes and executes ONE kind of step for the lanes that can take it:
+//   N  open node `next` (or first pop a child group: groups whose distance bound is beyond the closest hit are
+//      dropped unopened): 8 quantised child boxes; the nearest child hit becomes `next`, the other children hit go
+//      on the stack as one group, the triangles hit become a pending group.  A lane may open a node while ONE
+//      triangle group is still pending (it traverses on with the closest hit it knows, which only costs an
+//      occasional node that the pending triangles would have culled): with that slack ~3/4 of the lanes can take
+//      an N step at any time, where "no triangle pending" allowed ~1/2 (profiles/r02_wf_traverse_f64_cw3_summary.txt:
+//      14 of 32 lanes per instruction)
+//   T  one triangle of tg0: float test (float instantiation) or conservative float cull (double)
+//   E  one triangle of eg: reload the ray in double, exact Moller-Trumbore                  (double only)
+// so that the expensive exact test (80-byte triangle + 64-byte ray + ~50 FP64 operations) also runs on many lanes.
+// The cheap kinds go first when they serve enough lanes (a T step is about a quarter of an N step).
+// A lane with nothing left and an empty stack has finished its ray and is refilled from the queue.
+#ifndef DRTB_PREFETCH
+#define DRTB_PREFETCH 0      // measured: prefetching the next node and triangle to L1 costs 3 % (profiles/README.md, round 2)
+#endif
+#ifndef DRTB_VOTE_T
+#define DRTB_VOTE_T 2      // a T step runs when DRTB_VOTE_T * (lanes with a triangle to test) >= lanes that can open a node
+#endif
+#ifndef DRTB_VOTE_E
+#define DRTB_VOTE_E 2
+#endif
 template <typename R>
 __global__ void __launch_bounds__(128, DRTB_WF_MIN_BLOCKS)
 wf_traverse(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
@@ -159,15 +184,22 @@ wf_traverse(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
     if (b.alive_count[a.depth] == 0) return;
     const MeshView& m = a.mesh;
     const int lane = threadIdx.x & 31;
+    constexpr uint32_t kNone = 0xffffffffu;
     uint32_t n_nodes = 0, n_tests = 0;
+#ifdef DRTB_TRAV_DEBUG
+    uint32_t dbg_stale = 0, dbg_children = 0, dbg_leaf_hits = 0;
+#endif
     // lane state
     int p = -1;                                   // path slot whose ray this lane traverses, -1 = none
     RayF r{};
     R tmin = R(0);
     float tmax = 0.f;
-    int best = -1, cur = 0, sp = 0;
+    int best = -1, sp = 0;
+    uint32_t next = kNone;
+    uint2 tg0 = make_uint2(0u, 0u), tg1 = make_uint2(0u, 0u);
+    uint32_t eg = 0u;
     bool overflow = false;
-    __shared__ int2 s_stack[kSmemStack + 1][128];
+    __shared__ uint2 s_stack[kSmemStack + 1][128];
     SmemStack<128> stack;
     stack.col = &s_stack[0][threadIdx.x];
     bool exhausted = false;                       // warp-uniform: the queue has no more rays
@@ -186,66 +218,87 @@ wf_traverse(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
                     const R4<R> ra = b.ray_a[p], rb = b.ray_b[p];
                     r = make_rayf<R>(V3<R>{ra.x, ra.y, ra.z}, V3<R>{ra.w, rb.x, rb.y});
                     tmin = rb.z; tmax = upper_float<R>(tmin);
-                    best = -1; cur = 0; sp = 0; overflow = false;
+                    best = -1; sp = 0; overflow = false;
+                    next = 0u; tg0 = make_uint2(0u, 0u); tg1 = make_uint2(0u, 0u); eg = 0u;          // the root
                 }
             }
             exhausted = first + (uint32_t)__popc(idle) >= (uint32_t)a.n_paths;
             if (__ballot_sync(0xffffffffu, p >= 0) == 0u) { if (exhausted) break; else continue; }
         } else if (busy == 0u) break;
-        // One step of the kind most lanes wait for (see bvh_closest).  Three kinds in the
-        // double instantiation: wide node, leaf (float cull of its triangles), and the exact
-        // double test of ONE triangle that survived a cull -- survivors are pushed on the
-        // lane's stack as entries of their own, so the expensive test (80-byte triangle +
-        // 64-byte ray reload + ~50 FP64 operations) also runs with many lanes instead of
-        // the 1.5 of 32 it had inside the leaf loop (profiles/r01_wf_traverse_f64_v1_summary.txt).
-        const int code = ~cur;
         const bool on = p >= 0;
-        const bool at_node = on && cur >= 0;
-        const bool at_exact = on && cur < 0 && (code & kExactTag);
-        const bool at_leaf = on && cur < 0 && !(code & kExactTag);
-        const int nn = __popc(__ballot_sync(0xffffffffu, at_node)), nl = __popc(__ballot_sync(0xffffffffu, at_leaf)),
-                  ne = sizeof(R) == 8 ? __popc(__ballot_sync(0xffffffffu, at_exact)) : 0;
-        const int kind = (ne > 0 && ne >= nl && ne >= nn) ? 2 : (nl > 0 && nl >= nn) ? 1 : 0;
-        bool pop = false;
+        const bool can_e = sizeof(R) == 8 && on && eg != 0u;
+        const bool can_t = on && tg0.y != 0u;
+        const bool can_n = on && tg1.y == 0u && (next != kNone || sp > 0);      // a node to open (or a group to pop) and room for its triangles
+        const int nn = __popc(__ballot_sync(0xffffffffu, can_n)), nt = __popc(__ballot_sync(0xffffffffu, can_t)),
+                  ne = sizeof(R) == 8 ? __popc(__ballot_sync(0xffffffffu, can_e)) : 0;
+        const int kind = (ne > 0 && DRTB_VOTE_E * ne >= nt && DRTB_VOTE_E * ne >= nn) ? 2 : (nt > 0 && DRTB_VOTE_T * nt >= nn) ? 1 : 0;
         if (kind == 0) {
-            if (at_node) {
-                ++n_nodes;
-                pop = bvh_node_step(m, r, tmax, cur, stack, sp, overflow);
+            if (can_n) {
+                if (next == kNone) {                  // nothing pending: pop one child group
+                    uint2 g = stack.get(sp - 1);
+                    const bool ok = take_from_popped(g, tmax, r.octinv4, next);
+                    const bool keep = ok && (g.y & kHitBits) != 0u;       // its other children stay on the stack
+                    stack.put(sp - 1, g, keep);
+                    sp -= keep ? 0 : 1;
+                }
+                if (next != kNone) {
+                    uint2 ng, tg, rest;
+                    int m1, m2;
+                    ++n_nodes;
+                    node8_step(m, r, tmax, next, ng, tg, m1, m2);
+#ifdef DRTB_TRAV_DEBUG
+                    dbg_stale += (ng.y & kHitBits) == 0u && tg.y == 0u;
+                    dbg_children += __popc(ng.y >> 24);
+                    dbg_leaf_hits += __popc(tg.y);
+#endif
+                    const bool free0 = tg0.y == 0u && eg == 0u;           // tg0's base is still needed while eg is pending
+                    tg0 = free0 ? tg : tg0;
+                    tg1 = free0 ? tg1 : tg;
+                    next = kNone;
+                    if (ng.y & kHitBits) {
+                        next = take_nearest(ng, m1, m2, rest);
+                        const bool more = (rest.y & kHitBits) != 0u;    // the other children hit wait on the stack
+                        stack.put(sp, rest, more && sp < kBvhStack);
+                        overflow |= more && sp >= kBvhStack;
+                        sp += (more && sp < kBvhStack) ? 1 : 0;
+#if DRTB_PREFETCH
+                        // the child is opened a few iterations from now (its siblings' triangles come first): start its
+                        // 128-byte line on the way to L1 now -- the top stall of this kernel is the wait for node data
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(m.nodes + (size_t)next * kNodeStride));
+#endif
+                    }
+#if DRTB_PREFETCH
+                    if (tg.y) asm volatile("prefetch.global.L1 [%0];" :: "l"(m.tri32 + (size_t)(tg.x + __ffs(tg.y) - 1) * kTri32Stride));
+#endif
+                }
             }
         } else if (kind == 1) {
-            if (at_leaf) {
-                const int first = code >> 2, count = (code & 3) + 1;
-                for (int k = 0; k < count; ++k) {
-                    ++n_tests;
-                    const TriF T = load_trif(m, first + k);
-                    if constexpr (sizeof(R) == 8) {
-                        const bool keep = !tri_cull_f(T, r, tmax);
-                        stack.put(sp, make_int2(0, ~(kExactTag | T.id)), keep && sp < kBvhStack);
-                        overflow |= keep && sp >= kBvhStack;
-                        sp += (keep && sp < kBvhStack) ? 1 : 0;
-                    } else {
-                        const TriData<R> D = {{T.v0x, T.v0y, T.v0z}, {T.e1x, T.e1y, T.e1z}, {T.e2x, T.e2y, T.e2z}};
-                        tri_test_exact<R>(D, T.id, V3<R>{r.ox, r.oy, r.oz}, V3<R>{r.dx, r.dy, r.dz}, tmin, best);
-                    }
+            if (can_t) {
+                const int bit = __ffs(tg0.y) - 1;
+                tg0.y &= tg0.y - 1u;
+                ++n_tests;
+                const TriF T = load_trif(m, int(tg0.x) + bit);
+                if constexpr (sizeof(R) == 8) {
+                    eg |= tri_cull_f(T, r, tmax) ? 0u : (1u << bit);
+                } else {
+                    const TriData<R> D = {{T.v0x, T.v0y, T.v0z}, {T.e1x, T.e1y, T.e1z}, {T.e2x, T.e2y, T.e2z}};
+                    tri_test_exact<R>(D, T.id, V3<R>{r.ox, r.oy, r.oz}, V3<R>{r.dx, r.dy, r.dz}, tmin, best);
+                    tmax = upper_float<R>(tmin);
                 }
-                tmax = upper_float<R>(tmin);
-                pop = true;
             }
-        } else if (at_exact) {
-            const int tri = code & (kExactTag - 1);
+        } else if (can_e) {
+            const int bit = __ffs(eg) - 1;
+            eg &= eg - 1u;
+            const int tri = __float_as_int(__ldg(&m.tri32[(size_t)(int(tg0.x) + bit) * kTri32Stride + 2].w));   // original index
             V3<R> o, d;
             wf_reload_ray(b, p, o, d);                // o, d stay out of the registers between the rare exact tests
             tri_test_exact<R>(load_tri<R>(m, tri), tri, o, d, tmin, best);
             tmax = upper_float<R>(tmin);
-            pop = true;
         }
-        if (pop) {
-            bool more = false;
-            while (sp > 0) {
-                const int2 e = stack.get(--sp);
-                if (__int_as_float(e.x & ~3) <= tmax) { cur = e.y; more = true; break; }
-            }
-            if (!more) {                          // this ray is done: publish the hit, free the lane
+        if (on && tg0.y == 0u && eg == 0u) {
+            // tg0 is done: the waiting group moves up; with nothing left anywhere the ray is finished
+            tg0 = tg1; tg1.y = 0u;
+            if (tg0.y == 0u && next == kNone && sp == 0) {
                 if (overflow) {
                     V3<R> o, d;
                     wf_reload_ray(b, p, o, d);
@@ -264,6 +317,11 @@ wf_traverse(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
             atomicAdd((unsigned long long*)&a.stats->bvh_nodes, nn);
             atomicAdd((unsigned long long*)&a.stats->tri_tests, nt);
         }
+#ifdef DRTB_TRAV_DEBUG
+        atomicAdd((unsigned long long*)&a.stats->truncated_paths, (unsigned long long)dbg_stale);
+        atomicAdd((unsigned long long*)&a.stats->retraced_paths, (unsigned long long)dbg_children);
+        atomicAdd((unsigned long long*)&a.stats->paths, (unsigned long long)dbg_leaf_hits);
+#endif
     }
 }
 
