@@ -10,11 +10,15 @@ traced to termination plus its gradient contribution (BASELINE.json `metric`).
 `e2e`    : the same through the C ABI call with HOST buffers (drtb_set_params +
            drtb_render), parameter H2D and image/gradient D2H inside the timing.
 N > 1    : launched under torchrun, one rank per GPU; image rows are sharded in
-           interleaved bands, gradients summed with one NCCL all-reduce; the image
-           gather is fused into the render kernel (every rank's kernel stores its
-           pixels into all ranks' full images over NVLink, drtb_set_image_peers),
-           checked once against an NCCL all-gather before timing; max over ranks;
-           weak scaling is NOT used -- the workload is fixed, so "scaling" is "strong".
+           interleaved bands; the image gather is fused into the render kernel (every
+           rank's kernel stores its pixels into all ranks' full images over NVLink,
+           drtb_set_image_peers) and the gradient sum is a one-block peer-store kernel
+           behind the render (drtb_set_grad_peers); both are checked once against NCCL
+           (all-gather, all-reduce) before timing, and NCCL stays the fallback; max over
+           ranks; the workload is fixed, so "scaling" is "strong".  e2e at N > 1 lands the
+           ASSEMBLED image in one pinned host buffer on rank 0 every step.
+Extra keys (N = 1): "mesh" = config 4 of BASELINE.json (1 M triangles, GPU-built BVH, wavefront
+           integrator), "f32" / "mixed" = the other arithmetic modes on the headline workload.
 """
 from __future__ import annotations
 
@@ -49,6 +53,7 @@ def parse_args():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--band-rows", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the mesh / f32 / mixed blocks (N = 1)")
     return ap.parse_args()
 
 
@@ -105,6 +110,38 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU legs
+def kernel_source_sha() -> str:
+    """Hash of the sources the analytic render kernels are compiled from: profiles/ncu_render_kernel.json carries
+    the hash it was captured at, so that a stale ncu figure is not reported for a kernel that has changed."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = ROOT / "differentiable-renderer_b200" / "csrc"
+    for name in ("render_kernels.cuh", "path.cuh", "real.cuh", "rng.cuh", "sinks.cuh"):
+        h.update((csrc / name).read_bytes())
+    return h.hexdigest()[:16]
+
+
+def cpu_one_core_as_shipped(a, seconds_budget: float = 4.0):
+    """the reference AS SHIPPED -- one thread, the sequential unseeded glibc rand() of
+    random.hpp:9, the loop order of src/render.cpp:72-76 -- on a small sample of the same scene and settings."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib
+    import drt_b200 as drt
+    if not oracle_lib.have_ref():
+        return None
+    side, spp = 48, min(a.spp, 16)
+    t = time.perf_counter()
+    oracle_lib.ref_render(drt.cornell_box(side, side), drt.make_opts(spp, a.bounces, 1.0), threads=1, rand_mode=1)
+    dt = time.perf_counter() - t
+    if dt < seconds_budget / 4:
+        side = int(min(256, side * (seconds_budget / max(dt, 1e-3)) ** 0.5)) // 8 * 8
+        t = time.perf_counter()
+        oracle_lib.ref_render(drt.cornell_box(side, side), drt.make_opts(spp, a.bounces, 1.0), threads=1, rand_mode=1)
+        dt = time.perf_counter() - t
+    return {"value": side * side * spp / dt / 1e6, "unit": UNIT, "cores": 1,
+            "sample": f"{side}x{side}, {spp} spp, min_bounces={a.bounces}, absorb=1, sequential glibc rand(), 1 thread"}
+
+
 def cpu_render_rate(a, seconds_budget: float, threads: int | None = None):
     """Times the reference's CPU path (oracle/_ref when built, else the C port)
     on a bounded sample of the SAME workload (same scene, mb, absorb, stream);
@@ -170,6 +207,78 @@ def run_reference_arm(a):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def timed_renders(ctx, torch, opts, d_img, d_grad, flush, reps=3):
+    """Best CUDA-event time (ms) of `reps` device-resident renders, L2 flushed before each."""
+    stream = torch.cuda.current_stream()
+    best = None
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.render_device(opts, 0, d_img.data_ptr(), d_grad.data_ptr(), 0, stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return best
+
+
+def extra_blocks(a, drt, ctx, scene, torch, dev, hbm_peak):
+    """Separately keyed blocks beside the headline (N = 1): the other arithmetic modes on the headline workload and
+    config 4 of BASELINE.json.  Same timing rules: device-resident, CUDA events, L2 flushed, warm."""
+    import math
+    out = {}
+    W, H, spp, B = a.width, a.height, a.spp, a.bounces
+    P = len(scene.params)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    d_img = torch.empty((H, W, 3), dtype=torch.float64, device=dev)
+    d_grad = torch.empty((P, 3), dtype=torch.float64, device=dev)
+    paths = W * H * spp
+    for name, prec in (("f32", drt.F32), ("mixed", drt.MIXED)):
+        try:
+            o = drt.make_opts(spp, B, 1.0, precision=prec)
+            ctx.reserve(o)
+            ms = timed_renders(ctx, torch, o, d_img, d_grad, flush)
+            out[name] = {"value": paths / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms,
+                         "workload": "the headline workload in this arithmetic mode"}
+            if prec == drt.MIXED:
+                img, grad, st = ctx.render(o, stats=True)
+                out[name]["retraced_path_fraction"] = st.retraced_paths / st.paths
+        except drt.DrtbError as e:
+            out[name] = {"unavailable": str(e)}
+    # ---- config 4: ~1 M procedurally tessellated triangles, GPU-built BVH, 1024 x 1024, 64 spp, 8 bounces,
+    # gradient w.r.t. per-triangle albedo (3 M scalars)
+    try:
+        t0 = time.time()
+        mscene = drt.tessellated_room(204, 362, width=1024, height=1024)
+        gen_s = time.time() - t0
+        n = mscene.mesh.n_triangles
+        with drt.Context(dev.index or 0) as mctx:
+            t0 = time.time(); mctx.upload(mscene); up_s = time.time() - t0
+            Pm = mscene.n_params
+            m_img = torch.empty((1024, 1024, 3), dtype=torch.float64, device=dev)
+            m_grad = torch.empty((Pm, 3), dtype=torch.float64, device=dev)
+            bytes_per_seg = math.ceil(math.log2(n / 4)) * 64 + 4 * 48 + 32          # SURVEY.md §8(d)
+            blk = {"workload": f"tessellated_room: {n} triangles, 1024x1024, 64 spp, min_bounces=8, absorb=1, per-triangle "
+                               f"albedo gradient ({n * 3} scalars)", "bvh_build_ms_device": mctx.mesh_build_ms,
+                   "host_generate_s": gen_s, "upload_and_build_s": up_s, "algorithmic_bytes_per_segment": bytes_per_seg}
+            for name, prec in (("f64", drt.F64), ("f32", drt.F32)):
+                o = drt.make_opts(64, 8, 1.0, precision=prec)
+                _, _, st = mctx.render(o, stats=True)                            # warm + counters
+                ms = timed_renders(mctx, torch, o, m_img, m_grad, flush, reps=2)
+                gbs = st.segments * bytes_per_seg / (ms * 1e-3) / 1e9
+                blk[name] = {"ms_per_step": ms, "Mpaths_per_s": st.paths / ms / 1e3, "Msegments_per_s": st.segments / ms / 1e3,
+                             "segments_per_path": st.segments / st.paths, "bvh_nodes_per_segment": st.bvh_nodes / st.segments,
+                             "tri_tests_per_segment": st.tri_tests / st.segments,
+                             "node_and_triangle_bytes_per_segment": st.bvh_nodes / st.segments * 128 + st.tri_tests / st.segments * 64,
+                             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                          "kernel": "wf_traverse (85 % of the step)"}}
+            out["mesh"] = blk
+    except Exception as e:                                                     # noqa: BLE001 -- reported in the line
+        out["mesh"] = {"unavailable": repr(e)}
+    return out
+
+
 def run_b200_arm(a):
     import numpy as np
     import torch
@@ -242,10 +351,46 @@ def run_b200_arm(a):
     use_peer = peer is not None
     img_arg = 0 if use_peer else d_img.data_ptr()
 
+    # ---- N > 1: the gradient sum as a peer-store kernel behind the render (drtb_set_grad_peers), checked once
+    # against ncclAllReduce; NCCL stays in the step if the exchange buffers cannot be mapped.
+    pgrad, grad_sum = None, "none (1 GPU)"
+    if world > 1:
+        grad_sum = f"NCCL all-reduce of {P * 3} doubles"
+        try:
+            pgrad = sharding.PeerGrad(ctx, dist)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:                                     # noqa: BLE001 -- reported, not hidden
+            print(f"[bench] rank {rank}: peer gradient exchange unavailable ({e}); using NCCL", file=sys.stderr)
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0 and pgrad is not None:
+            pgrad.close(); pgrad = None
+        if pgrad is not None:
+            dist.barrier(); torch.cuda.synchronize()
+            ctx.render_device(opts, 0, img_arg, d_grad.data_ptr(), 0, stream.cuda_stream)        # exchange on: d_grad = the sum
+            torch.cuda.synchronize()
+            summed = d_grad.clone()
+            ctx.set_grad_peers([])
+            ctx.render_device(opts, 0, img_arg, d_grad.data_ptr(), 0, stream.cuda_stream)
+            dist.all_reduce(d_grad, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+            close = (summed - d_grad).abs().max() <= 1e-12 * d_grad.abs().max()              # NCCL adds in its own order
+            ranks = [torch.empty_like(summed) for _ in range(world)]
+            dist.all_gather(ranks, summed)
+            same = torch.tensor([1.0 if (close and all(torch.equal(r, ranks[0]) for r in ranks)) else 0.0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            if same.item() != 1.0:
+                raise SystemExit("peer gradient exchange differs from ncclAllReduce")
+            ctx.set_grad_peers(pgrad.ptrs, rank)
+            grad_sum = (f"fused: one-block kernel behind the render stores {P * 3} doubles into every rank's exchange buffer "
+                        "(NVLink peer stores) and adds them in rank order; verified against ncclAllReduce, bit-identical on all ranks")
+    use_pgrad = pgrad is not None
+
     def step_device():
-        ctx.render_device(opts, 0, img_arg, d_grad.data_ptr(), 0, stream.cuda_stream)
+        ctx.render_device(opts, 0, img_arg, d_grad.data_ptr(), 0, stream.cuda_stream)        # + gradient exchange when on
         if world > 1:
-            dist.all_reduce(d_grad, op=dist.ReduceOp.SUM)          # the one collective of the path
+            if not use_pgrad:
+                dist.all_reduce(d_grad, op=dist.ReduceOp.SUM)      # the one collective of the path
             if equal and not use_peer:
                 dist.all_gather_into_tensor(d_full.view(world, rows, W, 3), d_img)
 
@@ -282,9 +427,10 @@ def run_b200_arm(a):
         flush.zero_()                                  # evict L2 between timed iterations (untimed)
         s0.record(stream)
         ctx.render_device(opts, 0, img_arg, d_grad.data_ptr(), 0, stream.cuda_stream)
-        s1.record(stream)                              # render + gradient reduction kernels only
+        s1.record(stream)                              # render + gradient reduction (+ peer exchange) kernels
         if world > 1:
-            dist.all_reduce(d_grad, op=dist.ReduceOp.SUM)
+            if not use_pgrad:
+                dist.all_reduce(d_grad, op=dist.ReduceOp.SUM)
             if equal and not use_peer:
                 dist.all_gather_into_tensor(d_full.view(world, rows, W, 3), d_img)
         s2.record(stream)
@@ -301,22 +447,47 @@ def run_b200_arm(a):
     ms_per_step = total_ms / a.steps
     value = paths_total / (ms_per_step * 1e-3) / 1e6
 
-    # ---- end to end through the C ABI with host buffers
-    h_img = torch.empty((rows, W, 3), dtype=torch.float64).pin_memory()
+    # ---- end to end: this step's inputs from pinned host memory, its results back in pinned host memory
+    h_img = torch.empty((rows if world == 1 else H, W, 3), dtype=torch.float64).pin_memory()
     h_grad = torch.empty((P, 3), dtype=torch.float64).pin_memory()
     g_dev = torch.empty((P, 3), dtype=torch.float64, device=dev)
     pvals = scene.param_values()
+    e2e_api = "drtb_set_params + drtb_render (host buffers, pinned)"
+    peer2 = None
+    if world > 1 and use_peer and use_pgrad:
+        # N > 1: the ASSEMBLED image must land in ONE host buffer.  Every rank's kernel stores its pixels into rank
+        # 0's full image, the gradient exchange orders "all stores have landed", and rank 0 copies the full image
+        # out.  Two full images alternate (drtb.h: the caller double-buffers): a fast rank's next render may store
+        # into rank 0's image while rank 0 still copies the previous one out.
+        peer2 = sharding.PeerImage(ctx, H, W, dist)
+        bufs = [(peer, peer.tensor(dev)), (peer2, peer2.tensor(dev))]
+        e2e_api = ("drtb_set_params + drtb_render_device (image peers + gradient peers) + one D2H of the assembled "
+                   "full image on rank 0 (pinned), gradients D2H on every rank")
+        flip = [0]
 
-    if use_peer:
-        ctx.set_image_peers([])                                          # the host-buffer API returns this rank's rows
+        def step_e2e():
+            pi, full = bufs[flip[0]]; flip[0] ^= 1
+            ctx.set_params(pvals)                                            # H2D: this step's inputs
+            ctx.set_image_peers(pi.ptrs)
+            ctx.render_device(opts, 0, 0, g_dev.data_ptr(), 0, stream.cuda_stream)
+            h_grad.copy_(g_dev, non_blocking=True)                           # D2H: the summed gradients
+            if rank == 0:
+                h_img.copy_(full, non_blocking=True)                         # D2H: the whole image, assembled by the kernels
+            stream.synchronize()
+    else:
+        if use_peer:
+            ctx.set_image_peers([])                                          # the host-buffer API returns this rank's rows
+        if use_pgrad:
+            ctx.set_grad_peers([])
+        h_img = torch.empty((rows, W, 3), dtype=torch.float64).pin_memory()
 
-    def step_e2e():
-        ctx.set_params(pvals)                                            # H2D: this step's inputs
-        ctx.render_host_ptrs(opts, 0, h_img.data_ptr(), h_grad.data_ptr())   # render + D2H image, gradients
-        if world > 1:
-            g_dev.copy_(h_grad, non_blocking=True)
-            dist.all_reduce(g_dev, op=dist.ReduceOp.SUM)
-            h_grad.copy_(g_dev)
+        def step_e2e():
+            ctx.set_params(pvals)                                            # H2D: this step's inputs
+            ctx.render_host_ptrs(opts, 0, h_img.data_ptr(), h_grad.data_ptr())   # render + D2H image, gradients
+            if world > 1:
+                g_dev.copy_(h_grad, non_blocking=True)
+                dist.all_reduce(g_dev, op=dist.ReduceOp.SUM)
+                h_grad.copy_(g_dev)
     for _ in range(2):
         step_e2e()
     sync_all()
@@ -331,7 +502,17 @@ def run_b200_arm(a):
     e2e_value = paths_total / (float(te_t.item()) / a.steps) / 1e6
     h2d = P * 3 * 8 * world
     d2h = (H * W * 3 * 8) + P * 3 * 8 * world
+    e2e_check = None
+    if peer2 is not None and rank == 0:
+        # the image in the host buffer is the whole picture: compare with the device image of the verification above
+        e2e_check = bool(torch.equal(h_img, bufs[flip[0] ^ 1][1].cpu())) and bool(torch.isfinite(h_img).all())
 
+    if pgrad is not None:
+        torch.cuda.synchronize()
+        pgrad.close()                                                    # collective
+    if peer2 is not None:
+        torch.cuda.synchronize()
+        peer2.close()
     if peer is not None:
         torch.cuda.synchronize()
         peer.close()                                                     # collective
@@ -347,25 +528,34 @@ def run_b200_arm(a):
     except Exception:
         pass
     fma_peak = ctx.fma_peak(prec)                                       # TFLOP/s, measured live
+    ctx_sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     flop_launch = FLOP_PER_PATH * paths_local + FLOP_PER_SEGMENT * segs_local
     achieved_tf = flop_launch / (kern_ms * 1e-3) / 1e12
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = rows * W * 3 * 8 + P * 3 * 8                            # the outputs; the scene is 0.4 KB
-    traffic = None
+    # DRAM bytes per launch come from an ncu capture (counters are not readable from inside the run); the capture
+    # records the hash of the kernel sources it was taken at and a figure from other sources is NOT reported
+    traffic, traffic_note = None, "no ncu capture for this workload under profiles/"
     prof = ROOT / "profiles" / "ncu_render_kernel.json"
     if prof.exists():
         try:
-            pj = json.loads(prof.read_text())
-            key = f"{a.precision}_{W}x{H}_{spp}spp_b{B}"
-            traffic = pj.get(key, {}).get("dram_bytes_per_launch")
+            ent = json.loads(prof.read_text()).get(f"{a.precision}_{W}x{H}_{spp}spp_b{B}", {})
+            if ent.get("source_sha") == kernel_source_sha():
+                traffic, traffic_note = ent.get("dram_bytes_per_launch"), f"ncu --set full, {ent.get('source')}"
+            elif ent:
+                traffic_note = (f"stale: {ent.get('source')} was captured at kernel sources {ent.get('source_sha')}, "
+                                f"this build is {kernel_source_sha()} (tools/ncu_traffic.sh regenerates it)")
         except Exception:
             pass
+    nominal_tf = ctx_sm_count * (64 if a.precision == "f64" else 128) * 2 * 1.965e9 / 1e12
     roofline = {
         "bound": "fma_" + a.precision, "kernel": "render_kernel",
         "achieved": achieved_tf, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved_tf / fma_peak,
-        "traffic": traffic,
+        "traffic": traffic, "traffic_source": traffic_note,
         "peak_source": "measured live: drtb_fma_peak (dependent-free FMA chains, all SMs); "
                        "MEASURED_PEAKS.json has no non-tensor FMA figure",
+        "peak_nominal": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf,
+        "peak_nominal_source": f"{ctx_sm_count} SMs x {64 if a.precision == 'f64' else 128} FMA/clk x 2 x 1.965 GHz",
         "algorithmic_flop_per_launch": flop_launch, "kernel_ms": kern_ms,
         "hbm": {"bound": "hbm", "achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
@@ -380,20 +570,23 @@ def run_b200_arm(a):
         "config": {"workload": workload_name(a), "width": W, "height": H, "spp": spp, "bounces": B,
                    "paths_per_step": int(paths_total), "segments_per_path": segs_total / paths_total,
                    "lit_path_fraction": lit_total / paths_total,
-                   "parallelism": f"pixel-band dp{world} (bands of {band} rows), 1 NCCL all-reduce of {P * 3} doubles",
-                   "image_gather": gather,
+                   "parallelism": f"pixel-band dp{world} (bands of {band} rows)",
+                   "image_gather": gather, "gradient_sum": grad_sum,
                    "l2": "flushed between timed iterations (256 MiB memset, untimed)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "drtb_set_params + drtb_render (host buffers, pinned)"},
+                "api": e2e_api, "assembled_image_on_rank0": e2e_check},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
     }
 
+    if world == 1 and not a.no_extras:
+        out.update(extra_blocks(a, drt, ctx, scene, torch, dev, hbm_peak))
     if world == 1 and not a.no_cpu_baseline:
         kind, nthr, sample, step = cpu_render_rate(a, seconds_budget=12.0)
         p, dt = step()
-        out["cpu_baseline"] = {"value": p / dt / 1e6, "unit": UNIT, "cores": nthr, "kind": kind, "sample": sample}
+        out["cpu_baseline"] = {"value": p / dt / 1e6, "unit": UNIT, "cores": nthr, "kind": kind, "sample": sample,
+                               "one_core_as_shipped": cpu_one_core_as_shipped(a)}
     print(json.dumps(out), file=_REAL_STDOUT, flush=True)
     ctx.close()
     if world > 1:

@@ -92,10 +92,20 @@ SYMBOLS = [
     ("drtb_render_grad_image_device", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), C.c_int32, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("drtb_set_image_peers", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]),
+    ("drtb_grad_exchange_bytes", C.c_size_t, [C.c_int32, C.c_int32]),
+    ("drtb_set_grad_peers", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
     ("drtb_ipc_alloc", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
     ("drtb_ipc_open", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("drtb_ipc_close", C.c_int, [C.c_void_p, C.c_void_p]),
     ("drtb_ipc_free", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("drtb_multi_create", C.c_int, [C.POINTER(C.c_int), C.c_int32, C.POINTER(C.c_void_p)]),
+    ("drtb_multi_destroy", None, [C.c_void_p]),
+    ("drtb_multi_last_error", C.c_char_p, [C.c_void_p]),
+    ("drtb_multi_device_count", C.c_int32, [C.c_void_p]),
+    ("drtb_multi_scene_upload", C.c_int, [C.c_void_p, C.POINTER(Scene)]),
+    ("drtb_multi_mesh_upload", C.c_int, [C.c_void_p, C.POINTER(Mesh)]),
+    ("drtb_multi_set_params", C.c_int, [C.c_void_p, _dp, C.c_int32]),
+    ("drtb_multi_render", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), _dp, _dp, _dp, C.POINTER(Stats)]),
     ("drtb_trace_rays", C.c_int, [C.c_void_p, C.POINTER(RenderOpts), C.c_int64, _dp, _dp,
                                   C.POINTER(C.c_uint64), _dp, _dp]),
     ("drtb_fma_peak", C.c_int, [C.c_void_p, C.c_int32, _dp]),

@@ -18,7 +18,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libdrtb.so"
 # one translation unit per kernel group, compiled in parallel (host.hpp says what each one exports)
-SOURCES = [CSRC / "drtb.cu", CSRC / "render_f64.cu", CSRC / "render_f32.cu", CSRC / "mesh.cu"]
+SOURCES = [CSRC / "drtb.cu", CSRC / "render_f64.cu", CSRC / "render_f32.cu", CSRC / "mesh.cu", CSRC / "multi.cu"]
 HEADERS = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.hpp")) + [ROOT / "include" / "drtb.h"]
 OBJ = PKG / "lib" / "obj"
 

@@ -49,6 +49,49 @@ reduce_grad_kernel(const double* __restrict__ partial, int n_rows, int rows_per_
     }
 }
 
+// Sum of the gradients of the GPUs of one NVSwitch box WITHOUT a collective library: every rank stores its P3
+// doubles into slot `rank` of the exchange buffer of EVERY rank (peer stores over NVLink), then a flag; waits until
+// the flags of all ranks have arrived in its OWN buffer; and adds the slots in rank order -- the same bits on every
+// rank.  One 1-block launch behind reduce_grad_kernel, where ncclAllReduce of these 96 bytes cost ~0.1 ms of
+// latency per render at 8 GPUs.
+//   exchange buffer of a rank: [2 parities][n][P3] doubles, then n 64-bit flags (zero-initialised)
+// Slots alternate between two parities per call (`epoch`), so a fast rank's stores of call e + 1 never land on
+// the slots a slow rank is still adding for call e; it cannot reach call e + 2 before the slow rank has set its
+// flag for e + 1, i.e. finished e.  A rank that never arrives (its render failed) is given ~2 s, then the sums
+// are poisoned with NaN instead of hanging the GPU.
+struct GradPeers { double* buf[kMaxPeers]; };
+__global__ void __launch_bounds__(256)
+grad_allreduce_kernel(const __grid_constant__ GradPeers peers, int n, int rank, int P3, unsigned long long epoch, double* grad)
+{
+    __shared__ int s_timeout;
+    if (threadIdx.x == 0) s_timeout = 0;
+    const size_t parity = size_t(epoch & 1ull) * n * P3;
+    for (int i = threadIdx.x; i < n * P3; i += blockDim.x) {
+        const int peer = i / P3, j = i - peer * P3;
+        peers.buf[peer][parity + size_t(rank) * P3 + j] = grad[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < n) {
+        unsigned long long* theirs = reinterpret_cast<unsigned long long*>(peers.buf[threadIdx.x] + size_t(2) * n * P3);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(theirs + rank), "l"(epoch) : "memory");
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peers.buf[rank] + size_t(2) * n * P3) + threadIdx.x;
+        const long long t0 = clock64();
+        unsigned long long seen = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+            if (seen >= epoch) break;
+            if (clock64() - t0 > 4000000000ll) { s_timeout = 1; break; }
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < P3; j += blockDim.x) {
+        double v = 0.0;
+        for (int r = 0; r < n; ++r) v += peers.buf[rank][parity + size_t(r) * P3 + j];
+        grad[j] = s_timeout ? __longlong_as_double(0x7ff8000000000000ll) : v;
+    }
+}
+
 // Pathtracer<T>::trace(scene, orig, dir) for user-supplied rays (pathtracer.hpp:121-136).
 template <typename R, bool MESH>
 __global__ void __launch_bounds__(kBlock)
@@ -108,6 +151,7 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(R* out, int iters, R a, R
 namespace {
 
 thread_local std::string g_create_err;
+constexpr int kMaxExchangeP3 = 4096;      // gradient scalars the peer exchange (grad_allreduce_kernel) serves
 
 template <typename R>
 void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
@@ -379,8 +423,29 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
 // fresh samples for the backward pass): the image comes from stream `seed`, the
 // gradients from stream `adjoint_seed`.  With a counter-based RNG that is simply
 // a second, gradient-only launch keyed differently.
+int launch_render_local(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed, double* d_img,
+                        double* d_grad, drtb_stats* d_stats, const GradImage& gi, cudaStream_t stream);
+
+// One render of this GPU's shard and, with drtb_set_grad_peers, the sum of the gradients over the GPUs of the job.
 int launch_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed, double* d_img,
                   double* d_grad, drtb_stats* d_stats, const GradImage& gi, cudaStream_t stream)
+{
+    const int P3 = int(ctx->params.size());
+    const bool exchange = ctx->n_grad_peers > 1 && (o->flags & DRTB_FLAG_GRAD) && P3 > 0;
+    if (exchange && P3 > kMaxExchangeP3)
+        return fail(ctx, DRTB_ERR_UNSUPPORTED, "the peer gradient exchange serves up to 4096 gradient scalars; use a collective library for more");
+    int rc = launch_render_local(ctx, o, d_seed, d_img, d_grad, d_stats, gi, stream);
+    if (rc != DRTB_OK || ctx->dry || !exchange) return rc;
+    GradPeers gp{};
+    for (int p = 0; p < ctx->n_grad_peers; ++p) gp.buf[p] = ctx->grad_peers[p];
+    grad_allreduce_kernel<<<1, 256, 0, stream>>>(gp, ctx->n_grad_peers, ctx->grad_rank, P3, ++ctx->grad_epoch, d_grad);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    return DRTB_OK;
+}
+
+int launch_render_local(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed, double* d_img,
+                        double* d_grad, drtb_stats* d_stats, const GradImage& gi, cudaStream_t stream)
 {
     if (gi.d_out) {
         if (!(o->flags & DRTB_FLAG_GRAD)) return fail(ctx, DRTB_ERR_INVALID, "a gradient image needs DRTB_FLAG_GRAD");
@@ -703,6 +768,26 @@ int drtb_set_image_peers(drtb_ctx* ctx, double* const* full_images, int32_t n)
     return DRTB_OK;
 }
 
+size_t drtb_grad_exchange_bytes(int32_t n_ranks, int32_t n_params)
+{
+    if (n_ranks < 1 || n_ranks > kMaxPeers || n_params < 0) return 0;
+    return (size_t(2) * n_ranks * n_params * 3 + n_ranks) * sizeof(double);
+}
+
+int drtb_set_grad_peers(drtb_ctx* ctx, void* const* exchange, int32_t n, int32_t rank)
+{
+    if (!ctx) return DRTB_ERR_INVALID;
+    if (n < 0 || n > kMaxPeers) return fail(ctx, DRTB_ERR_INVALID, "between 0 and 8 gradient peers");
+    if (n > 0 && (!exchange || rank < 0 || rank >= n)) return fail(ctx, DRTB_ERR_INVALID, "exchange is NULL or rank out of range");
+    for (int p = 0; p < n; ++p)
+        if (!exchange[p]) return fail(ctx, DRTB_ERR_INVALID, "an exchange buffer pointer is NULL");
+    for (int p = 0; p < kMaxPeers; ++p) ctx->grad_peers[p] = p < n ? static_cast<double*>(exchange[p]) : nullptr;
+    ctx->n_grad_peers = n;
+    ctx->grad_rank = rank;
+    ctx->grad_epoch = 0;
+    return DRTB_OK;
+}
+
 int drtb_ipc_alloc(drtb_ctx* ctx, size_t bytes, void** d_ptr, void* handle)
 {
     if (!ctx) return DRTB_ERR_INVALID;
@@ -711,6 +796,7 @@ int drtb_ipc_alloc(drtb_ctx* ctx, size_t bytes, void** d_ptr, void* handle)
     CK(ctx, cudaSetDevice(ctx->device));
     void* p = nullptr;
     CK(ctx, cudaMalloc(&p, bytes));
+    if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaFree(p); return fail(ctx, DRTB_ERR_CUDA, "cudaMemset of the shared allocation failed"); }
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, p);
     if (e != cudaSuccess) { cudaFree(p); return fail(ctx, DRTB_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }

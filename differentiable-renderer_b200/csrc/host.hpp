@@ -73,6 +73,9 @@ struct drtb_ctx {
     unsigned long long* d_task_counter = nullptr;
     double* img_peers[drtb::kMaxPeers] = {};   // drtb_set_image_peers: full images the render kernel fills directly
     int n_img_peers = 0;
+    double* grad_peers[drtb::kMaxPeers] = {};  // drtb_set_grad_peers: every rank's gradient exchange buffer
+    int n_grad_peers = 0, grad_rank = 0;
+    unsigned long long grad_epoch = 0;         // calls of the exchange so far (all ranks count alike)
     size_t l2_persist_max = 0;    // cudaDevAttrMaxPersistingL2CacheSize, reserved at create (0: not supported)
     size_t l2_window_max = 0;     // cudaDevAttrMaxAccessPolicyWindowSize
     // Preparation pass (drtb_reserve, and drtb_render before it starts its timer): every scratch buffer is

@@ -144,6 +144,16 @@ class Context:
         arr = (C.c_void_p * max(n, 1))(*[int(p) for p in full_images])
         self._check(self._lib.drtb_set_image_peers(self._h, arr, n))
 
+    def set_grad_peers(self, exchange, rank: int = 0):
+        """drtb_set_grad_peers: device addresses of every rank's gradient exchange buffer (rank order); renders
+        with FLAG_GRAD then return the sum over the ranks.  An empty list switches it off."""
+        n = len(exchange)
+        arr = (C.c_void_p * max(n, 1))(*[int(p) for p in exchange])
+        self._check(self._lib.drtb_set_grad_peers(self._h, arr, n, int(rank)))
+
+    def grad_exchange_bytes(self, n_ranks: int) -> int:
+        return int(self._lib.drtb_grad_exchange_bytes(int(n_ranks), int(self.scene.n_params)))
+
     def ipc_alloc(self, nbytes: int):
         """(device address, 64-byte handle) of memory a peer process can map."""
         ptr = C.c_void_p()

@@ -124,3 +124,35 @@ class PeerImage:
         self._dist.barrier()
         self.ctx.ipc_free(self.local_ptr)
         self.ctx = None
+
+
+class PeerGrad:
+    """The gradient sum over the ranks without a collective library (drtb_set_grad_peers): every rank allocates a
+    small exchange buffer (zero-filled by `ctx.ipc_alloc`), the IPC handles travel through
+    `dist.all_gather_object`, and from then on every render with FLAG_GRAD on `ctx` ends with a one-block kernel
+    that stores this rank's gradients into all ranks' buffers over NVLink, waits for theirs and adds them in rank
+    order -- `grad` comes back summed over the job, bit-identical on every rank.  Host-side plumbing only."""
+
+    def __init__(self, ctx, dist):
+        self.ctx = ctx
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.nbytes = ctx.grad_exchange_bytes(self.world)
+        self.local_ptr, handle = ctx.ipc_alloc(self.nbytes)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle)
+        self.ptrs = [self.local_ptr if r == self.rank else ctx.ipc_open(handles[r]) for r in range(self.world)]
+        dist.barrier()                                   # every buffer is zeroed and mapped before the first exchange
+        ctx.set_grad_peers(self.ptrs, self.rank)
+        self._dist = dist
+
+    def close(self):
+        """Collective: every rank unmaps its peers before anyone frees."""
+        if self.ctx is None:
+            return
+        self.ctx.set_grad_peers([])
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                self.ctx.ipc_close(p)
+        self._dist.barrier()
+        self.ctx.ipc_free(self.local_ptr)
+        self.ctx = None

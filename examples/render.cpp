@@ -34,6 +34,7 @@ struct Args {
     double absorb_prob = 0.5;
     std::string output;
     bool f32 = false;
+    int gpus = 1;              // --gpus N (NEW): spread the image bands over N GPUs of one box
 };
 
 static bool parse_args(int argc, const char* argv[], Args* a)
@@ -42,6 +43,7 @@ static bool parse_args(int argc, const char* argv[], Args* a)
     for (int i = 1; i < argc; ++i) {
         const char* f = argv[i];
         if (!std::strcmp(f, "--f32")) { a->f32 = true; continue; }
+        if (!std::strcmp(f, "--gpus") && i + 1 < argc) { a->gpus = int(std::strtol(argv[++i], nullptr, 10)); continue; }
         if (i + 1 >= argc) { std::fprintf(stderr, "PARSE ERROR: missing value for %s\n", f); return false; }
         const char* v = argv[++i];
         if (is(f, "-x", "--width")) a->width = std::strtoull(v, nullptr, 10);
@@ -115,6 +117,7 @@ int main(int argc, const char* argv[])
     drtb_stats st{};
     RenderOptions opt;
     opt.precision = args.f32 ? DRTB_F32 : DRTB_F64;
+    for (int g = 0; g < args.gpus; ++g) opt.devices.push_back(g);     // --gpus N: image bands over N GPUs of the box
     opt.stats = &st;
     try {
         render(scene, cam, tracer, args.samples, img.data(), opt);

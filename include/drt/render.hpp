@@ -28,6 +28,9 @@ struct RenderOptions {
     std::uint64_t adjoint_stream = 0;              // != 0: decorrelated adjoint (fresh samples in backward)
     int precision = DRTB_F64;                      // DRTB_F64 (parity) | DRTB_F32 (throughput)
     int device = 0;
+    // More than one entry: the image rows are spread over these GPUs of one box (bands of 8 rows), the image is
+    // assembled on the first and the gradients are summed over all of them (drtb_multi_render).  Same results.
+    std::vector<int> devices;
     drtb_stats* stats = nullptr;
     // Per-pixel gradient image (README.md:138-145): if grad_image != nullptr it receives, per
     // pixel, the share of grad_image_of.grad() that the pixel's samples contributed (w*h entries).
@@ -64,8 +67,16 @@ void render(const Scene<T>& scene, const Camera<T>& cam, const Pathtracer<T>& tr
             if (flat.handles[k].id() == h.id()) gparam = int(k);
         if (gparam < 0) throw std::runtime_error("drt::render: grad_image_of is not a parameter of this scene");
     }
-    {
-        gpu::Device& dev = gpu::device(opt.device);
+    if (opt.devices.size() > 1) {
+        if (opt.grad_image) throw std::runtime_error("drt::render: grad_image is a single-device call");
+        gpu::MultiDevice& md = gpu::multi_device(opt.devices);
+        std::lock_guard<std::mutex> g(md.lock);
+        md.sync(flat, c);
+        md.check("drtb_multi_render",
+                 drtb_multi_render(md.handle(), &o, reinterpret_cast<const double*>(opt.seed_image),
+                                   reinterpret_cast<double*>(img), opt.gradients ? grad.data() : nullptr, opt.stats));
+    } else {
+        gpu::Device& dev = gpu::device(opt.devices.size() == 1 ? opt.devices[0] : opt.device);
         std::lock_guard<std::mutex> g(dev.lock);
         dev.sync(flat, c);
         if (opt.grad_image)

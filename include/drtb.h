@@ -279,8 +279,23 @@ int drtb_reserve(drtb_ctx* ctx, const drtb_render_opts* opts);
  * the full images and alternates drtb_set_image_peers). */
 int drtb_set_image_peers(drtb_ctx* ctx, double* const* full_images, int32_t n);
 
+/* ---- multi-GPU: the gradient sum without a collective library ----------------
+ * north_star asks for "one NCCL allreduce" of each GPU's parameter gradients.  For the Cornell box that is 96
+ * bytes, and its cost is pure latency (~0.1 ms per render at 8 GPUs, a third of a 256 x 256 render).  Since every
+ * GPU of the box can store into every other GPU's memory, the library can do the sum itself: every rank allocates
+ * an exchange buffer of drtb_grad_exchange_bytes(n, n_params) bytes, ZERO-INITIALISED (cudaMemset), shares it
+ * (drtb_ipc_alloc / drtb_ipc_open across processes, plain peer access within one), and hands the rank-ordered list
+ * to its context.  From then on every render with DRTB_FLAG_GRAD ends with a one-block kernel that stores this
+ * rank's gradients into all buffers, waits for the other ranks' and adds them in rank order: `grad` holds the SUM
+ * over the job, bit-identical on every rank, and that kernel is also what orders "every rank's image stores have
+ * landed" (drtb_set_image_peers).  All ranks must issue the same sequence of such renders (it is a collective);
+ * a rank that never arrives poisons the sums with NaN after ~2 s instead of hanging the GPUs.  Up to 4096
+ * gradient scalars (mesh scenes with per-triangle parameters keep the collective library).  n = 0 switches it off. */
+size_t drtb_grad_exchange_bytes(int32_t n_ranks, int32_t n_params);
+int drtb_set_grad_peers(drtb_ctx* ctx, void* const* exchange, int32_t n, int32_t rank);
+
 /* Device memory that another process on the same box can map (CUDA IPC, one
- * process per GPU).  drtb_ipc_alloc: cudaMalloc on ctx's device + its
+ * process per GPU).  drtb_ipc_alloc: cudaMalloc on ctx's device, zero-filled, + its
  * DRTB_IPC_HANDLE_BYTES-byte handle, to be sent to the peers by the host's own
  * means; drtb_ipc_open: map a peer's handle into this process (peer access is
  * enabled on demand); drtb_ipc_close / drtb_ipc_free undo them. */
@@ -289,6 +304,32 @@ int drtb_ipc_alloc(drtb_ctx* ctx, size_t bytes, void** d_ptr, void* handle);
 int drtb_ipc_open(drtb_ctx* ctx, const void* handle, void** d_ptr);
 int drtb_ipc_close(drtb_ctx* ctx, void* d_ptr);
 int drtb_ipc_free(drtb_ctx* ctx, void* d_ptr);
+
+/* ---- multi-GPU in one process -------------------------------------------------
+ * The GPUs of one NVSwitch box behind ONE handle: what a C or C++ caller of the drop-in headers uses to reach
+ * them (drt::RenderOptions::devices, `build/render --gpus N`); a job with one process per GPU uses the shard_*
+ * fields of drtb_render_opts with drtb_set_image_peers / drtb_set_grad_peers instead.  Every call mirrors its
+ * single-device namesake; the scene is uploaded to (and a mesh's BVH built on) every device.
+ * drtb_multi_render replaces the pixel loop of src/render.cpp:72-86 like drtb_render does:
+ *   opts     : shard_index / shard_count are set by the library (band b of band_rows rows -> device b mod n;
+ *              band_rows <= 0 means 8)
+ *   seed_img : NULL or the FULL H*W*3 per-pixel adjoint seed
+ *   img      : the FULL H*W*3 image.  Analytic scenes: every device's kernel stores its pixels into the full
+ *              image on the first device over NVLink, which then leaves in one copy; mesh scenes (and devices
+ *              without peer access): each device's bands are copied to their rows
+ *   grad     : n_params*3 doubles, the SUM over the devices (added on the host in device order)
+ *   stats    : NULL or the totals over the devices; kernel_ms = the slowest device's
+ * Blocking; one host thread at a time per handle. */
+typedef struct drtb_multi drtb_multi;
+int drtb_multi_create(const int* devices, int32_t n, drtb_multi** out);      /* 1 <= n <= 8, distinct devices */
+void drtb_multi_destroy(drtb_multi* m);
+const char* drtb_multi_last_error(const drtb_multi* m);                       /* m == NULL: last create error */
+int32_t drtb_multi_device_count(const drtb_multi* m);
+int drtb_multi_scene_upload(drtb_multi* m, const drtb_scene* scene);
+int drtb_multi_mesh_upload(drtb_multi* m, const drtb_mesh* mesh);
+int drtb_multi_set_params(drtb_multi* m, const double* params, int32_t n_params);
+int drtb_multi_render(drtb_multi* m, const drtb_render_opts* opts, const double* seed_img, double* img, double* grad,
+                      drtb_stats* stats);
 
 /* drtb_render plus the PER-PIXEL gradient image of ONE parameter (the figure of
  * README.md:138-145, "gradients of the pixel colors with respect to the

@@ -137,6 +137,38 @@ int main(int argc, char**)
     try { gpu::flatten(bad_scene); } catch (const std::runtime_error&) { threw = true; }
     CHECK(threw);
 
+    // ---- Triangle<T> (new shape): host intersect with the rules of include/drtb.h, flattening into one drtb_mesh
+    {
+        auto tri_mat = std::make_shared<DiffuseBxDF<double>>(albedo);
+        Triangle<double> tri(V{0, 0, 2}, V{1, 0, 2}, V{0, 1, 2}, tri_mat);
+        double tt = -1;
+        CHECK(tri.intersect(V{0.25, 0.25, 0}, V{0, 0, 1}, tt) && tt == 2.0);
+        CHECK(tri.intersect(V{0, 0, 0}, V{0, 0, 1}, tt));                      // a vertex: inclusive bounds
+        CHECK(tri.intersect(V{0.5, 0.5, 0}, V{0, 0, 1}, tt));                  // the hypotenuse: u + v == 1
+        CHECK(!tri.intersect(V{0.6, 0.6, 0}, V{0, 0, 1}, tt));
+        CHECK(!tri.intersect(V{0.25, 0.25, 3}, V{0, 0, 1}, tt));               // behind the origin: t < 0
+        CHECK(tri.intersect(V{0.25, 0.25, 3}, V{0, 0, -1}, tt) && tt == 1.0);  // both sides are hit
+        CHECK(!tri.intersect(V{0.25, 0.25, 0}, V{1, 0, 0}, tt));               // parallel: det == 0
+        const V tn = tri.normal(V{0, 0, 2});
+        CHECK(tn[0] == 0 && tn[1] == 0 && tn[2] == 1);
+        Triangle<double> lamp_tri(V{0, 0, 5}, V{1, 0, 5}, V{0, 1, 5}, nullptr, lamp);
+        Scene<double> mesh_scene{&s0, &p0, &tri, &lamp_tri};
+        auto mf = gpu::flatten(mesh_scene);
+        CHECK(mf.prims.size() == 2 && mf.tri_indices.size() == 6 && mf.tri_vertices.size() == 18);
+        CHECK(mf.tri_vertices[3] == 1.0 && mf.tri_vertices[7] == 1.0 && mf.tri_vertices[2] == 2.0 && mf.tri_vertices[11] == 5.0);
+        CHECK(mf.tri_color[0] == mf.materials[0].color && mf.tri_color[1] == -1);
+        CHECK(mf.tri_emission[0] == -1 && mf.tri_emission[1] >= 0 && mf.tri_indices[5] == 5);
+        Scene<double> wrong_order{&tri, &s0};       // an analytic shape after a triangle would change the tie-break order
+        threw = false;
+        try { gpu::flatten(wrong_order); } catch (const std::runtime_error&) { threw = true; }
+        CHECK(threw);
+        Triangle<double> glossy_tri(V{0, 0, 2}, V{1, 0, 2}, V{0, 1, 2}, std::make_shared<SpecularBxDF<double>>(albedo, 10));
+        Scene<double> glossy_mesh{&glossy_tri};
+        threw = false;
+        try { gpu::flatten(glossy_mesh); } catch (const std::runtime_error&) { threw = true; }
+        CHECK(threw);
+    }
+
     // ---- no GPU => a loud exception, never a silent CPU render
     if (argc > 1 || drtb_device_count() == 0) {
         Pathtracer<double> tracer(0.5, 1);

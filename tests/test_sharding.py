@@ -74,6 +74,12 @@ class _FakeCtx:
     def set_image_peers(self, ptrs):
         self.peers = list(ptrs)
 
+    def set_grad_peers(self, ptrs, rank=0):
+        self.grad_peers, self.grad_rank = list(ptrs), rank
+
+    def grad_exchange_bytes(self, n_ranks):
+        return (2 * n_ranks * 12 + n_ranks) * 8
+
     def ipc_close(self, ptr):
         self.closed.append(ptr)
 
@@ -111,5 +117,36 @@ def test_peer_image_handle_exchange_on_two_gloo_ranks(tmp_path):
         want = [base[q] if q == r else base[q] + 1 for q in range(world)]
         assert z["peers"].tolist() == want and int(z["local"]) == base[r]
         assert int(z["nbytes"]) == 16 * 8 * 3 * 8 and z["shape"].tolist() == [16, 8, 3]
+        assert z["closed"].tolist() == [w for q, w in enumerate(want) if q != r]
+        assert z["freed"].tolist() == [base[r]] and int(z["after"]) == 0
+
+
+def _peer_grad_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from differentiable_renderer_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = _FakeCtx(rank)
+    pg = sharding.PeerGrad(ctx, dist)
+    peers, grank = list(ctx.grad_peers), ctx.grad_rank
+    pg.close()
+    np.savez(out + f".{rank}.npz", peers=np.array(peers, dtype=np.uint64), rank=grank, nbytes=pg.nbytes,
+             closed=np.array(ctx.closed, dtype=np.uint64), freed=np.array(ctx.freed, dtype=np.uint64), after=len(ctx.grad_peers))
+    dist.destroy_process_group()
+
+
+def test_peer_gradient_exchange_plumbing_on_two_gloo_ranks(tmp_path):
+    """Host logic of the NCCL-free gradient sum (sharding.PeerGrad): buffer size from the ABI, rank-ordered
+    pointer list with the own buffer by its local address, rank passed on, everything unmapped on close."""
+    import torch.multiprocessing as mp
+    world = 2
+    out = str(tmp_path / "g")
+    mp.spawn(_peer_grad_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        z = np.load(out + f".{r}.npz")
+        base = [0x7000_0000_0000 + q * 0x1000_0000 for q in range(world)]
+        want = [base[q] if q == r else base[q] + 1 for q in range(world)]
+        assert z["peers"].tolist() == want and int(z["rank"]) == r and int(z["nbytes"]) == (2 * 2 * 12 + 2) * 8
         assert z["closed"].tolist() == [w for q, w in enumerate(want) if q != r]
         assert z["freed"].tolist() == [base[r]] and int(z["after"]) == 0

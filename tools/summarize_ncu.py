@@ -74,6 +74,11 @@ if json_key:
         return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
     jf = out / "ncu_render_kernel.json"
     j = json.loads(jf.read_text()) if jf.exists() else {}
-    j[json_key] = {"dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+    import hashlib
+    hsh = hashlib.sha256()
+    for nm in ("render_kernels.cuh", "path.cuh", "real.cuh", "rng.cuh", "sinks.cuh"):     # = bench.py kernel_source_sha()
+        hsh.update((ROOT / "differentiable-renderer_b200" / "csrc" / nm).read_bytes())
+    j[json_key] = {"source_sha": hsh.hexdigest()[:16],
+                   "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
                    "kernel_ms_under_ncu": float(vals["gpu__time_duration.sum"][0]), "source": f"profiles/{name}_summary.txt"}
     jf.write_text(json.dumps(j, indent=1) + "\n")
