@@ -230,6 +230,24 @@ void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
     d.tan_half = R(std::tan(cam.vfov / 2.));                 // camera.hpp:56-57, host libm
     d.inv_w = R(1.0 / cam.width); d.inv_h = R(1.0 / cam.height);
     d.width = cam.width; d.height = cam.height;
+    // eye_clear (path.cuh, ClosestMargin): camera rays are unit vectors, so |t| >= |h| / |n| for a plane and
+    // >= | |eye - c| - r | for a sphere
+    d.eye_clear = 1;
+    for (int i = 0; i < d.n_prims; ++i) {
+        const drtb_prim& p = c.prims[i];
+        if (p.type == DRTB_PLANE) {
+            const double h = cam.eye[0] * p.v[0] + cam.eye[1] * p.v[1] + cam.eye[2] * p.v[2] - p.v[3];
+            const double nn = std::sqrt(p.v[0] * p.v[0] + p.v[1] * p.v[1] + p.v[2] * p.v[2]);
+            bool exact = h == 0.0;
+            for (int j = 0; j < 3; ++j)                     // ... and exactly so in float as well
+                exact = exact && double(float(cam.eye[j])) == cam.eye[j] && double(float(p.v[j])) == p.v[j];
+            exact = exact && double(float(p.v[3])) == p.v[3];
+            if (!exact && !(std::fabs(h) >= 2e-4 * nn)) d.eye_clear = 0;
+        } else {
+            const double ox = cam.eye[0] - p.v[0], oy = cam.eye[1] - p.v[1], oz = cam.eye[2] - p.v[2];
+            if (!(std::fabs(std::sqrt(ox * ox + oy * oy + oz * oz) - p.v[3]) >= 2e-4)) d.eye_clear = 0;
+        }
+    }
 }
 
 // How a render's units of work are cut into the chunks that warps claim from the global counter
@@ -307,8 +325,7 @@ int validate_opts(drtb_ctx* ctx, const drtb_render_opts* o)
     if (o->spp < 1) return fail(ctx, DRTB_ERR_INVALID, "spp must be >= 1");
     if (o->min_bounces < 0) return fail(ctx, DRTB_ERR_INVALID, "min_bounces must be >= 0");
     if (!(o->absorb >= 0.0 && o->absorb <= 1.0)) return fail(ctx, DRTB_ERR_INVALID, "absorb must be in [0, 1]");
-    if (o->precision == DRTB_MIXED) return fail(ctx, DRTB_ERR_UNSUPPORTED, "DRTB_MIXED is not implemented in this build");
-    if (o->precision != DRTB_F64 && o->precision != DRTB_F32) return fail(ctx, DRTB_ERR_INVALID, "unknown precision");
+    if (o->precision != DRTB_F64 && o->precision != DRTB_F32 && o->precision != DRTB_MIXED) return fail(ctx, DRTB_ERR_INVALID, "unknown precision");
     if (o->shard_count > 1 && (o->shard_index < 0 || o->shard_index >= o->shard_count || o->band_rows < 1))
         return fail(ctx, DRTB_ERR_INVALID, "bad shard (index, count, band_rows)");
     if (o->max_depth < 0 || o->max_depth > kMaxDepth)
@@ -362,7 +379,11 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     const bool gen = ctx->has_specular || want_gimg;
 
     const bool smallp = P <= kSmallP;
-    const bool f32 = o->precision == DRTB_F32;
+    // DRTB_MIXED: float pass + double re-trace of the close calls, where both kernels exist -- fixed-length paths
+    // (absorb == 1) on an all-diffuse analytic scene with <= kSmallP parameters, compact image.  Anything else
+    // renders in double, which meets the same promise (parity on every pixel) without the speed-up.
+    const bool mixed = o->precision == DRTB_MIXED && o->absorb >= 1.0 && !gen && smallp && !peers;
+    const bool f32 = o->precision == DRTB_F32 || mixed;
     // lit-path compaction needs whole-pixel warp tasks and records that fit the ring
     const bool queue = o->spp >= 32 && a.max_depth <= kQueueDepth;
     constexpr bool mesh = false;                  // mesh scenes took the wavefront above
@@ -412,9 +433,25 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     int rc;
     // Russian roulette on an all-diffuse analytic scene: the path-regenerating kernel
     const bool regen = o->absorb < 1.0 && !mesh && !gen && !ctx->no_regen;
-    const AnalyticLaunch l{smallp, queue_kind, gen, regen, smem, n_tasks, npix, P3, want_grad};
+    ctx->partial_extra_rows = 0;
+    if (mixed) {
+        const size_t cap = std::max<size_t>(size_t(1) << 16, size_t(npix) * size_t(o->spp) / 8);
+        if (cap > 0xffffffffull) return fail(ctx, DRTB_ERR_UNSUPPORTED, "DRTB_MIXED: more than 2^35 paths in one render");
+        if ((rc = ensure(ctx, ctx->d_retrace, ctx->retrace_cap, cap)) != DRTB_OK) return rc;
+        if (!ctx->d_retrace_count) CK(ctx, cudaMalloc((void**)&ctx->d_retrace_count, sizeof(unsigned int)));
+        a.retrace_list = ctx->d_retrace; a.retrace_count = ctx->d_retrace_count; a.retrace_cap = (unsigned int)cap;
+        if (!ctx->dry) CK(ctx, cudaMemsetAsync(ctx->d_retrace_count, 0, sizeof(unsigned int), stream));
+        ctx->partial_extra_rows = want_grad ? size_t(ctx->sm_count) * 4 : 0;
+    }
+    const AnalyticLaunch l{smallp, queue_kind, gen, regen, mixed, smem, n_tasks, npix, P3, want_grad};
     rc = f32 ? launch_analytic_f32(ctx, a, l, stream, partial_rows) : launch_analytic_f64(ctx, a, l, stream, partial_rows);
-    if (rc != DRTB_OK || ctx->dry) return rc;
+    if (rc != DRTB_OK) return rc;
+    if (mixed) {
+        size_t extra = 0;
+        if ((rc = launch_retrace_f64(ctx, a, P3, want_grad, partial_rows, stream, extra)) != DRTB_OK) return rc;
+        partial_rows += extra;
+    }
+    if (ctx->dry) return DRTB_OK;
     if (want_grad && (smallp || shared_atomic)) return reduce_partials(ctx, ctx->d_partial, partial_rows, P3, d_grad, stream);
     return DRTB_OK;
 }
@@ -550,6 +587,7 @@ void drtb_destroy(drtb_ctx* ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     cudaFree(ctx->d_params); cudaFree(ctx->d_partial); cudaFree(ctx->d_img); cudaFree(ctx->d_task_counter); cudaFree(ctx->d_ring);
+    cudaFree(ctx->d_retrace); cudaFree(ctx->d_retrace_count);
     cudaFree(ctx->d_seed); cudaFree(ctx->d_grad); cudaFree(ctx->d_gimg); cudaFree(ctx->d_stats); cudaFree(ctx->wf_mem);
     free_mesh(ctx);
     delete ctx;
@@ -687,13 +725,19 @@ int render_host(drtb_ctx* ctx, const drtb_render_opts* o, int32_t gparam, const 
     if (grad_img && npx3) CK(ctx, cudaMemcpyAsync(grad_img, ctx->d_gimg, sizeof(double) * npx3, cudaMemcpyDeviceToHost, st));
     if (stats) CK(ctx, cudaMemcpyAsync(stats, ctx->d_stats, sizeof(drtb_stats), cudaMemcpyDeviceToHost, st));
     CK(ctx, cudaStreamSynchronize(st));
+    if (o->precision == DRTB_MIXED && ((want_img && npx3 && std::isnan(img[0])) || (want_grad && P3 && std::isnan(grad[0])))) {
+        // more close calls than the re-trace list holds (the kernels poison the outputs rather than return them
+        // incomplete): render in double instead
+        drtb_render_opts exact = *o;
+        exact.precision = DRTB_F64;
+        return render_host(ctx, &exact, gparam, seed_img, img, grad, grad_img, stats);
+    }
     if (stats) {
         float ms = 0.f;
         CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         stats->kernel_ms = ms;
-#ifndef DRTB_TRAV_DEBUG                               // (the debug build of the traversal borrows these two fields)
+#ifndef DRTB_TRAV_DEBUG                               // (the debug build of the traversal borrows this field)
         stats->paths = uint64_t(rows) * W * o->spp;
-        stats->retraced_paths = 0;
 #endif
     }
     return DRTB_OK;

@@ -71,6 +71,9 @@ struct drtb_ctx {
     // wavefront buffers (mesh scenes), grown on demand
     void* wf_mem = nullptr;       size_t wf_cap = 0;
     unsigned long long* d_task_counter = nullptr;
+    unsigned long long* d_retrace = nullptr;  size_t retrace_cap = 0;     // DRTB_MIXED: (pixel, sample) of the paths to re-trace
+    unsigned int* d_retrace_count = nullptr;
+    size_t partial_extra_rows = 0;            // gradient partial rows the re-trace will append behind the float pass's
     double* img_peers[drtb::kMaxPeers] = {};   // drtb_set_image_peers: full images the render kernel fills directly
     int n_img_peers = 0;
     double* grad_peers[drtb::kMaxPeers] = {};  // drtb_set_grad_peers: every rank's gradient exchange buffer
@@ -182,6 +185,7 @@ struct AnalyticLaunch {
     int  queue;             // 0 no lit-path ring, 1 ring in shared memory, 2 ring in global memory
     bool gen;               // SpecularBxDF materials and / or a gradient image
     bool regen;             // Russian roulette on an all-diffuse scene: render_regen_kernel
+    bool mixed;             // DRTB_MIXED's float pass: close calls go on the re-trace list (float launcher only)
     size_t smem;            // dynamic shared memory of render_kernel
     long long n_tasks;      // warp tasks (render_kernel)
     long long npix;         // pixels of the shard (render_regen_kernel)
@@ -191,6 +195,8 @@ struct AnalyticLaunch {
 // Enqueue (or, with ctx->dry, prepare) the analytic-scene render; `rows` = gradient partial rows written.
 int launch_analytic_f64(drtb_ctx* ctx, drtb::RenderArgs& a, const AnalyticLaunch& l, cudaStream_t stream, size_t& rows);   // render_f64.cu
 int launch_analytic_f32(drtb_ctx* ctx, drtb::RenderArgs& a, const AnalyticLaunch& l, cudaStream_t stream, size_t& rows);   // render_f32.cu
+// DRTB_MIXED's second pass (render_f64.cu): re-traces the listed paths in double; its gradient rows follow row0.
+int launch_retrace_f64(drtb_ctx* ctx, drtb::RenderArgs& a, int P3, bool want_grad, size_t row0, cudaStream_t stream, size_t& rows_added);
 // Mesh scenes: the wavefront, batch by batch (mesh.cu).
 int launch_wavefront(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed, double* d_img, double* d_grad,
                      drtb_stats* d_stats, const GradImage& gi, cudaStream_t stream);

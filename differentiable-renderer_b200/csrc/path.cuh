@@ -69,6 +69,9 @@ struct alignas(16) DevScene {
     R aspect, tan_half;                  // W/H, tan(vfov/2)
     R inv_w, inv_h;                      // only used by the float instantiation
     int32_t width, height;
+    // DRTB_MIXED: 1 if every primitive either passes EXACTLY through the eye (its t is an exact 0 for every camera ray
+    // in float as in double, and is rejected by t > 0 in both) or stays clear of it by more than the near-zero margin
+    int32_t eye_clear;
 };
 
 
@@ -118,6 +121,10 @@ struct RenderArgs {
     int32_t  chunk_tasks;                // consecutive warp tasks per big chunk
     long long n_big_chunks, n_chunks;    // chunks [n_big_chunks, n_chunks) are single tasks (render_kernel)
     int32_t  small_chunk;                // ... or small_chunk pixels each (render_regen_kernel, whose tasks are pixels)
+    // DRTB_MIXED: paths whose float trace met a close call, as (pixel-in-shard * spp + sample), for the double re-trace
+    unsigned long long* retrace_list;
+    unsigned int* retrace_count;         // entries appended so far (may exceed retrace_cap: the excess is dropped AND reported)
+    unsigned int retrace_cap;
 };
 
 // Per-block shared copy of what is looked up with a PER-LANE index (the prim a
@@ -216,6 +223,55 @@ struct Closest<double, true> {
     }
 };
 
+// DRTB_MIXED: the closest hit in FLOAT that also says whether the decision was a close call.  A float path takes
+// the same sequence of primitives as the double path as long as no closest-hit decision along it could go the
+// other way; its radiance then differs by the float rounding of the weights only (~1e-6 relative after 8 vertices).
+// A decision is a close call if
+//   * the runner-up is within kGapAbs + kGapRel t of the winner (hit point within ~1e-3 of an edge or silhouette),
+//   * some primitive's t is within kNearZero of 0 (acceptance t > 0; a ray leaving a surface sits at |t| = 1e-3,
+//     the origin offset of pathtracer.hpp:99, a decade away),
+//   * a sphere's discriminant is within kDiscRel r^2 of 0 (hit / miss of a grazing ray), or
+//   * a plane is nearly parallel to the ray (|d.n| <= kParallel: t is huge or infinite either way).
+// The float evaluation error of t is ~1e-6 at scene scale 6 and the float path drifts from the double one by
+// ~1e-6 per plane bounce, one to two orders below these margins.  Two more things can part the two paths, and
+// trace_path watches both:
+//   * make_frame (bxdf.hpp:29-41) picks its helper axis by |n.x| < |n.y|: on a sphere whose normal has the two within
+//     kFrameGap of each other the float and the double frame may differ by a rotation -- a close call like the others;
+//   * DRIFT: a plane's frame is a constant, so the direction sampled off a plane carries only fresh rounding, but a
+//     sphere's normal is (hit point - centre) / r and turns a position error e into a direction error e / r, which
+//     the next segment multiplies by its length.  trace_path carries a bound (e_pos, e_dir) of the float path's
+//     distance from the double one and gives the path up once the bound at a hit exceeds kDriftMax (a tenth of the
+//     gap margin): in practice after three sphere bounces in a row.
+// Such a path is not used: its key goes on a list and a double kernel re-traces it (render_kernels.cuh, retrace_kernel).
+constexpr float kGapAbs = 1e-3f, kGapRel = 2e-4f, kNearZero = 1e-4f, kDiscRel = 1e-3f, kParallel = 1e-5f;
+constexpr float kFrameGap = 1e-3f, kDriftMax = 1e-4f, kRoundPos = 1e-6f, kRoundDir = 3e-7f;
+struct ClosestMargin {
+    static constexpr bool kMargin = true;
+    float bt, bt2, tz; int best; bool flag;       // tz = the largest t that was NOT accepted (t <= 0)
+    __device__ __forceinline__ ClosestMargin()
+        : bt(Real<float>::inf()), bt2(Real<float>::inf()), tz(-Real<float>::inf()), best(-1), flag(false) {}
+    __device__ __forceinline__ void offer(float t, int id)
+    {
+        const bool valid = t > 0.0f;
+        tz = valid ? tz : fmaxf(tz, t);                          // NaN (ray parallel to a plane through its origin) is dropped
+        const bool closer = valid & ((t < bt) | ((t == bt) & (id < best)));
+        bt2 = closer ? bt : (valid ? fminf(bt2, t) : bt2);
+        if (closer) { bt = t; best = id; }
+    }
+    // skip_zero: the caller knows that no primitive can be within kNearZero of t = 0 except exactly AT 0 (camera rays
+    // of a scene whose eye lies exactly on a plane, as the Cornell box's does: DevScene::eye_clear)
+    __device__ __forceinline__ int finish(float& tmin, bool skip_zero)
+    {
+        flag |= (bt2 - bt) < kGapAbs + kGapRel * bt;          // a miss (bt = inf) gives NaN: no flag
+        flag |= bt < kNearZero;
+        if (!skip_zero) flag |= tz > -kNearZero;
+        tmin = bt;
+        return best;
+    }
+};
+template <typename C> struct HasMargin { static constexpr bool value = false; };
+template <> struct HasMargin<ClosestMargin> { static constexpr bool value = true; };
+
 // Axis-aligned unit plane p_a = c: t = (c - o_a) / d_a, inv_a = 1 / d_a once per segment.
 template <typename R, typename C>
 __device__ __forceinline__ void axis_plane_test(const DevScene<R>& sc, int axis, int slot, R o_a, R inv_a, C& cl)
@@ -229,6 +285,7 @@ __device__ __forceinline__ void plane_test(const DevScene<R>& sc, int slot, V3<R
     const R a0 = sc.prim[slot][0], a1 = sc.prim[slot][1], a2 = sc.prim[slot][2], a3 = sc.prim[slot][3];
     const R h = Real<R>::fma(o.x, a0, Real<R>::fma(o.y, a1, Real<R>::fma(o.z, a2, -a3)));   // o.n - offset
     const R g = Real<R>::fma(d.x, a0, Real<R>::fma(d.y, a1, d.z * a2));                     // d.n ; t = h / -g
+    if constexpr (HasMargin<C>::value) cl.flag |= Real<R>::abs(g) <= kParallel;
     cl.offer(-h * Real<R>::rcp(g), sc.id[slot]);
 }
 
@@ -240,6 +297,7 @@ __device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<
     const R hb = dot(oc, d);                       // b/2
     const R c = Real<R>::fma(-a3, a3, dot(oc, oc));
     const R disc = Real<R>::fma(hb, hb, -c);       // (b^2 - 4c)/4, an exact rescaling
+    if constexpr (HasMargin<C>::value) cl.flag |= Real<R>::abs(disc) < kDiscRel * a3 * a3;
     const R sq = Real<R>::sqrt(disc);              // NaN when disc < 0: every compare below fails
     const R t1 = -hb - sq, t2 = sq - hb;           // t1 <= t2
     cl.offer(Real<R>::select(Real<R>::is_pos(t1), t1, t2), sc.id[slot]);
@@ -257,10 +315,13 @@ __device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<
 // immediate constant-bank addresses); larger scenes continue in rolled loops
 // with a warp-uniform slot.
 // ---------------------------------------------------------------------------
-template <typename R, bool PACK = false>
-__device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R> d, R& tmin)
+template <typename R, bool MARGIN> struct ClosestOf { template <bool PACK> using type = Closest<R, PACK>; };
+template <> struct ClosestOf<float, true> { template <bool PACK> using type = ClosestMargin; };
+template <typename R, bool PACK = false, bool MARGIN = false>
+__device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R> d, R& tmin, bool* close_call = nullptr,
+                                           bool skip_zero = false)
 {
-    Closest<R, PACK> cl;
+    typename ClosestOf<R, MARGIN>::template type<PACK> cl;
     // Entry into the straight-line tests by a compare tree on the (warp-uniform)
     // first live slot: ~6 instructions, where the compiler's jump table for the
     // equivalent switch cost ~20 per entry.
@@ -268,6 +329,7 @@ __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R>
 #define DRTB_AXIS(AX, OA, DA)                                                                  \
     if (sc.n_aa[AX] > 0) {                                                                      \
         const R inv = Real<R>::rcp(DA);                                                         \
+        if constexpr (HasMargin<decltype(cl)>::value) cl.flag |= Real<R>::abs(DA) <= kParallel;  \
         if (sc.n_aa[AX] > 1) axis_plane_test(sc, AX, 0, OA, inv, cl);                     \
         axis_plane_test(sc, AX, 1, OA, inv, cl);                                          \
     }
@@ -310,7 +372,13 @@ __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R>
 #undef DRTB_ENTER
     for (int i = 0; i < sc.n_over_spheres; ++i)
         sphere_test(sc, 2 * kFast + sc.n_over_planes + i, o, d, cl);
-    return cl.finish(tmin);
+    if constexpr (MARGIN) {
+        const int k = cl.finish(tmin, skip_zero);
+        *close_call = cl.flag;
+        return k;
+    } else {
+        return cl.finish(tmin);
+    }
 }
 
 // make_frame (bxdf.hpp:29-41) for a UNIT normal (spheres, triangles): with
@@ -453,7 +521,7 @@ template <typename R> struct Materials<R, true> {
     __device__ __forceinline__ R param(int i) const { return R(__ldg(params + i)); }
 };
 
-struct TraceCounters { uint32_t segments = 0, truncated = 0, bvh_nodes = 0, tri_tests = 0; };
+struct TraceCounters { uint32_t segments = 0, truncated = 0, bvh_nodes = 0, tri_tests = 0, close_call = 0; };
 
 // ---------------------------------------------------------------------------
 // Pathtracer::trace + scatter (pathtracer.hpp:91-136), recursion unrolled into
@@ -464,7 +532,9 @@ struct TraceCounters { uint32_t segments = 0, truncated = 0, bvh_nodes = 0, tri_
 // ---------------------------------------------------------------------------
 // SPEC: the scene has SpecularBxDF materials (per-lane material lookup and the
 // lobe code are compiled in; the all-diffuse kernels do not carry them).
-template <typename R, bool MESH, int CAP, bool SPEC = false>
+// MIXED (float, analytic, all-diffuse): every closest hit is checked for a close call (ClosestMargin); the first one
+// ends the trace with cnt.close_call = 1 and the caller hands the path to the double re-trace.
+template <typename R, bool MESH, int CAP, bool SPEC = false, bool MIXED = false>
 __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScene<R>& bs,
                                           const Materials<R, MESH>& mat, bool no_bvh,
                                           uint64_t base, uint32_t slot, V3<R> o, V3<R> d,
@@ -480,6 +550,7 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
     constexpr bool kSync = MESH || DRTB_SYNC_DEPTH;         // mesh kernels: the lanes must enter the BVH traversal together
     unsigned live = kSync ? __activemask() : 0u;
     bool alive = true;
+    float e_pos = 0.f, e_dir = kRoundDir;                   // MIXED: bound on the float path's drift from the double one
     uint64_t ctr = base + kGolden + slot;                  // splitmix64's increment folded in (rng.cuh)
     for (int depth = 0;; ++depth) {
         if constexpr (kSync) live = __ballot_sync(live, alive);
@@ -492,7 +563,14 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
         }
         if (n >= max_depth) { ++cnt.truncated; alive = false; continue; }
         R t;
-        int k = closest_hit<R, kPackHit && !MESH>(sc, o, d, t);   // analytic primitives
+        int k;
+        if constexpr (MIXED) {
+            bool close_call;
+            k = closest_hit<R, false, true>(sc, o, d, t, &close_call, depth == 0 && sc.eye_clear != 0);
+            if (close_call) { cnt.close_call = 1; alive = false; continue; }
+        } else {
+            k = closest_hit<R, kPackHit && !MESH>(sc, o, d, t);   // analytic primitives
+        }
         int tri = -1;
         if constexpr (MESH) {                               // then the mesh; analytic wins exact ties
             if (k < 0) t = Real<R>::inf();
@@ -529,12 +607,21 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
         }
         if (!on_mesh) {
             nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]};
-            if (bs.type[k] == DRTB_SPHERE) {                // shape.hpp:105-106
+            const bool sphere = bs.type[k] == DRTB_SPHERE;
+            if (sphere) {                                   // shape.hpp:105-106
                 nrm = normalize(V3<R>{pt.x - nrm.x, pt.y - nrm.y, pt.z - nrm.z});
                 unit_frame(nrm, tg, bt);
             } else {                                        // plane: constant frame, bxdf.hpp:29-41 on the host
                 tg = {bs.frame[k][0], bs.frame[k][1], bs.frame[k][2]};
                 bt = {bs.frame[k][3], bs.frame[k][4], bs.frame[k][5]};
+            }
+            if constexpr (MIXED) {                          // drift bound and the frame's axis switch (see ClosestMargin)
+                const float cosi = fmaxf(fabsf(float(dot(d, nrm))), 0.02f);
+                const float e_hit = (e_pos + float(t) * e_dir + kRoundPos * (1.0f + float(t))) / cosi;
+                const bool axis_call = sphere && fabsf(fabsf(float(nrm.x)) - fabsf(float(nrm.y))) < kFrameGap;
+                if (e_hit > kDriftMax || axis_call) { cnt.close_call = 1; alive = false; continue; }
+                e_pos = e_hit;
+                e_dir = sphere ? e_hit / float(bs.prim[k][3]) + kRoundDir : kRoundDir;
             }
         }
         R u_theta = Real<R>::uniform_fast(stream_draw_ctr(ctr));

@@ -41,7 +41,9 @@ using drtbh::reduce_scratch_rows;
 //   MESH  : a triangle mesh + BVH is attached (ids are 32-bit, parameters in global memory)
 //   GEN   : the general variant -- SpecularBxDF materials (bxdf.hpp:85-124) and the
 //           per-pixel gradient image; the all-diffuse kernels do not carry that code
-template <typename R, bool SMALLP, int QUEUE, bool MESH, bool GEN>
+//   MIXED : DRTB_MIXED's fast pass (float): a path whose trace met a close call (path.cuh, ClosestMargin) is not
+//           swept; its (pixel, sample) goes on a list that retrace_kernel re-traces in double
+template <typename R, bool SMALLP, int QUEUE, bool MESH, bool GEN, bool MIXED = false>
 __global__ void __launch_bounds__(kBlock, MESH ? DRTB_MESH_MIN_BLOCKS : sizeof(R) == 4 ? DRTB_MIN_BLOCKS_F32 : DRTB_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ RenderArgs a)
 {
@@ -158,7 +160,7 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
 
             for (int pass = 0; pass < passes; ++pass) {
                 const int i = i0 + pass * 32;
-                bool lit = false;
+                bool lit = false, close_call = false;
                 int n = 0;
                 PathRecord<R, MESH, QUEUE ? kQueueDepth : kMaxDepth> rec;
                 if (lane_ok && i < spp) {
@@ -166,9 +168,26 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                     const uint64_t base = key * kKeyMul;
                     V3<R> o = {sc.eye[0], sc.eye[1], sc.eye[2]};
                     V3<R> d = camera_ray(sc, x, y, base);
-                    n = trace_path<R, MESH, QUEUE ? kQueueDepth : kMaxDepth, GEN>(sc, bs, mat, no_bvh, base, 2u, o, d, a.min_bounces,
-                                                                                  a.absorb, a.max_depth, rec, lit, cnt);
+                    const uint32_t seg0 = cnt.segments;
+                    n = trace_path<R, MESH, QUEUE ? kQueueDepth : kMaxDepth, GEN, MIXED>(sc, bs, mat, no_bvh, base, 2u, o, d, a.min_bounces,
+                                                                                         a.absorb, a.max_depth, rec, lit, cnt);
+                    if constexpr (MIXED) {
+                        if (cnt.close_call) {               // this path belongs to the double re-trace, segments and all
+                            close_call = true; lit = false;
+                            cnt.close_call = 0; cnt.segments = seg0;
+                        }
+                    }
                     if (!QUEUE && lit) sweep(rec, n);
+                }
+                if constexpr (MIXED) {
+                    const unsigned cm = __ballot_sync(0xffffffffu, close_call);
+                    if (cm) {                               // one counter update per warp, entries in lane order
+                        unsigned int first = 0;
+                        if (lane == 0) first = atomicAdd(a.retrace_count, (unsigned int)__popc(cm));
+                        first = __shfl_sync(0xffffffffu, first, 0);
+                        const unsigned int at = first + __popc(cm & ((1u << lane) - 1u));
+                        if (close_call && at < a.retrace_cap) a.retrace_list[at] = (unsigned long long)pix * (unsigned long long)spp + (unsigned long long)i;
+                    }
                 }
                 if (QUEUE) {
                     const unsigned m = __ballot_sync(0xffffffffu, lit);
@@ -501,6 +520,112 @@ render_regen_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constan
     }
 }
 
+// DRTB_MIXED's second pass: the paths the float pass set aside, re-traced in double -- the same camera_ray /
+// trace_path / radiance_and_adjoint as the parity kernel, one lane per listed path.  Radiance is ADDED to the
+// pixel the float pass wrote (red.global.add.f64; a pixel rarely holds two such paths, so the order of these
+// additions matters in the last bit at most), gradients go through the per-thread shared columns into one partial
+// row per block behind the float pass's rows.  More close calls than the list holds (retrace_cap = 1/8 of the
+// paths; ~0.3 % are expected) cannot be served: the image and the gradients are poisoned with NaN rather than
+// returned incomplete (drtb_render re-renders in double when it sees that).
+template <typename R>
+__global__ void __launch_bounds__(kBlock)
+retrace_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ RenderArgs a, int partial_row0)
+{
+    static_assert(sizeof(R) == 8, "the re-trace is the double instantiation");
+    extern __shared__ double s_dyn[];
+    __shared__ BlockScene<R> bs;
+    __shared__ double s_red[kSmallP * 3][kWarpsPerBlock];
+    const bool want_grad = (a.flags & DRTB_FLAG_GRAD) != 0;
+    const int P3 = sc.n_params * 3;
+    double* s_acc = s_dyn;
+    load_block_scene(bs, sc, a.params);
+    for (int i = threadIdx.x; i < (want_grad ? P3 * kBlock : 0); i += kBlock) s_acc[i] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int listed = *a.retrace_count, n = min(listed, a.retrace_cap);
+    const int W = sc.width, spp = a.spp;
+    const R inv_p = a.absorb < 1.0 ? R(1.0 / (1.0 - a.absorb)) : R(0);
+    SmemSink ssink{s_acc + threadIdx.x};
+    Materials<R, false> mat;
+    mat.bs = &bs;
+    TraceCounters cnt;
+    uint32_t n_lit = 0;
+    for (unsigned int e = blockIdx.x * kBlock + threadIdx.x; e < n; e += gridDim.x * kBlock) {
+        const unsigned long long entry = a.retrace_list[e];
+        const long long pix = (long long)(entry / (unsigned long long)spp);
+        const int i = int(entry - (unsigned long long)pix * (unsigned long long)spp);
+        const int r = int(pix / W), x = int(pix - (long long)r * W);
+        const int y = a.shard_count > 1 ? ((r / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + r % a.band_rows : r;
+        const uint64_t key = a.key0 + ((uint64_t)y * W + x) * (uint64_t)spp + (uint64_t)i;
+        const uint64_t base = key * kKeyMul;
+        V3<R> o = {sc.eye[0], sc.eye[1], sc.eye[2]};
+        V3<R> d = camera_ray(sc, x, y, base);
+        PathRecord<R, false, kMaxDepth> rec;
+        bool lit;
+        const int nv = trace_path<R, false, kMaxDepth, false>(sc, bs, mat, false, base, 2u, o, d, a.min_bounces, a.absorb, a.max_depth, rec, lit, cnt);
+        if (!lit) continue;
+        R g0[3] = {R(0), R(0), R(0)}, L0[3];
+        if (want_grad) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) g0[c] = R(a.seed_scale * (a.seed_img ? a.seed_img[pix * 3 + c] : 1.0));
+        }
+        radiance_and_adjoint(mat, rec, nv, a.min_bounces, inv_p, want_grad, g0, L0, ssink);
+        n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
+        if (a.img) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) if (L0[c] != R(0)) atomicAdd(a.img + pix * 3 + c, double(L0[c]) / double(spp));
+        }
+    }
+    const bool overflow = listed > a.retrace_cap;
+    if (want_grad) {
+        __syncthreads();
+        for (int j = 0; j < P3; ++j) {
+            const double v = warp_sum(s_acc[j * kBlock + threadIdx.x]);
+            if (lane == 0) s_red[j][warp] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < P3) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarpsPerBlock; ++w) v += s_red[threadIdx.x][w];
+            a.grad_partial[((size_t)partial_row0 + blockIdx.x) * P3 + threadIdx.x] = overflow ? __longlong_as_double(0x7ff8000000000000ll) : v;
+        }
+    }
+    if (overflow && a.img && blockIdx.x == 0 && threadIdx.x < 3) a.img[threadIdx.x] = __longlong_as_double(0x7ff8000000000000ll);
+    if (a.stats) {
+        unsigned long long seg = cnt.segments, litp = n_lit;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { seg += __shfl_xor_sync(0xffffffffu, seg, o); litp += __shfl_xor_sync(0xffffffffu, litp, o); }
+        if (lane == 0) {
+            atomicAdd((unsigned long long*)&a.stats->segments, seg);
+            atomicAdd((unsigned long long*)&a.stats->lit_paths, litp);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.stats->retraced_paths = listed;
+    }
+}
+
+// Enqueue the re-trace behind the float pass: `row0` partial rows are taken; returns the rows it adds.
+template <typename R>
+int launch_retrace(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, int P3, bool want_grad, size_t row0, cudaStream_t stream,
+                   size_t& rows_added)
+{
+    const size_t smem = want_grad ? size_t(P3) * kBlock * sizeof(double) : 0;
+    CK(ctx, cudaFuncSetAttribute(retrace_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const int grid = ctx->sm_count * 4;
+    rows_added = want_grad ? size_t(grid) : 0;
+    if (ctx->dry) {
+        if (first_use(ctx, (const void*)retrace_kernel<R>)) {
+            cudaFuncAttributes fa;
+            CK(ctx, cudaFuncGetAttributes(&fa, retrace_kernel<R>));       // loads the kernel (lazy module loading)
+        }
+        return DRTB_OK;
+    }
+    retrace_kernel<R><<<grid, kBlock, smem, stream>>>(sc, a, int(row0));
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    return DRTB_OK;
+}
+
 // Resident blocks per SM of one render_kernel instantiation at `smem` dynamic bytes.
 template <typename K>
 int occupancy(drtb_ctx* ctx, K kernel, size_t smem, int& out)
@@ -513,12 +638,12 @@ int occupancy(drtb_ctx* ctx, K kernel, size_t smem, int& out)
     return DRTB_OK;
 }
 
-template <typename R, bool SMALLP, int QUEUE, bool MESH, bool GEN>
+template <typename R, bool SMALLP, int QUEUE, bool MESH, bool GEN, bool MIXED = false>
 int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t smem, long long n_tasks,
                    int P3, bool want_grad, cudaStream_t stream, size_t& rows_out)
 {
     int per_sm = 0;
-    int rc = occupancy(ctx, render_kernel<R, SMALLP, QUEUE, MESH, GEN>, smem, per_sm);
+    int rc = occupancy(ctx, render_kernel<R, SMALLP, QUEUE, MESH, GEN, MIXED>, smem, per_sm);
     if (rc != DRTB_OK) return rc;
     const long long need_blocks = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
     long long grid = (long long)ctx->sm_count * per_sm;
@@ -540,7 +665,8 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
     if (want_grad && SMALLP) rows = size_t(n_chunks);
     else if (want_grad && !MESH) rows = size_t(grid);
     if (rows) {
-        rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (rows + reduce_scratch_rows(rows)) * P3);
+        const size_t total = rows + (MIXED ? ctx->partial_extra_rows : 0);      // the re-trace's rows follow (launch_retrace)
+        rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (total + reduce_scratch_rows(total)) * P3);
         if (rc != DRTB_OK) return rc;
         a.grad_partial = ctx->d_partial;
     }
@@ -553,17 +679,17 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
     rows_out = rows;
     if (ctx->dry) {
         // first use of this instantiation: one launch on zero chunks (module load, local-memory reservation)
-        if (first_use(ctx, (const void*)render_kernel<R, SMALLP, QUEUE, MESH, GEN>)) {
+        if (first_use(ctx, (const void*)render_kernel<R, SMALLP, QUEUE, MESH, GEN, MIXED>)) {
             RenderArgs w = a;
             w.n_chunks = 0; w.stats = nullptr;
-            render_kernel<R, SMALLP, QUEUE, MESH, GEN><<<1, kBlock, smem, stream>>>(sc, w);
+            render_kernel<R, SMALLP, QUEUE, MESH, GEN, MIXED><<<1, kBlock, smem, stream>>>(sc, w);
             CK(ctx, cudaGetLastError());
             CK(ctx, cudaStreamSynchronize(stream));
         }
         return DRTB_OK;
     }
     CK(ctx, cudaMemsetAsync(ctx->d_task_counter, 0, sizeof(unsigned long long), stream));
-    render_kernel<R, SMALLP, QUEUE, MESH, GEN><<<int(grid), kBlock, smem, stream>>>(sc, a);
+    render_kernel<R, SMALLP, QUEUE, MESH, GEN, MIXED><<<int(grid), kBlock, smem, stream>>>(sc, a);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     return DRTB_OK;
@@ -624,6 +750,12 @@ int launch_analytic(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, const d
     if (l.regen)
         return l.smallp ? launch_regen<R, true>(ctx, sc, a, l.npix, l.P3, l.want_grad, stream, rows)
                         : launch_regen<R, false>(ctx, sc, a, l.npix, l.P3, l.want_grad, stream, rows);
+    if constexpr (sizeof(R) == 4) {
+        if (l.mixed)                                  // DRTB_MIXED's fast pass: all-diffuse, <= kSmallP parameters (drtb.cu)
+            return l.queue == 2 ? launch_variant<R, true, 2, false, false, true>(ctx, sc, a, l.smem, l.n_tasks, l.P3, l.want_grad, stream, rows)
+                 : l.queue == 1 ? launch_variant<R, true, 1, false, false, true>(ctx, sc, a, l.smem, l.n_tasks, l.P3, l.want_grad, stream, rows)
+                                : launch_variant<R, true, 0, false, false, true>(ctx, sc, a, l.smem, l.n_tasks, l.P3, l.want_grad, stream, rows);
+    }
 #define DRTB_LAUNCH(SP, Q, G) launch_variant<R, SP, Q, false, G>(ctx, sc, a, l.smem, l.n_tasks, l.P3, l.want_grad, stream, rows)
 #define DRTB_BY_QUEUE(SP, G) (l.queue == 2 ? DRTB_LAUNCH(SP, 2, G) : l.queue == 1 ? DRTB_LAUNCH(SP, 1, G) : DRTB_LAUNCH(SP, 0, G))
     // GEN: SpecularBxDF materials and/or a gradient image; the all-diffuse kernels do not carry that code

@@ -36,7 +36,7 @@ def triangle_room(drt):
              ((-3, -3, 0), (-3, -3, 6), (-3, 3, 6), (-3, 3, 0), wall_col), ((3, -3, 0), (3, 3, 0), (3, 3, 6), (3, -3, 6), floor_col)]
     verts, idx, cols = [], [], []
     for a, b, c, d, col in quads:
-        for tri in ((a, b, c), (a, c, d)):
+        for tri in ((a, c, b), (a, d, c)):
             base = len(verts)
             verts += [tri[0], tri[1], tri[2]]
             idx.append((base, base + 1, base + 2))
@@ -110,7 +110,11 @@ def test_multi_handle_through_the_c_abi_matches_one_device(drt, ctx):
             rc = lib.drtb_multi_render(m, C.byref(o2), seed_img.ctypes.data_as(dp), img.ctypes.data_as(dp),
                                        grad.ctypes.data_as(dp), C.byref(st))
             assert rc == 0, lib.drtb_multi_last_error(m)
-            assert np.array_equal(img, ref_img)
+            # Russian roulette: the regenerating kernel adds a pixel's lit samples in the order they finish, which depends
+            # on which pixels share a chunk -- and so on the sharding: equal up to the last bit, not bit for bit
+            bad_rows = np.nonzero((np.abs(img - ref_img) > 4e-16 * np.abs(ref_img)).any(axis=(1, 2)))[0]
+            assert bad_rows.size == 0, (f"{n} devices, mesh={mesh is not None}: rows {bad_rows.tolist()} differ, "
+                                        f"max |diff| {np.nanmax(np.abs(img - ref_img))}, NaNs {int(np.isnan(img).sum())}")
             assert np.abs(grad - ref_grad).max() <= 1e-11 * np.abs(ref_grad).max()
             assert st.paths == ref_st.paths and st.segments == ref_st.segments and st.lit_paths == ref_st.lit_paths
         bad = drt.make_opts(0, 3, 0.4)
