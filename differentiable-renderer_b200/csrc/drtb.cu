@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(R* out, int iters, R a, R
 namespace {
 
 thread_local std::string g_create_err;
+constexpr int kMixedMaxDepth = 8;         // DRTB_MIXED's float pass: deeper paths drift too far from the double path (path.cuh)
 constexpr int kMaxExchangeP3 = 4096;      // gradient scalars the peer exchange (grad_allreduce_kernel) serves
 
 template <typename R>
@@ -379,10 +380,11 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     const bool gen = ctx->has_specular || want_gimg;
 
     const bool smallp = P <= kSmallP;
-    // DRTB_MIXED: float pass + double re-trace of the close calls, where both kernels exist -- fixed-length paths
-    // (absorb == 1) on an all-diffuse analytic scene with <= kSmallP parameters, compact image.  Anything else
-    // renders in double, which meets the same promise (parity on every pixel) without the speed-up.
-    const bool mixed = o->precision == DRTB_MIXED && o->absorb >= 1.0 && !gen && smallp && !peers;
+    // DRTB_MIXED: float pass + double re-trace of the close calls, where both kernels exist and the float path stays
+    // close to the double one -- fixed-length paths (absorb == 1) of at most kMixedMaxDepth bounces on an all-diffuse
+    // analytic scene with <= kSmallP parameters, compact image.  Anything else renders in double, which meets the
+    // same promise (parity on every pixel) without the speed-up.
+    const bool mixed = o->precision == DRTB_MIXED && o->absorb >= 1.0 && a.max_depth <= kMixedMaxDepth && !gen && smallp && !peers;
     const bool f32 = o->precision == DRTB_F32 || mixed;
     // lit-path compaction needs whole-pixel warp tasks and records that fit the ring
     const bool queue = o->spp >= 32 && a.max_depth <= kQueueDepth;

@@ -237,34 +237,42 @@ struct Closest<double, true> {
 // trace_path watches both:
 //   * make_frame (bxdf.hpp:29-41) picks its helper axis by |n.x| < |n.y|: on a sphere whose normal has the two within
 //     kFrameGap of each other the float and the double frame may differ by a rotation -- a close call like the others;
-//   * DRIFT: a plane's frame is a constant, so the direction sampled off a plane carries only fresh rounding, but a
-//     sphere's normal is (hit point - centre) / r and turns a position error e into a direction error e / r, which
-//     the next segment multiplies by its length.  trace_path carries a bound (e_pos, e_dir) of the float path's
-//     distance from the double one and gives the path up once the bound at a hit exceeds kDriftMax (a tenth of the
-//     gap margin): in practice after three sphere bounces in a row.
+//   * DRIFT: the float path's hit points move away from the double path's, and what a margin has to cover is that
+//     distance, not just one segment's rounding.  trace_path carries a bound on it: at a hit at distance t under
+//     incidence cosine c the position bound becomes e' = (e_pos + t e_dir + rounding) / c (a displaced ray meets the
+//     surface up to 1 / c further along it); the direction sampled off a PLANE carries only fresh rounding (its
+//     frame is a constant), off a SPHERE of radius r it inherits e' / r (the normal is (hit point - centre) / r).
+//     Every margin of the next scan is widened by kDriftK times the bound carried to it (`slack`), so the close-call
+//     test scales with how far the two paths may already be apart; a bound beyond kDriftMax gives the path up.
+// These are engineering margins, not a proof: what is guaranteed is the re-trace of every path that trips one, and
+// what is TESTED is the outcome -- segment and lit-path counts equal to the double reference's and the parity bar at
+// BASELINE's sizes (tests/test_gpu_mixed.py: every pixel of full config 2 through its tile sums).
 // Such a path is not used: its key goes on a list and a double kernel re-traces it (render_kernels.cuh, retrace_kernel).
 constexpr float kGapAbs = 1e-3f, kGapRel = 2e-4f, kNearZero = 1e-4f, kDiscRel = 1e-3f, kParallel = 1e-5f;
-constexpr float kFrameGap = 1e-3f, kDriftMax = 1e-4f, kRoundPos = 1e-6f, kRoundDir = 3e-7f;
+constexpr float kFrameGap = 1e-3f, kDriftK = 2.0f, kDriftMax = 2e-2f, kRoundPos = 3e-7f, kRoundDir = 3e-7f;
 struct ClosestMargin {
     static constexpr bool kMargin = true;
-    float bt, bt2, tz; int best; bool flag;       // tz = the largest t that was NOT accepted (t <= 0)
+    float bt, bt2, ta, slack; int best; bool flag;   // ta = the smallest |t| any primitive returned, accepted or not; slack: see DRIFT
     __device__ __forceinline__ ClosestMargin()
-        : bt(Real<float>::inf()), bt2(Real<float>::inf()), tz(-Real<float>::inf()), best(-1), flag(false) {}
+        : bt(Real<float>::inf()), bt2(Real<float>::inf()), ta(Real<float>::inf()), slack(0.0f), best(-1), flag(false) {}
+    // Eight instructions per primitive (the plain float scan takes six): the two smallest accepted t by a min / max
+    // pair, the winner's id, and min |t|.  Exact ties need no index rule here: a tie is a close call by definition.
     __device__ __forceinline__ void offer(float t, int id)
     {
-        const bool valid = t > 0.0f;
-        tz = valid ? tz : fmaxf(tz, t);                          // NaN (ray parallel to a plane through its origin) is dropped
-        const bool closer = valid & ((t < bt) | ((t == bt) & (id < best)));
-        bt2 = closer ? bt : (valid ? fminf(bt2, t) : bt2);
-        if (closer) { bt = t; best = id; }
+        ta = fminf(ta, fabsf(t));                                // NaN (ray parallel to a plane through its origin) is dropped
+        const float tp = t > 0.0f ? t : Real<float>::inf();      // acceptance t > 0, shape.hpp:55, 91-99
+        bt2 = fminf(bt2, fmaxf(bt, tp));
+        best = tp < bt ? id : best;
+        bt = fminf(bt, tp);
     }
+    __device__ __forceinline__ void rejected(float t) { ta = fminf(ta, fabsf(t)); }   // a sphere's first root when it is <= 0
     // skip_zero: the caller knows that no primitive can be within kNearZero of t = 0 except exactly AT 0 (camera rays
     // of a scene whose eye lies exactly on a plane, as the Cornell box's does: DevScene::eye_clear)
     __device__ __forceinline__ int finish(float& tmin, bool skip_zero)
     {
-        flag |= (bt2 - bt) < kGapAbs + kGapRel * bt;          // a miss (bt = inf) gives NaN: no flag
-        flag |= bt < kNearZero;
-        if (!skip_zero) flag |= tz > -kNearZero;
+        flag |= (bt2 - bt) < kGapAbs + slack + kGapRel * bt;  // a miss (bt = inf) gives NaN: no flag
+        // (capped below 1e-3: a ray leaving a surface sees that surface at |t| = 1e-3 whatever the drift, pathtracer.hpp:99)
+        if (!skip_zero) flag |= ta < fminf(kNearZero + slack, 5e-4f);
         tmin = bt;
         return best;
     }
@@ -297,9 +305,10 @@ __device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<
     const R hb = dot(oc, d);                       // b/2
     const R c = Real<R>::fma(-a3, a3, dot(oc, oc));
     const R disc = Real<R>::fma(hb, hb, -c);       // (b^2 - 4c)/4, an exact rescaling
-    if constexpr (HasMargin<C>::value) cl.flag |= Real<R>::abs(disc) < kDiscRel * a3 * a3;
+    if constexpr (HasMargin<C>::value) cl.flag |= Real<R>::abs(disc) < kDiscRel * a3 * a3 + cl.slack * 4.0f * (Real<R>::abs(hb) + a3);
     const R sq = Real<R>::sqrt(disc);              // NaN when disc < 0: every compare below fails
     const R t1 = -hb - sq, t2 = sq - hb;           // t1 <= t2
+    if constexpr (HasMargin<C>::value) cl.rejected(t1);      // the root that is not offered must not be a near-zero either
     cl.offer(Real<R>::select(Real<R>::is_pos(t1), t1, t2), sc.id[slot]);
 }
 
@@ -319,9 +328,10 @@ template <typename R, bool MARGIN> struct ClosestOf { template <bool PACK> using
 template <> struct ClosestOf<float, true> { template <bool PACK> using type = ClosestMargin; };
 template <typename R, bool PACK = false, bool MARGIN = false>
 __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R> d, R& tmin, bool* close_call = nullptr,
-                                           bool skip_zero = false)
+                                           bool skip_zero = false, float slack = 0.0f)
 {
     typename ClosestOf<R, MARGIN>::template type<PACK> cl;
+    if constexpr (MARGIN) cl.slack = slack;
     // Entry into the straight-line tests by a compare tree on the (warp-uniform)
     // first live slot: ~6 instructions, where the compiler's jump table for the
     // equivalent switch cost ~20 per entry.
@@ -550,7 +560,7 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
     constexpr bool kSync = MESH || DRTB_SYNC_DEPTH;         // mesh kernels: the lanes must enter the BVH traversal together
     unsigned live = kSync ? __activemask() : 0u;
     bool alive = true;
-    float e_pos = 0.f, e_dir = kRoundDir;                   // MIXED: bound on the float path's drift from the double one
+    float e_pos = 0.f, e_dir = kRoundDir;                   // MIXED: bound on the float path's distance from the double one
     uint64_t ctr = base + kGolden + slot;                  // splitmix64's increment folded in (rng.cuh)
     for (int depth = 0;; ++depth) {
         if constexpr (kSync) live = __ballot_sync(live, alive);
@@ -566,7 +576,7 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
         int k;
         if constexpr (MIXED) {
             bool close_call;
-            k = closest_hit<R, false, true>(sc, o, d, t, &close_call, depth == 0 && sc.eye_clear != 0);
+            k = closest_hit<R, false, true>(sc, o, d, t, &close_call, depth == 0 && sc.eye_clear != 0, kDriftK * (e_pos + 4.0f * e_dir));
             if (close_call) { cnt.close_call = 1; alive = false; continue; }
         } else {
             k = closest_hit<R, kPackHit && !MESH>(sc, o, d, t);   // analytic primitives
@@ -615,11 +625,11 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
                 tg = {bs.frame[k][0], bs.frame[k][1], bs.frame[k][2]};
                 bt = {bs.frame[k][3], bs.frame[k][4], bs.frame[k][5]};
             }
-            if constexpr (MIXED) {                          // drift bound and the frame's axis switch (see ClosestMargin)
-                const float cosi = fmaxf(fabsf(float(dot(d, nrm))), 0.02f);
+            if constexpr (MIXED) {                          // the frame's axis switch and the drift bound (see ClosestMargin)
+                const float cosi = fmaxf(fabsf(float(dot(d, nrm))), 0.05f);
                 const float e_hit = (e_pos + float(t) * e_dir + kRoundPos * (1.0f + float(t))) / cosi;
-                const bool axis_call = sphere && fabsf(fabsf(float(nrm.x)) - fabsf(float(nrm.y))) < kFrameGap;
-                if (e_hit > kDriftMax || axis_call) { cnt.close_call = 1; alive = false; continue; }
+                const bool axis_call = sphere && fabsf(fabsf(float(nrm.x)) - fabsf(float(nrm.y))) < kFrameGap + kDriftK * e_hit;
+                if (axis_call || e_hit > kDriftMax) { cnt.close_call = 1; alive = false; continue; }
                 e_pos = e_hit;
                 e_dir = sphere ? e_hit / float(bs.prim[k][3]) + kRoundDir : kRoundDir;
             }

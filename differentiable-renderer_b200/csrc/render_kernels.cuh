@@ -102,7 +102,7 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
         unsigned long long claimed = 0;
         if (lane == 0) claimed = atomicAdd(a.task_counter, 1ull);
         const long long chunk = (long long)__shfl_sync(0xffffffffu, claimed, 0);
-        if (chunk >= a.n_chunks) break;
+        if (chunk < 0 || chunk >= a.n_chunks) break;
         // the first n_big chunks hold chunk_tasks tasks each, the rest a single task: the tail of
         // the kernel is then one task long, not one chunk
         const long long task0 = chunk < a.n_big_chunks ? chunk * a.chunk_tasks
@@ -364,7 +364,7 @@ render_regen_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constan
         unsigned long long claimed = 0;
         if (lane == 0) claimed = atomicAdd(a.task_counter, 1ull);
         const long long chunk = (long long)__shfl_sync(0xffffffffu, claimed, 0);
-        if (chunk >= a.n_chunks) break;
+        if (chunk < 0 || chunk >= a.n_chunks) break;
         // big chunks of chunk_tasks pixels, then a last round of small ones (render_kernel's tail rule)
         const long long big_end = a.n_big_chunks * a.chunk_tasks;
         const long long pix0 = chunk < a.n_big_chunks ? chunk * a.chunk_tasks : big_end + (chunk - a.n_big_chunks) * a.small_chunk;
@@ -657,7 +657,10 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
     a.n_big_chunks = plan.n_big;
     const long long n_chunks = plan.n_chunks;
     a.n_chunks = n_chunks;
-    if (!ctx->d_task_counter) CK(ctx, cudaMalloc(&ctx->d_task_counter, sizeof(unsigned long long)));
+    if (!ctx->d_task_counter) {
+        CK(ctx, cudaMalloc(&ctx->d_task_counter, sizeof(unsigned long long)));
+        CK(ctx, cudaMemset(ctx->d_task_counter, 0, sizeof(unsigned long long)));     // the first-use launches claim from it too
+    }
     a.task_counter = ctx->d_task_counter;
     // gradient partials: one row per chunk (SMALLP, summed in chunk order whoever ran the chunk) or
     // per block (shared atomic columns)
@@ -713,7 +716,10 @@ int launch_regen(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, long long 
     a.n_chunks = plan.n_chunks;
     long long grid = std::min<long long>((long long)ctx->sm_count * per_sm, (a.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock);
     if (grid < 1) grid = 1;
-    if (!ctx->d_task_counter) CK(ctx, cudaMalloc(&ctx->d_task_counter, sizeof(unsigned long long)));
+    if (!ctx->d_task_counter) {
+        CK(ctx, cudaMalloc(&ctx->d_task_counter, sizeof(unsigned long long)));
+        CK(ctx, cudaMemset(ctx->d_task_counter, 0, sizeof(unsigned long long)));     // the first-use launches claim from it too
+    }
     a.task_counter = ctx->d_task_counter;
     int rc = ensure(ctx, ctx->d_ring, ctx->ring_cap, size_t(grid) * kWarpsPerBlock * regen_ring_per_warp(sizeof(R)) / sizeof(double));
     if (rc != DRTB_OK) return rc;
