@@ -297,6 +297,7 @@ drtbh::ChunkPlan drtbh::plan_chunks(long long n_units, int spp, long long reside
 int drtbh::reduce_partials(drtb_ctx* ctx, double* partial, size_t rows, int P3, double* d_grad, cudaStream_t stream)
 {
     if (P3 <= 0 || rows == 0) return DRTB_OK;
+    Range r("drtb: gradient reduction");
     if (rows <= kReduceDirectRows) {
         reduce_grad_kernel<<<1, 256, 0, stream>>>(partial, int(rows), int(rows), P3, d_grad);
         ctx->launches++;
@@ -473,8 +474,14 @@ int launch_render(drtb_ctx* ctx, const drtb_render_opts* o, const double* d_seed
     const bool exchange = ctx->n_grad_peers > 1 && (o->flags & DRTB_FLAG_GRAD) && P3 > 0;
     if (exchange && P3 > kMaxExchangeP3)
         return fail(ctx, DRTB_ERR_UNSUPPORTED, "the peer gradient exchange serves up to 4096 gradient scalars; use a collective library for more");
-    int rc = launch_render_local(ctx, o, d_seed, d_img, d_grad, d_stats, gi, stream);
+    int rc;
+    {
+        Range r(ctx->dry ? "drtb: prepare (scratch, kernel attributes, first-use launches)"
+                         : (o->flags & DRTB_FLAG_GRAD) ? "drtb: render forward + adjoint" : "drtb: render forward");
+        rc = launch_render_local(ctx, o, d_seed, d_img, d_grad, d_stats, gi, stream);
+    }
     if (rc != DRTB_OK || ctx->dry || !exchange) return rc;
+    Range r("drtb: gradient exchange over NVLink peers");
     GradPeers gp{};
     for (int p = 0; p < ctx->n_grad_peers; ++p) gp.buf[p] = ctx->grad_peers[p];
     grad_allreduce_kernel<<<1, 256, 0, stream>>>(gp, ctx->n_grad_peers, ctx->grad_rank, P3, ++ctx->grad_epoch, d_grad);
@@ -566,11 +573,10 @@ int drtb_create(int device, drtb_ctx** out)
         delete ctx;
         return fail(nullptr, DRTB_ERR_CUDA, "context setup failed: " + m);
     }
-    // L2 set-aside for the mesh geometry's persisting window (mesh.cu); costs nothing while no window is active
-    if (prop.persistingL2CacheMaxSize > 0 &&
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(prop.persistingL2CacheMaxSize)) == cudaSuccess)
-        ctx->l2_persist_max = size_t(prop.persistingL2CacheMaxSize);
-    else cudaGetLastError();
+    // the L2 set-aside for a mesh's geometry (mesh.cu) is reserved when a mesh is attached, not here: a persisting
+    // carve-out shrinks the L2 every other kernel sees (the analytic megakernel's 52 MB of vertex records then spill
+    // to HBM: 6.1 GB of write-backs per render against 0.15 GB, profiles/README.md round 2)
+    ctx->l2_persist_max = size_t(std::max(0, prop.persistingL2CacheMaxSize));
     // (sin, cos)(2 pi i 2^23 / M) for Real<double>::sincos_tab: one copy per translation unit that samples in double
     if (drtb::upload_sincos_tab() != cudaSuccess || init_tables_render_f64() != cudaSuccess || init_tables_mesh() != cudaSuccess) {
         std::string m = cudaGetErrorString(cudaGetLastError());
@@ -689,6 +695,7 @@ int render_host(drtb_ctx* ctx, const drtb_render_opts* o, int32_t gparam, const 
                 double* grad, double* grad_img, drtb_stats* stats)
 {
     if (!ctx) return DRTB_ERR_INVALID;
+    Range whole("drtb_render (host buffers)");
     int rc = validate_opts(ctx, o);
     if (rc != DRTB_OK) return rc;
     CK(ctx, cudaSetDevice(ctx->device));

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>          // header-only NVTX 3: ranges cost nothing unless a tool (nsys, ncu --nvtx) is attached
 
 #include "path.cuh"
 
@@ -79,7 +80,8 @@ struct drtb_ctx {
     double* grad_peers[drtb::kMaxPeers] = {};  // drtb_set_grad_peers: every rank's gradient exchange buffer
     int n_grad_peers = 0, grad_rank = 0;
     unsigned long long grad_epoch = 0;         // calls of the exchange so far (all ranks count alike)
-    size_t l2_persist_max = 0;    // cudaDevAttrMaxPersistingL2CacheSize, reserved at create (0: not supported)
+    size_t l2_persist_max = 0;    // cudaDevAttrMaxPersistingL2CacheSize (0: not supported)
+    bool l2_reserved = false;     // the persisting set-aside is currently reserved for this context's mesh
     size_t l2_window_max = 0;     // cudaDevAttrMaxAccessPolicyWindowSize
     // Preparation pass (drtb_reserve, and drtb_render before it starts its timer): every scratch buffer is
     // sized, every kernel attribute set and every kernel instantiation launched once on zero work (module load,
@@ -89,6 +91,15 @@ struct drtb_ctx {
 };
 
 namespace drtbh {
+
+// NVTX range for the lifetime of the object: forward / adjoint render, gradient reduction, the cross-GPU exchange,
+// the BVH build and the wavefront's batches show up as named spans in a timeline.
+struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+    Range(const Range&) = delete;
+    Range& operator=(const Range&) = delete;
+};
 
 int fail(drtb_ctx* ctx, int code, const std::string& msg);       // records the message, returns code
 
@@ -148,6 +159,11 @@ inline drtb::MeshView mesh_view(const drtb_ctx* ctx)
 inline void free_mesh(drtb_ctx* ctx)
 {
     cudaFree(ctx->d_tri64); cudaFree(ctx->d_tri32);           // d_nodes points into d_tri32's allocation
+    if (ctx->geom_bytes > 0 && ctx->l2_reserved) {            // give the L2 set-aside back to everybody else
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+        ctx->l2_reserved = false;
+    }
     ctx->geom_bytes = 0;
     cudaFree(ctx->d_tri_color); cudaFree(ctx->d_tri_emis);
     ctx->d_nodes = nullptr; ctx->d_tri64 = nullptr; ctx->d_tri32 = nullptr;

@@ -222,7 +222,12 @@ int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opt
     // (4 M x 72 B), which evicts the 85 MB of triangles and nodes that EVERY ray reads.  A persisting access-policy
     // window over the geometry keeps it resident; ray traffic is left to the normal (evict-first for misses) policy.
     const bool l2_window = ctx->l2_persist_max > 0 && ctx->geom_bytes > 0 && !no_bvh && std::getenv("DRTB_NO_L2_WINDOW") == nullptr;
-    if (l2_window) {
+    if (l2_window && !ctx->l2_reserved) {                    // reserved while the mesh is attached (free_mesh gives it back)
+        const size_t want = std::min(ctx->l2_persist_max, (ctx->geom_bytes + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1));
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) ctx->l2_reserved = true;
+        else cudaGetLastError();
+    }
+    if (l2_window && ctx->l2_reserved) {
         cudaStreamAttrValue av{};
         av.accessPolicyWindow.base_ptr = ctx->d_tri32;
         av.accessPolicyWindow.num_bytes = std::min(ctx->geom_bytes, ctx->l2_window_max);
@@ -232,6 +237,7 @@ int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opt
         CK(ctx, cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
     }
     for (int bi = 0; bi < n_batches; ++bi) {
+        drtbh::Range batch_range("drtb: wavefront batch (generate, traverse + shade per depth, adjoint)");
         const long long p0 = (long long)bi * pix_per_batch;
         a.first_path = p0 * o->spp;
         a.n_paths = int(std::min<long long>(pix_per_batch, npix - p0) * o->spp);
@@ -255,7 +261,7 @@ int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opt
         CK(ctx, cudaGetLastError());
         ctx->launches += 2 + 2 * D;
     }
-    if (l2_window) {
+    if (l2_window && ctx->l2_reserved) {
         cudaStreamAttrValue av{};                            // num_bytes = 0: window off for whatever the caller enqueues next
         CK(ctx, cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
     }
@@ -270,6 +276,7 @@ int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opt
 
 int mesh_upload_impl(drtb_ctx* ctx, const drtb_mesh* mesh)
 {
+    drtbh::Range whole("drtb_mesh_upload: copy + GPU BVH build");
     if (!ctx->has_scene) return fail(ctx, DRTB_ERR_INVALID, "upload a scene before attaching a mesh");
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -14,7 +14,7 @@ def test_gradient_descent_recovers_the_wall_albedos():
     spec = importlib.util.spec_from_file_location("inverse_render", ROOT / "examples" / "inverse_render.py")
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    theta, err, hist, ips = mod.fit(128, 128, 64, 4, iters=100)
+    theta, err, hist, ips = mod.fit(256, 256, 64, 4, iters=100)          # the survey's size for config 3 (256^2 .. 512^2)
     # the loss floor is the Monte Carlo variance of two independent 64-spp-class images
     assert hist[-1] < 0.7 * hist[0], (hist[0], hist[-1])
     assert err < 0.03, (theta, err)

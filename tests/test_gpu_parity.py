@@ -184,7 +184,6 @@ def test_errors_are_codes_with_messages(drt, ctx):
     ctx.upload(drt.cornell_box(16, 16))
     for bad, code in [(dict(spp=0), abi.ERR_INVALID), (dict(spp=1, absorb=1.5), abi.ERR_INVALID),
                       (dict(spp=1, min_bounces=-1), abi.ERR_INVALID), (dict(spp=1, precision=7), abi.ERR_INVALID),
-                      (dict(spp=1, precision=drt.MIXED), abi.ERR_UNSUPPORTED),
                       (dict(spp=1, shard_index=3, shard_count=2), abi.ERR_INVALID),
                       (dict(spp=1, min_bounces=100, absorb=1.0), abi.ERR_UNSUPPORTED)]:
         with pytest.raises(drt.DrtbError) as e:
