@@ -38,12 +38,30 @@ struct SmemAtomicSink {
         atomicAdd(col + (3 * p + c) * cols, double(v));
     }
 };
-// Large parameter sets (mesh scenes, per-triangle albedos): one red.global.add.f64 per contribution.
+// Large parameter sets (mesh scenes, per-triangle albedos: up to 3 * 2^20 scalars in HBM).  Contributions of the
+// lanes of a warp to the SAME scalar are added inside the warp first (the 32 samples of a pixel hit the same
+// triangle at their first vertex, so every one of its three channels is a 32-way collision) and one lane issues
+// one red.global.add.f64 for the group: __match_any_sync on the scalar's index among the lanes that reached this
+// add together, the group's values summed in lane order through shuffles.  Distinct scalars (the usual case at
+// deeper vertices) cost the match and one vote on top of the atomic.
 struct AtomicSink {
     double* grad;
     template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
     {
-        atomicAdd(grad + 3 * p + c, double(v));
+        const unsigned active = __activemask();
+        const int key = 3 * p + c;
+        const unsigned group = __match_any_sync(active, key);
+        const int size = __popc(group);
+        const int rounds = __reduce_max_sync(active, size);        // 1: no two lanes share a scalar
+        const int lane = threadIdx.x & 31;
+        double sum = double(v);
+        const int first = __ffs(group) - 1;
+        for (int r = 1; r < rounds; ++r) {                          // warp-uniform trip count
+            const int src = r < size ? int(__fns(group, 0, r + 1)) : lane;
+            const double other = __shfl_sync(active, double(v), src);
+            if (lane == first && r < size) sum += other;
+        }
+        if (lane == first) atomicAdd(grad + key, sum);
     }
 };
 // Gradient image (drtb_render_grad_image): parameter kp's contributions are

@@ -31,11 +31,11 @@ BS = [int(x) for x in a.bounces.split(",")]
 if a.merge_ncu:
     rows = [r for r in csv.reader(open(a.merge_ncu)) if len(r) > 5]
     hdr = next(r for r in rows if "Metric Name" in r)
-    iname, ival, ikern = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Kernel Name")
+    iname, ival, ikern, igrid = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Kernel Name"), hdr.index("Grid Size")
     lanes, ms = [], []
     for r in rows:
-        if r is hdr or len(r) <= ival or "render_kernel" not in r[ikern]:
-            continue
+        if r is hdr or len(r) <= ival or "render_kernel" not in r[ikern] or r[igrid].replace(" ", "") == "(1,1,1)":
+            continue                                          # (1,1,1): the first-use launch of drtb_reserve, no work
         if r[iname].startswith("smsp__thread_inst_executed_per_inst_executed"):
             lanes.append(float(r[ival].replace(",", "")))
         if r[iname].startswith("gpu__time_duration"):
