@@ -90,3 +90,20 @@ def test_independent_seeds_agree_within_three_sigma(drt, ctx):
     assert (np.abs(o_grad - grads[0]) <= 3.0 * np.sqrt(2.0) * gs * 1.5).all()
     m = imgs[2:].reshape(8, -1, 3).mean(1)
     assert (np.abs(o_img.reshape(-1, 3).mean(0) - m.mean(0)) <= 4.0 * m.std(0, ddof=1) + 1e-4).all()
+
+
+def test_config5_segment_rate_is_flat_across_bounce_counts(drt, ctx):
+    """BASELINE.json configs[4] (max-bounce sweep): a path of B bounces costs about B segments -- ray segments per
+    second stay within 25 % of their best for B = 1 .. 8 (deeper records lose a little more: the sweep table under
+    profiles/ goes to B = 16 at 2048^2, 128 spp on 1 / 2 / 8 GPUs).  Best of three timed renders each."""
+    ctx.upload(drt.cornell_box(1024, 1024))
+    rate = {}
+    for B in (1, 2, 4, 8):
+        o = drt.make_opts(64, B, 1.0)
+        best = None
+        for _ in range(3):
+            _, _, st = ctx.render(o, stats=True)
+            best = st.kernel_ms if best is None else min(best, st.kernel_ms)
+        rate[B] = st.segments / best / 1e3                      # Msegments/s
+    assert min(rate.values()) >= 0.75 * max(rate.values()), rate
+    assert rate[8] > 35000, rate                                 # ~45 Gsegments/s on a B200
