@@ -47,7 +47,10 @@ constexpr int kBvhStack   = 64;           // traversal stack entries per lane (o
 #define DRTB_LEAF_MAX 3
 #endif
 constexpr int kLeafMax    = DRTB_LEAF_MAX; // triangles per leaf, <= 3 (3 unary bits of the child's meta byte)
-constexpr int kPlocRadius = 16;           // PLOC neighbour search radius along the Morton order
+#ifndef DRTB_PLOC_RADIUS
+#define DRTB_PLOC_RADIUS 16
+#endif
+constexpr int kPlocRadius = DRTB_PLOC_RADIUS;           // PLOC neighbour search radius along the Morton order
 constexpr int kTri64Stride = 10;          // doubles per triangle: v0, e1, e2, pad (16-byte aligned rows)
 constexpr int kTri32Stride = 4;           // float4 per triangle (64 B: two 256-bit loads)
 constexpr int kNodeStride  = 8;           // 16-byte words per wide node (128 B)
