@@ -27,10 +27,12 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-    # 5 blocks of 128 threads per SM caps the double kernel at 96 registers with
-    # no spills; measured on B200: 69.4 ms vs 76.3 ms uncapped (141 registers),
-    # and no further gain from 6/7/8 (the kernel is issue bound, not latency bound).
-    "-DDRTB_MIN_BLOCKS=5",
+    # Resident blocks of 128 threads per SM for the double kernels.  The first kernel of round 1 (141 registers
+    # uncapped) gained from a cap of 96 (5 blocks) and nothing beyond; with today's kernel the picture is different:
+    # 5 / 6 / 7 / 8 blocks (96 / 80 / 72 / 64 registers) -> 42.9 / 40.7 / 38.8 / 39.1 ms on the headline workload
+    # (profiles/README.md, round 2).  72 registers are free of spills once the pixel accumulators live in shared
+    # memory and the adjoint seed is fetched in the sweep (render_kernels.cuh); 64 registers spill 28 bytes.
+    "-DDRTB_MIN_BLOCKS=7",
     # the float instantiation needs fewer registers: resident blocks 5 / 6 / 7 / 8 -> 34.6 / 33.1 / 31.2 / 31.1 ms;
     # 7 (72 registers) is the most that stays free of spills in every all-diffuse variant
     "-DDRTB_MIN_BLOCKS_F32=7",

@@ -326,12 +326,11 @@ __device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<
 // ---------------------------------------------------------------------------
 template <typename R, bool MARGIN> struct ClosestOf { template <bool PACK> using type = Closest<R, PACK>; };
 template <> struct ClosestOf<float, true> { template <bool PACK> using type = ClosestMargin; };
-template <typename R, bool PACK = false, bool MARGIN = false>
-__device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R> d, R& tmin, bool* close_call = nullptr,
-                                           bool skip_zero = false, float slack = 0.0f)
+
+// The scan itself, for any running-closest type C (offer / flag interface above).
+template <typename R, typename C>
+__device__ __forceinline__ void scan_prims(const DevScene<R>& sc, V3<R> o, V3<R> d, C& cl)
 {
-    typename ClosestOf<R, MARGIN>::template type<PACK> cl;
-    if constexpr (MARGIN) cl.slack = slack;
     // Entry into the straight-line tests by a compare tree on the (warp-uniform)
     // first live slot: ~6 instructions, where the compiler's jump table for the
     // equivalent switch cost ~20 per entry.
@@ -339,7 +338,7 @@ __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R>
 #define DRTB_AXIS(AX, OA, DA)                                                                  \
     if (sc.n_aa[AX] > 0) {                                                                      \
         const R inv = Real<R>::rcp(DA);                                                         \
-        if constexpr (HasMargin<decltype(cl)>::value) cl.flag |= Real<R>::abs(DA) <= kParallel;  \
+        if constexpr (HasMargin<C>::value) cl.flag |= Real<R>::abs(DA) <= kParallel;             \
         if (sc.n_aa[AX] > 1) axis_plane_test(sc, AX, 0, OA, inv, cl);                     \
         axis_plane_test(sc, AX, 1, OA, inv, cl);                                          \
     }
@@ -382,11 +381,22 @@ __device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R>
 #undef DRTB_ENTER
     for (int i = 0; i < sc.n_over_spheres; ++i)
         sphere_test(sc, 2 * kFast + sc.n_over_planes + i, o, d, cl);
+}
+
+template <typename R, bool PACK = false, bool MARGIN = false>
+__device__ __forceinline__ int closest_hit(const DevScene<R>& sc, V3<R> o, V3<R> d, R& tmin, bool* close_call = nullptr,
+                                           bool skip_zero = false, float slack = 0.0f)
+{
     if constexpr (MARGIN) {
+        typename ClosestOf<R, MARGIN>::template type<PACK> cl;
+        cl.slack = slack;
+        scan_prims(sc, o, d, cl);
         const int k = cl.finish(tmin, skip_zero);
         *close_call = cl.flag;
         return k;
     } else {
+        typename ClosestOf<R, MARGIN>::template type<PACK> cl;
+        scan_prims(sc, o, d, cl);
         return cl.finish(tmin);
     }
 }

@@ -35,6 +35,9 @@ using drtbh::reduce_scratch_rows;
 #ifndef DRTB_MESH_MIN_BLOCKS
 #define DRTB_MESH_MIN_BLOCKS DRTB_MIN_BLOCKS
 #endif
+#ifndef DRTB_MIN_BLOCKS_GEN
+#define DRTB_MIN_BLOCKS_GEN (DRTB_MIN_BLOCKS < 5 ? DRTB_MIN_BLOCKS : 5)   // double GEN kernels (lobe code, gradient image): 96 registers
+#endif
 #ifndef DRTB_MIN_BLOCKS_F32
 #define DRTB_MIN_BLOCKS_F32 DRTB_MIN_BLOCKS
 #endif
@@ -44,12 +47,14 @@ using drtbh::reduce_scratch_rows;
 //   MIXED : DRTB_MIXED's fast pass (float): a path whose trace met a close call (path.cuh, ClosestMargin) is not
 //           swept; its (pixel, sample) goes on a list that retrace_kernel re-traces in double
 template <typename R, bool SMALLP, int QUEUE, bool MESH, bool GEN, bool MIXED = false>
-__global__ void __launch_bounds__(kBlock, MESH ? DRTB_MESH_MIN_BLOCKS : sizeof(R) == 4 ? DRTB_MIN_BLOCKS_F32 : DRTB_MIN_BLOCKS)
+__global__ void __launch_bounds__(kBlock, MESH ? DRTB_MESH_MIN_BLOCKS : sizeof(R) == 4 ? DRTB_MIN_BLOCKS_F32 : GEN ? DRTB_MIN_BLOCKS_GEN : DRTB_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ RenderArgs a)
 {
     using Id = typename PrimId<MESH>::type;
     extern __shared__ double s_dyn[];              // [acc: n_params*3*kBlock doubles][rings]
     __shared__ BlockScene<R> bs;
+    constexpr bool kPixSmem = sizeof(R) == 8;
+    __shared__ double s_pix[kPixSmem ? 3 : 1][kPixSmem ? kBlock : 1];
 
     // gradient sink: per-thread columns (SMALLP), shared atomic columns (analytic scenes with
     // more parameters) or global atomics (mesh scenes with more parameters)
@@ -114,24 +119,31 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
             const long long pix = task * ppw + sub;
             const bool lane_ok = sub < ppw && pix < npix;
             int x = 0, y = 0;
-            R g0[3] = {R(0), R(0), R(0)};
             if (lane_ok) {
                 const int r = int(pix / W);
                 x = int(pix - (long long)r * W);
                 y = a.shard_count > 1 ? ((r / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + r % a.band_rows
                                       : r;
-                if (want_grad) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        g0[c] = R(a.seed_scale * (a.seed_img ? a.seed_img[pix * 3 + c] : 1.0));
-                }
             }
-            double acc[3] = {0.0, 0.0, 0.0};
+            // This lane's share of the pixel.  Double: a shared-memory column, not six registers held through the
+            // trace -- the kernel is latency bound, 7 resident blocks of 72 registers beat 5 of 96 by 10 %, and this
+            // (with the adjoint seed fetched in the sweep) is what makes 72 registers free of spills.  The float
+            // instantiation has the registers (measured: 2.7 % slower with the shared column).
+            double acc_r[3] = {0.0, 0.0, 0.0};
+            if constexpr (kPixSmem) { s_pix[0][threadIdx.x] = 0.0; s_pix[1][threadIdx.x] = 0.0; s_pix[2][threadIdx.x] = 0.0; }
             double gacc[3] = {0.0, 0.0, 0.0};          // GEN: this lane's share of the pixel's gradient-image value
 
             // sweeps over one record; accumulates this lane's share of the pixel and the gradients
             auto sweep = [&](const auto& rec, int n) {
                 R L0[3];
+                // the adjoint seed of this pixel (src/render.cpp:79-80), fetched here rather than held in six registers
+                // through the trace: only the lit paths need it
+                R g0[3] = {R(0), R(0), R(0)};
+                if (want_grad) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        g0[c] = R(a.seed_scale * (a.seed_img ? a.seed_img[pix * 3 + c] : 1.0));
+                }
                 auto run = [&](auto& sink) { radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, sink); };
                 if constexpr (GEN) {
                     if constexpr (SMALLP)             { PixelSink<SmemSink> s{ssink, a.gimg_param, gacc}; run(s); }
@@ -142,7 +154,12 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                     else if constexpr (kSharedAtomic) run(msink);
                     else                              run(asink);
                 }
-                acc[0] += double(L0[0]); acc[1] += double(L0[1]); acc[2] += double(L0[2]);       // render.cpp:78
+                if constexpr (kPixSmem) {                                                          // render.cpp:78
+                    s_pix[0][threadIdx.x] += double(L0[0]); s_pix[1][threadIdx.x] += double(L0[1]);
+                    s_pix[2][threadIdx.x] += double(L0[2]);
+                } else {
+                    acc_r[0] += double(L0[0]); acc_r[1] += double(L0[1]); acc_r[2] += double(L0[2]);
+                }
                 n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
             };
             // run the sweeps on the first m queued records, one per lane
@@ -230,6 +247,8 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                     }
                 }
             };
+            double acc[3] = {acc_r[0], acc_r[1], acc_r[2]};
+            if constexpr (kPixSmem) { acc[0] = s_pix[0][threadIdx.x]; acc[1] = s_pix[1][threadIdx.x]; acc[2] = s_pix[2][threadIdx.x]; }
             if (a.img) write_pixel(a.img, acc, true);
             if (a.n_peer_img > 0) {
                 // Image all-gather fused into the render: the pixel goes straight into the full image

@@ -6,7 +6,7 @@ mkdir -p build/variants/obj_$name
 C=differentiable-renderer_b200/csrc
 for tu in drtb render_f64 render_f32 mesh multi; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC \
-    -DDRTB_MIN_BLOCKS=5 -DDRTB_MIN_BLOCKS_F32=7 -DDRTB_MESH_MIN_BLOCKS=6 -DDRTB_WF_MIN_BLOCKS=7 "$@" -ccbin /usr/bin/g++ -I include \
+    -DDRTB_MIN_BLOCKS=7 -DDRTB_MIN_BLOCKS_F32=7 -DDRTB_MESH_MIN_BLOCKS=6 -DDRTB_WF_MIN_BLOCKS=7 "$@" -ccbin /usr/bin/g++ -I include \
     -c -o build/variants/obj_$name/$tu.o $C/$tu.cu 2> build/variants/obj_$name/$tu.log &
 done
 wait
