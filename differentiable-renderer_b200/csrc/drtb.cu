@@ -181,6 +181,7 @@ void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
     d.n_over_spheres = int(spheres.size()) - d.n_fast_spheres;
     auto put = [&](int slot, int i) {
         for (int j = 0; j < 4; ++j) d.prim[slot][j] = R(c.prims[i].v[j]);
+        d.r2[slot] = R(c.prims[i].v[3] * c.prims[i].v[3]);            // spheres: m_radius * m_radius, shape.hpp:85
         d.id[slot] = i;
         d.slot[i] = int8_t(slot);
     };

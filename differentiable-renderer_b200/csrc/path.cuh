@@ -48,6 +48,7 @@ struct alignas(16) DevScene {
     // subtraction and one multiplication by the per-segment 1 / d_a.  Their n, off
     // stay in prim[] behind the scanned slots for the per-lane lookups.
     R       prim[kSlots][4];             // plane: n.xyz (RAW), offset ; sphere: c.xyz, r
+    R       r2[kSlots];                  // sphere: r * r (host double)
     int32_t id[kSlots];                  // scan slot -> scene index
     R       aa_c[3][kAxisFast];          // s * offset: the plane is  p_a = aa_c
     int32_t aa_id[3][kAxisFast];
@@ -192,6 +193,7 @@ struct Closest {
         const bool closer = (t < bt) | ((t == bt) & (id < best));           // bitwise: no branch
         if (Real<R>::is_pos(t) & closer) { bt = t; best = id; }
     }
+    __device__ __forceinline__ void offer_nz(R t, int id) { offer(t, id); }
     __device__ __forceinline__ int finish(R& tmin) const { tmin = bt; return best; }
 };
 // Double, analytic scenes: the three FP64 compares per primitive (six issue
@@ -215,6 +217,15 @@ struct Closest<double, true> {
         const uint32_t lo = (uint32_t(__double2loint(t)) & keep) | uint32_t(id);
         const unsigned long long k = (unsigned long long)(uint32_t)hi << 32 | lo;
         if ((hi > 0) & (k < key)) key = k;
+    }
+    // The same for a t that is never +0 (the plane tests: Real<double>::mul_nz turns an exact zero into the
+    // number -2^-1000): as UNSIGNED integers negative doubles, -0 and NaNs compare above the +inf the key
+    // starts from, so the one compare rejects them -- five instructions instead of six.
+    __device__ __forceinline__ void offer_nz(double t, int id)
+    {
+        const uint32_t lo = (uint32_t(__double2loint(t)) & keep) | uint32_t(id);
+        const unsigned long long k = (unsigned long long)(uint32_t)__double2hiint(t) << 32 | lo;
+        if (k < key) key = k;
     }
     __device__ __forceinline__ int finish(double& tmin) const
     {
@@ -265,6 +276,7 @@ struct ClosestMargin {
         best = tp < bt ? id : best;
         bt = fminf(bt, tp);
     }
+    __device__ __forceinline__ void offer_nz(float t, int id) { offer(t, id); }
     __device__ __forceinline__ void rejected(float t) { ta = fminf(ta, fabsf(t)); }   // a sphere's first root when it is <= 0
     // skip_zero: the caller knows that no primitive can be within kNearZero of t = 0 except exactly AT 0 (camera rays
     // of a scene whose eye lies exactly on a plane, as the Cornell box's does: DevScene::eye_clear)
@@ -284,7 +296,7 @@ template <> struct HasMargin<ClosestMargin> { static constexpr bool value = true
 template <typename R, typename C>
 __device__ __forceinline__ void axis_plane_test(const DevScene<R>& sc, int axis, int slot, R o_a, R inv_a, C& cl)
 {
-    cl.offer((sc.aa_c[axis][slot] - o_a) * inv_a, sc.aa_id[axis][slot]);
+    cl.offer_nz(Real<R>::mul_nz(sc.aa_c[axis][slot] - o_a, inv_a), sc.aa_id[axis][slot]);
 }
 
 template <typename R, typename C>
@@ -294,22 +306,31 @@ __device__ __forceinline__ void plane_test(const DevScene<R>& sc, int slot, V3<R
     const R h = Real<R>::fma(o.x, a0, Real<R>::fma(o.y, a1, Real<R>::fma(o.z, a2, -a3)));   // o.n - offset
     const R g = Real<R>::fma(d.x, a0, Real<R>::fma(d.y, a1, d.z * a2));                     // d.n ; t = h / -g
     if constexpr (HasMargin<C>::value) cl.flag |= Real<R>::abs(g) <= kParallel;
-    cl.offer(-h * Real<R>::rcp(g), sc.id[slot]);
+    cl.offer_nz(Real<R>::mul_nz(-h, Real<R>::rcp(g)), sc.id[slot]);
 }
 
+// Sphere::intersect, shape.hpp:78-103 (a == 1): with hb = b / 2, c = |oc|^2 - r^2, disc = hb^2 - c (an exact
+// rescaling of b^2 - 4 c) the roots are t1 = -hb - sqrt(disc) <= t2 = -hb + sqrt(disc) and the reference returns t1
+// if t1 > 0, else t2.  t1 > 0 <=> the origin is outside (c > 0) and the centre lies ahead (hb < 0), so the root is
+// chosen from the two sign bits and ONE subtraction is made: sign logic on the high words instead of a second FP64
+// add, a compare and a 64-bit select.  (Not the same only when the origin lies on the sphere to the last bit --
+// c == 0 or a c below the rounding of hb^2 -- which a ray that left a surface by the 1e-3 offset of
+// pathtracer.hpp:99 cannot do.)  r^2 comes from the host; the chain starts from -r^2, one FMA fewer.
 template <typename R, typename C>
 __device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<R> o, V3<R> d, C& cl)
 {
-    const R a0 = sc.prim[slot][0], a1 = sc.prim[slot][1], a2 = sc.prim[slot][2], a3 = sc.prim[slot][3];
+    const R a0 = sc.prim[slot][0], a1 = sc.prim[slot][1], a2 = sc.prim[slot][2];
     const V3<R> oc = {o.x - a0, o.y - a1, o.z - a2};
     const R hb = dot(oc, d);                       // b/2
-    const R c = Real<R>::fma(-a3, a3, dot(oc, oc));
-    const R disc = Real<R>::fma(hb, hb, -c);       // (b^2 - 4c)/4, an exact rescaling
-    if constexpr (HasMargin<C>::value) cl.flag |= Real<R>::abs(disc) < kDiscRel * a3 * a3 + cl.slack * 4.0f * (Real<R>::abs(hb) + a3);
+    const R c = Real<R>::fma(oc.z, oc.z, Real<R>::fma(oc.y, oc.y, Real<R>::fma(oc.x, oc.x, -sc.r2[slot])));
+    const R disc = Real<R>::fma(hb, hb, -c);       // (b^2 - 4c)/4
+    if constexpr (HasMargin<C>::value) {
+        const R a3 = sc.prim[slot][3];
+        cl.flag |= Real<R>::abs(disc) < kDiscRel * a3 * a3 + cl.slack * 4.0f * (Real<R>::abs(hb) + a3);
+    }
     const R sq = Real<R>::sqrt(disc);              // NaN when disc < 0: every compare below fails
-    const R t1 = -hb - sq, t2 = sq - hb;           // t1 <= t2
-    if constexpr (HasMargin<C>::value) cl.rejected(t1);      // the root that is not offered must not be a near-zero either
-    cl.offer(Real<R>::select(Real<R>::is_pos(t1), t1, t2), sc.id[slot]);
+    if constexpr (HasMargin<C>::value) cl.rejected(-hb - sq);   // the root that is not offered must not be a near-zero either
+    cl.offer(Real<R>::neg_if_outside_ahead(sq, c, hb) - hb, sc.id[slot]);
 }
 
 // ---------------------------------------------------------------------------
@@ -428,6 +449,10 @@ __device__ __forceinline__ void unit_frame(V3<R> n, V3<R>& tg, V3<R>& bt)
 // w = cos / pdf.  n is used RAW (the non-unit green-wall normal stays non-unit).
 // sin(asin(sqrt u)) = sqrt u, cos(asin(sqrt u)) = sqrt(1 - u); u < 1 always, so
 // one rsqrt(1 - u) yields both cos(theta) and the 1/cos(theta) that pdf needs.
+// (w is pi |n|^2 + pi (n.tg) x / cos(theta) in exact arithmetic, a constant of the
+// primitive for unit normals; taking it from a table instead of evaluating the
+// reference's dot product and division was measured and is no faster at 72
+// registers: profiles/README.md, round 2.)
 // ---------------------------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, V3<R> tg, V3<R> bt, R u_theta, R sp, R cp, R& w)
@@ -442,6 +467,27 @@ __device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, V3<R> tg, V3<R> bt, R u
                         x * tg.z + y * bt.z + ct * n.z};
     w = dot(n, dout) * (Real<R>::pi() * inv_ct);       // dot(n, dout) / (cos(theta) / pi)
     return dout;
+}
+
+// Normal and tangent frame of analytic primitive k at the hit point pt.  Planes: constants of the primitive (the
+// frame is make_frame(n), bxdf.hpp:29-41, evaluated on the host).  Spheres: normal(point) = normalize(point -
+// centre), shape.hpp:105-106, and make_frame of that unit normal.  (The division by the norm cannot be replaced
+// by 1 / r: Sphere::intersect takes a == 1 even for the non-unit directions that leave the raw green-wall normal,
+// shape.hpp:83, so such a "hit point" is not on the sphere -- measured: 4 of 12 288 paths of a 48 x 32 Cornell
+// box take another course.)
+template <typename R>
+__device__ __forceinline__ bool analytic_frame(const BlockScene<R>& bs, int k, V3<R> pt, V3<R>& nrm, V3<R>& tg, V3<R>& bt)
+{
+    nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]};
+    const bool sphere = bs.type[k] == DRTB_SPHERE;
+    if (sphere) {
+        nrm = normalize(V3<R>{pt.x - nrm.x, pt.y - nrm.y, pt.z - nrm.z});
+        unit_frame(nrm, tg, bt);
+    } else {
+        tg = {bs.frame[k][0], bs.frame[k][1], bs.frame[k][2]};
+        bt = {bs.frame[k][3], bs.frame[k][4], bs.frame[k][5]};
+    }
+    return sphere;
 }
 
 // ---------------------------------------------------------------------------
@@ -626,15 +672,7 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
             }
         }
         if (!on_mesh) {
-            nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]};
-            const bool sphere = bs.type[k] == DRTB_SPHERE;
-            if (sphere) {                                   // shape.hpp:105-106
-                nrm = normalize(V3<R>{pt.x - nrm.x, pt.y - nrm.y, pt.z - nrm.z});
-                unit_frame(nrm, tg, bt);
-            } else {                                        // plane: constant frame, bxdf.hpp:29-41 on the host
-                tg = {bs.frame[k][0], bs.frame[k][1], bs.frame[k][2]};
-                bt = {bs.frame[k][3], bs.frame[k][4], bs.frame[k][5]};
-            }
+            const bool sphere = analytic_frame(bs, k, pt, nrm, tg, bt);
             if constexpr (MIXED) {                          // the frame's axis switch and the drift bound (see ClosestMargin)
                 const float cosi = fmaxf(fabsf(float(dot(d, nrm))), 0.05f);
                 const float e_hit = (e_pos + float(t) * e_dir + kRoundPos * (1.0f + float(t))) / cosi;
@@ -706,19 +744,13 @@ __device__ __forceinline__ bool trace_segment(const DevScene<R>& sc, const Block
         rec.w_[n++] = R(0);
         return true;
     }
-    V3<R> nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]}, tg, bt;
-    if (bs.type[k] == DRTB_SPHERE) {                        // shape.hpp:105-106
-        nrm = normalize(V3<R>{pt.x - nrm.x, pt.y - nrm.y, pt.z - nrm.z});
-        unit_frame(nrm, tg, bt);
-    } else {                                                // plane: constant frame, bxdf.hpp:29-41 on the host
-        tg = {bs.frame[k][0], bs.frame[k][1], bs.frame[k][2]};
-        bt = {bs.frame[k][3], bs.frame[k][4], bs.frame[k][5]};
-    }
+    V3<R> nrm, tg, bt;
+    R w;
+    analytic_frame(bs, k, pt, nrm, tg, bt);
     const R u_theta = Real<R>::uniform_fast(stream_draw_ctr(ctr));
     R sp, cp;                                               // phi = 2 * pi * uniform(), bxdf.hpp:74
     Real<R>::sincos_tab(bs.tab, stream_draw_ctr(ctr + 1), &sp, &cp);
     ctr += 2;
-    R w;
     const V3<R> dout = diffuse_sample(nrm, tg, bt, u_theta, sp, cp, w);
     rec.w_[n++] = w;
     const R eps = Real<R>::origin_eps();                    // 1e-3, pathtracer.hpp:99

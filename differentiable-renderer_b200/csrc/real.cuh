@@ -80,6 +80,18 @@ template <> struct Real<double> {
         const int flip = (gh > 0) ? int(0x80000000u) : 0;
         return __hiloint2double(__double2hiint(h) ^ flip, __double2loint(h));
     }
+    // a * b, except that an exact +-0 comes out negative (-2^-1000): for every product above 2^-947 in magnitude the
+    // addend is below half an ulp and the FMA rounds it away (a t that small cannot occur: segments start 1e-3 off the
+    // surface they leave).  Lets the plane tests reject t = 0 (shape.hpp:55, t > 0) without a test of their own
+    // (Closest<double, true>::offer_nz).  The low word of the constant is zero, so it is an immediate operand.
+    static __device__ __forceinline__ double mul_nz(double a, double b) { return ::fma(a, b, -0x1p-1000); }
+    // x with its sign flipped iff c > 0 and h < 0 (sphere_test: the nearer root), from the two sign words.
+    // c == +0 counts as positive and h == -0 as negative: see sphere_test for why that cannot matter.
+    static __device__ __forceinline__ double neg_if_outside_ahead(double x, double c, double h)
+    {
+        const uint32_t flip = uint32_t(__double2hiint(h)) & ~uint32_t(__double2hiint(c)) & 0x80000000u;
+        return __hiloint2double(int(uint32_t(__double2hiint(x)) ^ flip), __double2loint(x));
+    }
     static __device__ __forceinline__ double select(bool c, double a, double b)
     {
         return __hiloint2double(c ? __double2hiint(a) : __double2hiint(b), c ? __double2loint(a) : __double2loint(b));
@@ -195,6 +207,8 @@ template <> struct Real<float> {
     static __device__ __forceinline__ bool is_nonzero(float x) { return x != 0.0f; }
     static __device__ __forceinline__ float flip_if_pos(float h, float g) { return g > 0.0f ? -h : h; }
     static __device__ __forceinline__ float select(bool c, float a, float b) { return c ? a : b; }
+    static __device__ __forceinline__ float mul_nz(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float neg_if_outside_ahead(float x, float c, float h) { return (c > 0.0f && h < 0.0f) ? -x : x; }
     static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
     static __device__ __forceinline__ float rsqrt(float x) { return ::rsqrtf(x); }

@@ -392,14 +392,7 @@ wf_shade(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArgs 
                         nrm = normalize(cross(T.e1, T.e2));
                         unit_frame(nrm, tg, bt);
                     } else {
-                        nrm = {bs.prim[k][0], bs.prim[k][1], bs.prim[k][2]};
-                        if (bs.type[k] == DRTB_SPHERE) {          // shape.hpp:105-106
-                            nrm = normalize(V3<R>{pt.x - nrm.x, pt.y - nrm.y, pt.z - nrm.z});
-                            unit_frame(nrm, tg, bt);
-                        } else {
-                            tg = {bs.frame[k][0], bs.frame[k][1], bs.frame[k][2]};
-                            bt = {bs.frame[k][3], bs.frame[k][4], bs.frame[k][5]};
-                        }
+                        analytic_frame(bs, k, pt, nrm, tg, bt);
                     }
                     long long pix; int i, x, y;
                     wf_pixel_of(sc, a, a.first_path + p, pix, i, x, y);
