@@ -420,6 +420,9 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     // a per-launch persisting access-policy window over the rings did not change that -- and keeping the lanes' own
     // records in the freed shared memory instead of local memory was slower (43.71 ms).  DRTB_RING forces either.
     if (queue_kind == 1 && !mesh && ctx->ring_policy == 2) queue_kind = 2;
+    // records of at most 8 vertices (the headline's 8 bounces) in the global ring: the short-record instantiation
+    // (render_kernels.cuh, QUEUE == 3), compiled for the all-diffuse kernels with per-thread gradient columns
+    if (queue_kind == 2 && a.max_depth <= 8 && smallp && !gen && !mixed) queue_kind = 3;
     if (queue_kind < 2) smem += ring_bytes;
     smem = (smem + 15) & ~size_t(15);
     const long long npix = (long long)rows * W;

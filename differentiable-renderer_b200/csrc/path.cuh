@@ -551,10 +551,10 @@ struct PathRecord {
 constexpr int kQueueSlots = 64;    // ring capacity per warp (power of two)
 constexpr int kQueueDepth = 16;    // deepest record the ring stores; deeper runs use the direct path
 
-template <typename R, bool MESH>
+template <typename R, bool MESH, int CAP = kQueueDepth>
 struct QueueView {                 // one record of one warp's ring
     using Id = typename PrimId<MESH>::type;
-    static constexpr int kCap = kQueueDepth;
+    static constexpr int kCap = CAP;   // bounds the L_{v+1} array of the sweeps (radiance_and_adjoint)
     const R* w_;                   // &ring_w[slot], stride kQueueSlots
     const Id* prim_;
     __device__ __forceinline__ R w(int v) const { return w_[v * kQueueSlots]; }

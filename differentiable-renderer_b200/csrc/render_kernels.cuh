@@ -21,6 +21,7 @@ using drtbh::first_use;
 using drtbh::ChunkPlan;
 using drtbh::plan_chunks;
 using drtbh::reduce_scratch_rows;
+constexpr int kShortDepth = 8;     // QUEUE == 3: record capacity of the short-record variant
 
 // The pixel loop of src/render.cpp:72-86.
 //   SMALLP: <= kSmallP parameters, gradients in per-thread shared columns
@@ -28,7 +29,10 @@ using drtbh::reduce_scratch_rows;
 //           ring before the sweeps.  0: no ring; 1: the ring lives in shared memory; 2: in a global scratch
 //           buffer (L1/L2 resident), chosen when the shared ring of a deep record (max_depth > 8
 //           in double) would cost resident blocks -- the ring carries only the ~16-21 % of the
-//           paths that are lit, so its latency does not matter, the occupancy does
+//           paths that are lit, so its latency does not matter, the occupancy does; 3: like 2 for records of at
+//           most kShortDepth vertices (the headline's 8 bounces): the per-thread record and the sweeps' L_{v+1}
+//           array are half as deep, 288 instead of 552 bytes of local memory per resident thread, which is what
+//           the L2 has to hold beside the rings
 #ifndef DRTB_MIN_BLOCKS
 #define DRTB_MIN_BLOCKS 1
 #endif
@@ -76,11 +80,12 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     const int passes = spp >= 32 ? (spp + 31) / 32 : 1;
     const R inv_p = a.absorb < 1.0 ? R(1.0 / (1.0 - a.absorb)) : R(0);
 
+    constexpr int kQD = QUEUE == 3 ? kShortDepth : kQueueDepth;   // record capacity of the compacting variants
     // this warp's ring (QUEUE only)
     const int qdepth = a.max_depth;
     unsigned char* ring = reinterpret_cast<unsigned char*>(s_dyn + acc_doubles) +
                           (QUEUE ? size_t(warp) * queue_bytes_per_warp(qdepth, sizeof(R), sizeof(Id)) : 0);
-    if constexpr (QUEUE == 2)
+    if constexpr (QUEUE >= 2)
         ring = a.ring_scratch + (size_t(blockIdx.x) * kWarpsPerBlock + warp) * queue_bytes_per_warp(qdepth, sizeof(R), sizeof(Id));
     R* ring_w = reinterpret_cast<R*>(ring);
     Id* ring_prim = reinterpret_cast<Id*>(ring + size_t(qdepth) * kQueueSlots * sizeof(R));
@@ -167,7 +172,7 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                 __syncwarp();
                 if (lane < m) {
                     const int slot = (q_head + lane) & (kQueueSlots - 1);
-                    QueueView<R, MESH> qv{ring_w + slot, ring_prim + slot};
+                    QueueView<R, MESH, kQD> qv{ring_w + slot, ring_prim + slot};
                     sweep(qv, ring_n[slot]);
                 }
                 __syncwarp();
@@ -179,14 +184,14 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                 const int i = i0 + pass * 32;
                 bool lit = false, close_call = false;
                 int n = 0;
-                PathRecord<R, MESH, QUEUE ? kQueueDepth : kMaxDepth> rec;
+                PathRecord<R, MESH, QUEUE ? kQD : kMaxDepth> rec;
                 if (lane_ok && i < spp) {
                     const uint64_t key = a.key0 + ((uint64_t)y * W + x) * (uint64_t)spp + (uint64_t)i;
                     const uint64_t base = key * kKeyMul;
                     V3<R> o = {sc.eye[0], sc.eye[1], sc.eye[2]};
                     V3<R> d = camera_ray(sc, x, y, base);
                     const uint32_t seg0 = cnt.segments;
-                    n = trace_path<R, MESH, QUEUE ? kQueueDepth : kMaxDepth, GEN, MIXED>(sc, bs, mat, no_bvh, base, 2u, o, d, a.min_bounces,
+                    n = trace_path<R, MESH, QUEUE ? kQD : kMaxDepth, GEN, MIXED>(sc, bs, mat, no_bvh, base, 2u, o, d, a.min_bounces,
                                                                                          a.absorb, a.max_depth, rec, lit, cnt);
                     if constexpr (MIXED) {
                         if (cnt.close_call) {               // this path belongs to the double re-trace, segments and all
@@ -692,7 +697,7 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
         if (rc != DRTB_OK) return rc;
         a.grad_partial = ctx->d_partial;
     }
-    if (QUEUE == 2) {
+    if (QUEUE >= 2) {
         const size_t per_warp = queue_bytes_per_warp(a.max_depth, sizeof(R), MESH ? sizeof(int32_t) : sizeof(uint8_t));
         rc = ensure(ctx, ctx->d_ring, ctx->ring_cap, size_t(grid) * kWarpsPerBlock * per_warp / sizeof(double));
         if (rc != DRTB_OK) return rc;
@@ -783,6 +788,9 @@ int launch_analytic(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, const d
     }
 #define DRTB_LAUNCH(SP, Q, G) launch_variant<R, SP, Q, false, G>(ctx, sc, a, l.smem, l.n_tasks, l.P3, l.want_grad, stream, rows)
 #define DRTB_BY_QUEUE(SP, G) (l.queue == 2 ? DRTB_LAUNCH(SP, 2, G) : l.queue == 1 ? DRTB_LAUNCH(SP, 1, G) : DRTB_LAUNCH(SP, 0, G))
+    // short records in the global ring: the all-diffuse kernel with per-thread gradient columns only (drtb.cu asks
+    // for it only there)
+    if (l.queue == 3 && !l.gen && l.smallp) return DRTB_LAUNCH(true, 3, false);
     // GEN: SpecularBxDF materials and/or a gradient image; the all-diffuse kernels do not carry that code
     if (l.gen) return l.smallp ? DRTB_BY_QUEUE(true, true) : DRTB_BY_QUEUE(false, true);
     return l.smallp ? DRTB_BY_QUEUE(true, false) : DRTB_BY_QUEUE(false, false);

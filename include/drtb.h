@@ -192,8 +192,9 @@ int drtb_scene_upload(drtb_ctx* ctx, const drtb_scene* scene);
  * parameter indices refer to that scene's params[]).  Copies the mesh, builds
  * the BVH on the GPU: Morton codes -> radix sort -> binary tree by PLOC
  * (parallel locally-ordered clustering; DRTB_BVH=lbvh selects Karras' radix
- * tree + bottom-up refit instead) -> collapse to a 4-wide BVH with <= 4
- * triangles per leaf.  mesh == NULL or n_triangles == 0 detaches the mesh.
+ * tree + bottom-up refit instead) -> collapse to an 8-wide compressed BVH
+ * (128-byte nodes, quantised child boxes) with <= 3 triangles per leaf.
+ * mesh == NULL or n_triangles == 0 detaches the mesh.
  * A later drtb_scene_upload detaches it as well. */
 int drtb_mesh_upload(drtb_ctx* ctx, const drtb_mesh* mesh);
 
