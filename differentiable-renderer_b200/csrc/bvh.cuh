@@ -244,11 +244,20 @@ static __global__ void lbvh_refit_kernel(int n, const int* __restrict__ parent, 
 // ---- PLOC -------------------------------------------------------------------
 // clusters[i] = node id of the i-th live cluster, in Morton order.
 // nearest[i] = the j in [i - R, i + R] \ {i} minimising area(box_i U box_j); ties -> smaller j.
+// The build loops are DEVICE-paced: the live cluster count m, the nodes made so far and the collapse's task count
+// live in a BuildState in device memory, every kernel of an iteration reads them and exits at once when there is
+// nothing (left) for its block to do, and a one-thread kernel advances the state between iterations.  The host
+// launches a fixed schedule of iterations (grids sized for an upper bound of the work) and reads the state back
+// once per batch, not once per iteration.
+struct BuildState { int m, made, n_tasks, error; };
+
 static __global__ void __launch_bounds__(256)
-ploc_nearest_kernel(const int* __restrict__ clusters, int m, BinTree t, int* __restrict__ nearest)
+ploc_nearest_kernel(const int* __restrict__ clusters, const BuildState* __restrict__ state, BinTree t, int* __restrict__ nearest)
 {
     constexpr int R = kPlocRadius, T = 256;
     __shared__ float4 s_lo[T + 2 * R], s_hi[T + 2 * R];
+    const int m = state->m;
+    if (m <= 1 || blockIdx.x * T >= m) return;
     const int base = blockIdx.x * T - R;
     for (int k = threadIdx.x; k < T + 2 * R; k += T) {
         const int g = base + k;
@@ -273,10 +282,14 @@ ploc_nearest_kernel(const int* __restrict__ clusters, int m, BinTree t, int* __r
 
 // flags[i]: low 32 bits = 1 if cluster i survives (alone or as the merged pair's
 // left member), high 32 bits = 1 if i leads a merge (allocates a node)
-static __global__ void ploc_flag_kernel(const int* __restrict__ nearest, int m, uint64_t* __restrict__ flags)
+// (the grid covers n + 1 entries: everything from m on is zeroed, so that one scan of fixed length serves every iteration)
+static __global__ void ploc_flag_kernel(const int* __restrict__ nearest, const BuildState* __restrict__ state, int n,
+                                        uint64_t* __restrict__ flags)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
+    const int m = state->m;
+    if (m <= 1 || i > n) return;
+    if (i >= m) { flags[i] = 0; return; }
     const int j = nearest[i];
     const bool mutual = j >= 0 && nearest[j] == i;
     const uint64_t keep = !(mutual && j < i);
@@ -286,11 +299,12 @@ static __global__ void ploc_flag_kernel(const int* __restrict__ nearest, int m, 
 
 // scan[i] = exclusive prefix sums of flags; merged leaders create node n + first_node + (#leaders before i)
 static __global__ void ploc_merge_kernel(const int* __restrict__ clusters, const int* __restrict__ nearest,
-                                  const uint64_t* __restrict__ flags, const uint64_t* __restrict__ scan, int m, int n,
-                                  int first_node, BinTree t, int* __restrict__ out)
+                                  const uint64_t* __restrict__ flags, const uint64_t* __restrict__ scan,
+                                  const BuildState* __restrict__ state, int n, BinTree t, int* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
+    const int m = state->m, first_node = state->made;
+    if (m <= 1 || i >= m) return;
     const uint64_t f = flags[i];
     if (!(f & 1u)) return;
     const int pos = int(scan[i] & 0xffffffffu);
@@ -306,6 +320,19 @@ static __global__ void ploc_merge_kernel(const int* __restrict__ clusters, const
         id = n + k;
     }
     out[pos] = id;
+}
+
+// after the merge: m <- survivors, made += merged (scan[m] holds both totals); an iteration without a merge cannot
+// happen (the globally closest pair is mutual) and is reported instead of looping for ever
+static __global__ void ploc_advance_kernel(const uint64_t* __restrict__ scan, BuildState* __restrict__ state)
+{
+    const int m = state->m;
+    if (m <= 1) return;
+    const uint64_t tot = scan[m];
+    const int kept = int(tot & 0xffffffffu), merged = int(tot >> 32);
+    if (merged < 1 || kept != m - merged) { state->error = 1; state->m = 0; return; }
+    state->m = kept;
+    state->made += merged;
 }
 
 // ---- collapse to the 8-wide compressed BVH ------------------------------------
@@ -326,13 +353,13 @@ __device__ __forceinline__ int bin_count(const BinTree& t, int id) { return __fl
 // lies; a ray then visits the slots of a popped group in the order of (slot ^ its direction octant), near side
 // first, without sorting anything.
 // One thread per (binary node -> wide node index) task of this level.
-static __global__ void collapse8_kernel(const int2* __restrict__ tasks, int n_tasks, int n, BinTree t,
+static __global__ void collapse8_kernel(const int2* __restrict__ tasks, const BuildState* __restrict__ state, int n, BinTree t,
                                         const uint32_t* __restrict__ sorted_tri, uint4* __restrict__ nodes,
                                         int32_t* __restrict__ leaf_order, CollapseCounters* __restrict__ cnt,
                                         int2* __restrict__ next_tasks)
 {
     const int ti = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ti >= n_tasks) return;
+    if (ti >= state->n_tasks) return;
     const int b = tasks[ti].x, self = tasks[ti].y;
     int cand[8]; int nc;
     if (b < n || bin_count(t, b) <= kLeafMax) { cand[0] = b; nc = 1; }        // tiny mesh: the root is a leaf
@@ -432,6 +459,13 @@ static __global__ void collapse8_kernel(const int2* __restrict__ tasks, int n_ta
     out[1] = make_uint4(uint32_t(child_base), uint32_t(tri_base), meta[0], meta[1]);
 #pragma unroll
     for (int k = 0; k < 6; ++k) out[2 + k] = make_uint4(q[k][0], q[k][1], q[k][2], q[k][3]);
+}
+
+// between two levels of the collapse: the tasks the level queued become the next level's
+static __global__ void collapse_advance_kernel(CollapseCounters* __restrict__ cnt, BuildState* __restrict__ state)
+{
+    state->n_tasks = cnt->next;
+    cnt->next = 0;
 }
 
 // leaf-ordered float triangles: (v0.xyz, e1.x) (e1.yz, e2.xy) (e2.z, max|e1|, max|e2|, original index)

@@ -301,12 +301,13 @@ int mesh_upload_impl(drtb_ctx* ctx, const drtb_mesh* mesh)
     int2 *d_children = nullptr, *d_tasks = nullptr, *d_tasks2 = nullptr;
     int *d_parent = nullptr, *d_arrive = nullptr, *d_clusters = nullptr, *d_clusters2 = nullptr, *d_nearest = nullptr;
     int32_t* d_leaf_order = nullptr; CollapseCounters* d_cnt = nullptr; void *d_tmp = nullptr, *d_tmp2 = nullptr;
+    BuildState* d_state = nullptr;
     auto cleanup = [&]() {
         cudaFree(d_vert); cudaFree(d_idx); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_blo); cudaFree(d_bhi); cudaFree(d_wide);
         cudaFree(d_bounds); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_flags); cudaFree(d_scan); cudaFree(d_vals);
         cudaFree(d_vals2); cudaFree(d_children); cudaFree(d_tasks); cudaFree(d_tasks2); cudaFree(d_parent); cudaFree(d_arrive);
         cudaFree(d_clusters); cudaFree(d_clusters2); cudaFree(d_nearest); cudaFree(d_leaf_order); cudaFree(d_cnt);
-        cudaFree(d_tmp); cudaFree(d_tmp2);
+        cudaFree(d_tmp); cudaFree(d_tmp2); cudaFree(d_state);
     };
 #define CKM(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); free_mesh(ctx); return fail(ctx, e_ == cudaErrorMemoryAllocation ? DRTB_ERR_NOMEM : DRTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
     cudaStream_t st = ctx->stream;
@@ -326,6 +327,9 @@ int mesh_upload_impl(drtb_ctx* ctx, const drtb_mesh* mesh)
     CKM(cudaMalloc((void**)&d_tasks, nn * sizeof(int2)));     CKM(cudaMalloc((void**)&d_tasks2, nn * sizeof(int2)));
     CKM(cudaMalloc((void**)&d_leaf_order, nn * sizeof(int32_t)));
     CKM(cudaMalloc((void**)&d_cnt, sizeof(CollapseCounters)));
+    CKM(cudaMalloc((void**)&d_state, sizeof(BuildState)));
+    const BuildState init_state{int(n), 0, 1, 0};
+    CKM(cudaMemcpyAsync(d_state, &init_state, sizeof init_state, cudaMemcpyHostToDevice, ctx->stream));
     CKM(cudaMemcpyAsync(d_vert, mesh->vertices, size_t(nv) * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     CKM(cudaMemcpyAsync(d_idx, mesh->indices, nn * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (mesh->color) CKM(cudaMemcpyAsync(ctx->d_tri_color, mesh->color, nn * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -372,23 +376,28 @@ int mesh_upload_impl(drtb_ctx* ctx, const drtb_mesh* mesh)
         CKM(cudaMalloc(&d_tmp2, scan_bytes));
         iota_kernel<<<G, T, 0, st>>>(d_clusters, int(n));
         CKM(cudaGetLastError());
+        CKM(cudaMemsetAsync(d_flags, 0, (nn + 1) * sizeof(uint64_t), st));
+        // device-paced (bvh.cuh, BuildState): batches of kPlocBatch iterations between two reads of the state
+        constexpr int kPlocBatch = 8;
+        const int g1 = int((nn + 1 + T - 1) / T);
         int m = int(n), made = 0;
-        while (m > 1) {
-            const int g = (m + T - 1) / T;
-            ploc_nearest_kernel<<<g, 256, 0, st>>>(d_clusters, m, bt, d_nearest);
-            ploc_flag_kernel<<<g, T, 0, st>>>(d_nearest, m, d_flags);
-            CKM(cudaMemsetAsync(d_flags + m, 0, sizeof(uint64_t), st));
-            CKM(cub::DeviceScan::ExclusiveSum(d_tmp2, scan_bytes, d_flags, d_scan, m + 1, st));   // scan[m] = totals
-            ploc_merge_kernel<<<g, T, 0, st>>>(d_clusters, d_nearest, d_flags, d_scan, m, int(n), made, bt, d_clusters2);
-            CKM(cudaGetLastError());
-            uint64_t tot = 0;
-            CKM(cudaMemcpyAsync(&tot, d_scan + m, sizeof tot, cudaMemcpyDeviceToHost, st));
+        for (long long it = 0; m > 1; ) {
+            for (int k = 0; k < kPlocBatch; ++k, ++it) {
+                int* src = (it & 1) ? d_clusters2 : d_clusters;
+                int* dst = (it & 1) ? d_clusters : d_clusters2;
+                ploc_nearest_kernel<<<G, 256, 0, st>>>(src, d_state, bt, d_nearest);
+                ploc_flag_kernel<<<g1, T, 0, st>>>(d_nearest, d_state, int(n), d_flags);
+                CKM(cub::DeviceScan::ExclusiveSum(d_tmp2, scan_bytes, d_flags, d_scan, int(n) + 1, st));   // scan[m] = totals
+                ploc_merge_kernel<<<G, T, 0, st>>>(src, d_nearest, d_flags, d_scan, d_state, int(n), bt, dst);
+                ploc_advance_kernel<<<1, 1, 0, st>>>(d_scan, d_state);
+                CKM(cudaGetLastError());
+                ctx->launches += 5;
+            }
+            BuildState h{};
+            CKM(cudaMemcpyAsync(&h, d_state, sizeof h, cudaMemcpyDeviceToHost, st));
             CKM(cudaStreamSynchronize(st));
-            const int kept = int(tot & 0xffffffffu), merged = int(tot >> 32);
-            if (merged < 1 || kept != m - merged) { cleanup(); free_mesh(ctx); return fail(ctx, DRTB_ERR_CUDA, "PLOC iteration made no progress"); }
-            made += merged; m = kept;
-            std::swap(d_clusters, d_clusters2);
-            ctx->launches += 4;
+            if (h.error || (h.m >= m && h.m > 1)) { cleanup(); free_mesh(ctx); return fail(ctx, DRTB_ERR_CUDA, "PLOC iteration made no progress"); }
+            m = h.m; made = h.made;
         }
         root = int(n) + made - 1;                            // the last node created
     }
@@ -397,16 +406,26 @@ int mesh_upload_impl(drtb_ctx* ctx, const drtb_mesh* mesh)
     const int2 root_task = make_int2(root, 0);
     CKM(cudaMemcpyAsync(d_cnt, &init_cnt, sizeof init_cnt, cudaMemcpyHostToDevice, st));
     CKM(cudaMemcpyAsync(d_tasks, &root_task, sizeof root_task, cudaMemcpyHostToDevice, st));
+    // device-paced as well: a level's grid is sized for an upper bound of its tasks (8 x the level above, at most n),
+    // the task count itself stays on the device; the host looks once per kCollapseBatch levels
+    constexpr int kCollapseBatch = 4;
     CollapseCounters h_cnt = init_cnt;
-    for (int n_tasks = 1; n_tasks > 0;) {
-        collapse8_kernel<<<(n_tasks + T - 1) / T, T, 0, st>>>(d_tasks, n_tasks, int(n), bt, d_vals2, d_wide, d_leaf_order, d_cnt, d_tasks2);
-        CKM(cudaGetLastError());
+    long long bound = 1;
+    for (long long lvl = 0, n_tasks = 1; n_tasks > 0; ) {
+        for (int k = 0; k < kCollapseBatch; ++k, ++lvl) {
+            int2* src = (lvl & 1) ? d_tasks2 : d_tasks;
+            int2* dst = (lvl & 1) ? d_tasks : d_tasks2;
+            collapse8_kernel<<<int((bound + T - 1) / T), T, 0, st>>>(src, d_state, int(n), bt, d_vals2, d_wide, d_leaf_order, d_cnt, dst);
+            collapse_advance_kernel<<<1, 1, 0, st>>>(d_cnt, d_state);
+            CKM(cudaGetLastError());
+            bound = std::min<long long>(bound * 8, (long long)nn);
+            ctx->launches += 2;
+        }
+        BuildState h{};
+        CKM(cudaMemcpyAsync(&h, d_state, sizeof h, cudaMemcpyDeviceToHost, st));
         CKM(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
         CKM(cudaStreamSynchronize(st));
-        n_tasks = h_cnt.next;
-        CKM(cudaMemsetAsync(&d_cnt->next, 0, sizeof(int), st));
-        std::swap(d_tasks, d_tasks2);
-        ctx->launches++;
+        n_tasks = h.n_tasks;
     }
     if (h_cnt.tris != int(n)) { cleanup(); free_mesh(ctx); return fail(ctx, DRTB_ERR_CUDA, "BVH collapse lost triangles"); }
     // what the traversal reads -- float triangles (leaf order), then the wide nodes -- in ONE allocation, so that a
