@@ -181,7 +181,8 @@ void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
     d.n_over_spheres = int(spheres.size()) - d.n_fast_spheres;
     auto put = [&](int slot, int i) {
         for (int j = 0; j < 4; ++j) d.prim[slot][j] = R(c.prims[i].v[j]);
-        d.r2[slot] = R(c.prims[i].v[3] * c.prims[i].v[3]);            // spheres: m_radius * m_radius, shape.hpp:85
+        for (int j = 0; j < 3; ++j) d.sph[slot][j] = R(c.prims[i].v[j]);
+        d.sph[slot][3] = R(c.prims[i].v[3] * c.prims[i].v[3]);        // spheres: m_radius * m_radius, shape.hpp:85
         d.id[slot] = i;
         d.slot[i] = int8_t(slot);
     };
@@ -196,8 +197,8 @@ void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
         d.n_aa[ax] = n;
         for (int j = 0; j < n; ++j) {
             const int i = axis_planes[ax][j];
-            d.aa_c[ax][kAxisFast - n + j] = R(c.prims[i].v[ax] * c.prims[i].v[3]);   // s * off, exact (s = +-1)
-            d.aa_id[ax][kAxisFast - n + j] = i;
+            d.aa[ax][kAxisFast - n + j].c = R(c.prims[i].v[ax] * c.prims[i].v[3]);  // s * off, exact (s = +-1)
+            d.aa[ax][kAxisFast - n + j].id = i;
             put(store++, i);
         }
     }

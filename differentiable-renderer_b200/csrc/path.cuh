@@ -44,14 +44,14 @@ struct alignas(16) DevScene {
     // Planes whose normal is exactly +-e_x, +-e_y or +-e_z (the walls of a box
     // scene; 5 of the Cornell box's 6) are NOT scanned there: for n = s e_a,
     // t = (o.n - off) / (d.(-n)) = (s off - o_a) / d_a with every product exact, so
-    // they sit in aa_c / aa_id (up to kAxisFast per axis, right-aligned) and cost one
+    // they sit in aa[][] (up to kAxisFast per axis, right-aligned) and cost one
     // subtraction and one multiplication by the per-segment 1 / d_a.  Their n, off
     // stay in prim[] behind the scanned slots for the per-lane lookups.
     R       prim[kSlots][4];             // plane: n.xyz (RAW), offset ; sphere: c.xyz, r
-    R       r2[kSlots];                  // sphere: r * r (host double)
+    R       sph[kSlots][4];              // sphere slots as the scan reads them: c.xyz, r * r (host double) -- two 128-bit loads
     int32_t id[kSlots];                  // scan slot -> scene index
-    R       aa_c[3][kAxisFast];          // s * offset: the plane is  p_a = aa_c
-    int32_t aa_id[3][kAxisFast];
+    struct alignas(16) AxisSlot { R c; int32_t id; int32_t pad; };   // s * offset (the plane is p_a = c) and the scene index: one load
+    AxisSlot aa[3][kAxisFast];
     int32_t n_aa[3];
     int32_t n_fast_planes, n_fast_spheres, n_over_planes, n_over_spheres;
     // Indexed by SCENE index:
@@ -135,7 +135,7 @@ struct BlockScene {
     R       prim[kMaxPrims][4];
     R       frame[kMaxPrims][6];         // plane tangent + bitangent
     R       param[kMaxParams * 3];       // staged only when n_params <= kMaxParams
-    int32_t color[kMaxPrims], emis[kMaxPrims];
+    int2    em_col[kMaxPrims];           // (emission, albedo) parameter indices: one 64-bit load per vertex
     int8_t  type[kMaxPrims];
     int8_t  mtype[kMaxPrims];
     R       expo[kMaxPrims];
@@ -151,7 +151,7 @@ __device__ __forceinline__ void load_block_scene(BlockScene<R>& bs, const DevSce
     for (int i = threadIdx.x; i < sc.n_prims * 6; i += blockDim.x)
         bs.frame[i / 6][i % 6] = sc.frame[i / 6][i % 6];
     for (int i = threadIdx.x; i < sc.n_prims; i += blockDim.x) {
-        bs.type[i] = sc.type[i]; bs.color[i] = sc.color[i]; bs.emis[i] = sc.emis[i];
+        bs.type[i] = sc.type[i]; bs.em_col[i] = make_int2(sc.emis[i], sc.color[i]);
         bs.mtype[i] = sc.mtype[i]; bs.expo[i] = sc.expo[i];
     }
     if (sc.n_params <= kMaxParams)
@@ -296,7 +296,7 @@ template <> struct HasMargin<ClosestMargin> { static constexpr bool value = true
 template <typename R, typename C>
 __device__ __forceinline__ void axis_plane_test(const DevScene<R>& sc, int axis, int slot, R o_a, R inv_a, C& cl)
 {
-    cl.offer_nz(Real<R>::mul_nz(sc.aa_c[axis][slot] - o_a, inv_a), sc.aa_id[axis][slot]);
+    cl.offer_nz(Real<R>::mul_nz(sc.aa[axis][slot].c - o_a, inv_a), sc.aa[axis][slot].id);
 }
 
 template <typename R, typename C>
@@ -319,10 +319,10 @@ __device__ __forceinline__ void plane_test(const DevScene<R>& sc, int slot, V3<R
 template <typename R, typename C>
 __device__ __forceinline__ void sphere_test(const DevScene<R>& sc, int slot, V3<R> o, V3<R> d, C& cl)
 {
-    const R a0 = sc.prim[slot][0], a1 = sc.prim[slot][1], a2 = sc.prim[slot][2];
+    const R a0 = sc.sph[slot][0], a1 = sc.sph[slot][1], a2 = sc.sph[slot][2];
     const V3<R> oc = {o.x - a0, o.y - a1, o.z - a2};
     const R hb = dot(oc, d);                       // b/2
-    const R c = Real<R>::fma(oc.z, oc.z, Real<R>::fma(oc.y, oc.y, Real<R>::fma(oc.x, oc.x, -sc.r2[slot])));
+    const R c = Real<R>::fma(oc.z, oc.z, Real<R>::fma(oc.y, oc.y, Real<R>::fma(oc.x, oc.x, -sc.sph[slot][3])));
     const R disc = Real<R>::fma(hb, hb, -c);       // (b^2 - 4c)/4
     if constexpr (HasMargin<C>::value) {
         const R a3 = sc.prim[slot][3];
@@ -574,16 +574,17 @@ __host__ __device__ constexpr size_t queue_bytes_per_warp(int depth, size_t real
 template <typename R, bool MESH> struct Materials;
 template <typename R> struct Materials<R, false> {
     const BlockScene<R>* bs;
-    __device__ __forceinline__ int em(int k) const { return bs->emis[k]; }
-    __device__ __forceinline__ int col(int k) const { return bs->color[k]; }
+    __device__ __forceinline__ int2 em_col(int k) const { return bs->em_col[k]; }
     __device__ __forceinline__ R param(int i) const { return bs->param[i]; }
 };
 template <typename R> struct Materials<R, true> {
     const BlockScene<R>* bs;
     MeshView mesh;
     const double* params;
-    __device__ __forceinline__ int em(int k) const { return k < mesh.n_prims ? bs->emis[k] : __ldg(mesh.emis + (k - mesh.n_prims)); }
-    __device__ __forceinline__ int col(int k) const { return k < mesh.n_prims ? bs->color[k] : __ldg(mesh.color + (k - mesh.n_prims)); }
+    __device__ __forceinline__ int2 em_col(int k) const
+    {
+        return k < mesh.n_prims ? bs->em_col[k] : make_int2(__ldg(mesh.emis + (k - mesh.n_prims)), __ldg(mesh.color + (k - mesh.n_prims)));
+    }
     __device__ __forceinline__ R param(int i) const { return R(__ldg(params + i)); }
 };
 
@@ -647,7 +648,8 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
         ++cnt.segments;
         if (k < 0) { alive = false; continue; }             // miss, :134-135
         V3<R> pt = {o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
-        const int em = mat.em(k), col = mat.col(k);
+        const int2 ec = mat.em_col(k);
+        const int em = ec.x, col = ec.y;
         lit |= em >= 0;
         rec.prim_[n] = Id(k);
         // absorb >= 1: the next trace() call returns 0 before it looks at the ray (:128-129), so this
@@ -737,7 +739,8 @@ __device__ __forceinline__ bool trace_segment(const DevScene<R>& sc, const Block
     ++cnt.segments;
     if (k < 0) return true;                                 // miss, :134-135
     const V3<R> pt = {o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
-    const int em = mat.em(k), col = mat.col(k);
+    const int2 ec = mat.em_col(k);
+        const int em = ec.x, col = ec.y;
     lit |= em >= 0;
     rec.prim_[n] = uint8_t(k);
     if (col < 0) {                                          // null BxDF, :25-26, 38-39
@@ -779,7 +782,8 @@ __device__ __noinline__ void radiance_and_adjoint_deep(const Mat& mat, const Rec
         L[0] = L[1] = L[2] = R(0);
         for (int v = n - 1; v >= first; --v) {
             const int k = rec.prim(v);
-            const int em = mat.em(k), col = mat.col(k);
+            const int2 ec = mat.em_col(k);
+        const int em = ec.x, col = ec.y;
             const R ip = v >= min_bounces ? inv_p : R(1);
             const R f = rec.w(v) * Real<R>::inv_pi();
 #pragma unroll
@@ -795,7 +799,8 @@ __device__ __noinline__ void radiance_and_adjoint_deep(const Mat& mat, const Rec
     R g[3] = {g0[0], g0[1], g0[2]};
     for (int v = 0; v < n; ++v) {
         const int k = rec.prim(v);
-        const int em = mat.em(k), col = mat.col(k);
+        const int2 ec = mat.em_col(k);
+        const int em = ec.x, col = ec.y;
         const R ip = v >= min_bounces ? inv_p : R(1);
         const R f = rec.w(v) * Real<R>::inv_pi();
         R Ln[3];
@@ -833,7 +838,8 @@ __device__ __forceinline__ void radiance_and_adjoint(const Mat& mat, const Rec& 
     R L[3] = {R(0), R(0), R(0)};
     for (int v = n - 1; v >= 0; --v) {
         const int k = rec.prim(v);
-        const int em = mat.em(k), col = mat.col(k);
+        const int2 ec = mat.em_col(k);
+        const int em = ec.x, col = ec.y;
         const R ip = v >= min_bounces ? inv_p : R(1);
         const R f = rec.w(v) * Real<R>::inv_pi();
         if (want_grad) { Ls[v + 1][0] = L[0]; Ls[v + 1][1] = L[1]; Ls[v + 1][2] = L[2]; }
@@ -849,7 +855,8 @@ __device__ __forceinline__ void radiance_and_adjoint(const Mat& mat, const Rec& 
     R g[3] = {g0[0], g0[1], g0[2]};
     for (int v = 0; v < n; ++v) {
         const int k = rec.prim(v);
-        const int em = mat.em(k), col = mat.col(k);
+        const int2 ec = mat.em_col(k);
+        const int em = ec.x, col = ec.y;
         const R ip = v >= min_bounces ? inv_p : R(1);
         const R f = rec.w(v) * Real<R>::inv_pi();
 #pragma unroll

@@ -22,7 +22,7 @@ template <typename R> struct Real;
 // (34 per ray segment for the sincos polynomials alone in the first builds).
 struct ConstF64 {
     double sin_c[8], cos_c[8];
-    double half_pi, pi, inv_pi, inv_m, m, origin_eps;
+    double half_pi, pi, inv_pi, inv_m, m, origin_eps, k375;     // k375 = 3/8 of the Newton corrections (rsqrt, sqrt)
     double tab_s[3], tab_c[2], tab_step;         // sincos_tab: -1/7!, 1/5!, -1/3! ; -1/6!, 1/4! ; 2 pi / M
 };
 // (static: every translation unit of the library carries its own copy -- no relocatable device code)
@@ -31,7 +31,7 @@ static __constant__ ConstF64 kC64 = {
      2.7557319223985893e-06, -1.9841269841269841e-04, 8.3333333333333332e-03, -1.6666666666666666e-01},
     {-1.5619206968586225e-16, 4.7794773323873853e-14, -1.1470745597729725e-11, 2.0876756987868100e-09,
      -2.7557319223985888e-07, 2.4801587301587302e-05, -1.3888888888888889e-03, 4.1666666666666664e-02},
-    1.5707963267948966, 3.14159265358979323846, 0.31830988618379067154, 1.0 / 2147483647.0, 2147483647.0, 1e-3,
+    1.5707963267948966, 3.14159265358979323846, 0.31830988618379067154, 1.0 / 2147483647.0, 2147483647.0, 1e-3, 0.375,
     {-1.984126984126984e-04, 8.333333333333333e-03, -1.6666666666666666e-01},
     {-1.388888888888889e-03, 4.1666666666666664e-02}, 2.925836159896768e-09};
 
@@ -118,7 +118,7 @@ template <> struct Real<double> {
         double y;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); // e0 <= 2^-22
         const double e = ::fma(-x * y, y, 1.0);                  // 1 - x y^2
-        return ::fma(y, ::fma(0.375, e, 0.5) * e, y);            // y (1 + e/2 + 3e^2/8): ~e0^3
+        return ::fma(y, ::fma(kC64.k375, e, 0.5) * e, y);            // y (1 + e/2 + 3e^2/8): ~e0^3
     }
     // x >= 0; NaN for x < 0.  g = x y0 ~ sqrt(x) is corrected directly,
     // g (1 + e/2 + 3e^2/8) with e = 1 - g y0: five FP64 instructions, no final
@@ -132,7 +132,7 @@ template <> struct Real<double> {
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(__hiloint2double(int(xh), __double2loint(x))));   // e0 <= 2^-22
         const double g = x * y;
         const double e = ::fma(-g, y, 1.0);
-        return ::fma(g, ::fma(0.375, e, 0.5) * e, g);
+        return ::fma(g, ::fma(kC64.k375, e, 0.5) * e, g);
     }
     static __device__ __forceinline__ double pow(double a, double b) { return ::pow(a, b); }   // SpecularBxDF only
     // sin/cos(2*pi*u), u in [0, 1).  The reference forms phi = 2*pi*u in double and

@@ -379,7 +379,8 @@ wf_shade(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArgs 
                 V3<R> o = {ra.x, ra.y, ra.z}, d = {ra.w, rb.x, rb.y};
                 const R t = rb.z;
                 const V3<R> pt = {o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
-                const int em = mat.em(k), col = mat.col(k);
+                const int2 ec = mat.em_col(k);
+                const int em = ec.x, col = ec.y;
                 lit |= em >= 0;
                 b.rec_prim[(size_t)n * a.batch + p] = k;
                 if (col < 0) {                                    // null BxDF, :25-26, 38-39
