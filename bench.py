@@ -535,13 +535,22 @@ def run_b200_arm(a):
     alg_bytes = rows * W * 3 * 8 + P * 3 * 8                            # the outputs; the scene is 0.4 KB
     # DRAM bytes per launch come from an ncu capture (counters are not readable from inside the run); the capture
     # records the hash of the kernel sources it was taken at and a figure from other sources is NOT reported
-    traffic, traffic_note = None, "no ncu capture for this workload under profiles/"
+    traffic, traffic_note, issue = None, "no ncu capture for this workload under profiles/", None
     prof = ROOT / "profiles" / "ncu_render_kernel.json"
     if prof.exists():
         try:
             ent = json.loads(prof.read_text()).get(f"{a.precision}_{W}x{H}_{spp}spp_b{B}", {})
             if ent.get("source_sha") == kernel_source_sha():
                 traffic, traffic_note = ent.get("dram_bytes_per_launch"), f"ncu --set full, {ent.get('source')}"
+                if ent.get("warp_instructions") and world == 1:
+                    # The bound this kernel actually runs against: one instruction per cycle and
+                    # scheduler, an FP64 instruction holding the dispatch port for two.  Instruction counts from the
+                    # same ncu capture as `traffic`, time and clock from this run.
+                    slots = ent["warp_instructions"] + ent.get("fp64_warp_instructions", 0)
+                    cycles = kern_ms * 1e-3 * 1.965e9 * ctx_sm_count * 4
+                    issue = {"warp_instructions": ent["warp_instructions"], "fp64_warp_instructions": ent.get("fp64_warp_instructions"),
+                             "issue_slots_needed": slots, "issue_cycles_available": cycles, "frac": slots / cycles,
+                             "note": "instructions + FP64 instructions (two dispatch cycles each) over kernel time x 1.965 GHz x 4 schedulers x SMs"}
             elif ent:
                 traffic_note = (f"stale: {ent.get('source')} was captured at kernel sources {ent.get('source_sha')}, "
                                 f"this build is {kernel_source_sha()} (tools/ncu_traffic.sh regenerates it)")
@@ -556,7 +565,7 @@ def run_b200_arm(a):
                        "MEASURED_PEAKS.json has no non-tensor FMA figure",
         "peak_nominal": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf,
         "peak_nominal_source": f"{ctx_sm_count} SMs x {64 if a.precision == 'f64' else 128} FMA/clk x 2 x 1.965 GHz",
-        "algorithmic_flop_per_launch": flop_launch, "kernel_ms": kern_ms,
+        "algorithmic_flop_per_launch": flop_launch, "kernel_ms": kern_ms, "issue_bound": issue,
         "hbm": {"bound": "hbm", "achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",

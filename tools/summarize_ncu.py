@@ -78,7 +78,10 @@ if json_key:
     hsh = hashlib.sha256()
     for nm in ("render_kernels.cuh", "path.cuh", "real.cuh", "rng.cuh", "sinks.cuh"):     # = bench.py kernel_source_sha()
         hsh.update((ROOT / "differentiable-renderer_b200" / "csrc" / nm).read_bytes())
+    fp64 = sum(mix[o][0] for o in ("DFMA", "DMUL", "DADD", "DSETP"))
     j[json_key] = {"source_sha": hsh.hexdigest()[:16],
                    "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+                   "warp_instructions": tot, "fp64_warp_instructions": fp64,
+                   "issue_active_pct": float(vals["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
                    "kernel_ms_under_ncu": float(vals["gpu__time_duration.sum"][0]), "source": f"profiles/{name}_summary.txt"}
     jf.write_text(json.dumps(j, indent=1) + "\n")
