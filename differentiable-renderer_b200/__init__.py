@@ -7,7 +7,7 @@ for); import it through the `drt_b200` shim at the repo root.
 """
 from . import abi
 from .abi import (DrtbError, DrtbLibraryMissing, F32, F64, MIXED, FLAG_GRAD, FLAG_IMAGE,
-                  FLAG_NO_BVH, FLAG_STATS, load_library)
+                  FLAG_NO_BVH, FLAG_STATS, FLAG_DETERMINISTIC, load_library)
 from .scene import (AreaEmitter, Camera, DiffuseBxDF, Param, Plane, SceneDesc, SpecularBxDF, Sphere, TriangleMesh,
                     cornell_box, make_opts, specular_box, tessellated_room)
 from .render import Context, render, shard_rows, stream_draw

@@ -18,7 +18,7 @@ OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2
 SPHERE, PLANE = 0, 1
 DIFFUSE, SPECULAR = 0, 1
 F64, F32, MIXED = 0, 1, 2
-FLAG_IMAGE, FLAG_GRAD, FLAG_STATS, FLAG_NO_BVH = 1, 2, 4, 8
+FLAG_IMAGE, FLAG_GRAD, FLAG_STATS, FLAG_NO_BVH, FLAG_DETERMINISTIC = 1, 2, 4, 8, 16
 
 STREAM_KEY_MUL = 0x9E3779B97F4A7C15
 IPC_HANDLE_BYTES = 64

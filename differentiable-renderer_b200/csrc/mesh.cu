@@ -21,6 +21,13 @@ using drtbh::shard_rows_impl;
 using drtbh::effective_max_depth;
 using drtbh::GradImage;
 
+// DRTB_FLAG_DETERMINISTIC: the gradient buffer held 64-bit fixed-point sums (AtomicSink); back to doubles, in place
+__global__ void fixed_to_double_kernel(double* __restrict__ grad, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) grad[i] = double(reinterpret_cast<const long long*>(grad)[i]) * (1.0 / kFixedScale);
+}
+
 __global__ void iota_kernel(int* __restrict__ v, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,7 +61,7 @@ wf_adjoint(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArg
     const long long n_warps = (long long)gridDim.x * kWarpsPerBlock;
     const R inv_p = a.absorb < 1.0 ? R(1.0 / (1.0 - a.absorb)) : R(0);
     SmemSink ssink{s_acc + threadIdx.x};
-    AtomicSink asink{a.grad_atomic};
+    AtomicSink asink{a.grad_atomic, (a.flags & DRTB_FLAG_DETERMINISTIC) != 0};
     Materials<R, true> mat;
     mat.bs = &bs; mat.mesh = a.mesh; mat.params = a.params;
     uint32_t n_lit = 0;
@@ -264,6 +271,11 @@ int launch_wavefront(drtb_ctx* ctx, const DevScene<R>& sc, const drtb_render_opt
     if (l2_window && ctx->l2_reserved) {
         cudaStreamAttrValue av{};                            // num_bytes = 0: window off for whatever the caller enqueues next
         CK(ctx, cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
+    if (want_grad && !smallp && (o->flags & DRTB_FLAG_DETERMINISTIC) && !ctx->dry) {
+        fixed_to_double_kernel<<<(P3 + 255) / 256, 256, 0, stream>>>(d_grad, P3);
+        CK(ctx, cudaGetLastError());
+        ctx->launches++;
     }
     if (want_grad && smallp) {
         // at most 148 * 8 * n_batches rows: the fixed-order reduction of drtb.cu (one block up to 4096 rows)

@@ -44,8 +44,13 @@ struct SmemAtomicSink {
 // one red.global.add.f64 for the group: __match_any_sync on the scalar's index among the lanes that reached this
 // add together, the group's values summed in lane order through shuffles.  Distinct scalars (the usual case at
 // deeper vertices) cost the match and one vote on top of the atomic.
+// DRTB_FLAG_DETERMINISTIC (`fixed`): the same grouping, but every contribution is first rounded to 64-bit fixed point
+// (2^-32) and the sums are integer sums -- associative, so the result does not depend on which lanes met in a warp or
+// on the order the atomics land in; fixed_to_double_kernel converts the buffer in place after the last batch.
+constexpr double kFixedScale = 4294967296.0;      // 2^32
 struct AtomicSink {
     double* grad;
+    bool fixed = false;
     template <typename R> __device__ __forceinline__ void add(int p, int c, R v)
     {
         const unsigned active = __activemask();
@@ -54,8 +59,19 @@ struct AtomicSink {
         const int size = __popc(group);
         const int rounds = __reduce_max_sync(active, size);        // 1: no two lanes share a scalar
         const int lane = threadIdx.x & 31;
-        double sum = double(v);
         const int first = __ffs(group) - 1;
+        if (fixed) {
+            const long long q = __double2ll_rn(double(v) * kFixedScale);
+            long long sum = q;
+            for (int r = 1; r < rounds; ++r) {
+                const int src = r < size ? int(__fns(group, 0, r + 1)) : lane;
+                const long long other = __shfl_sync(active, q, src);
+                if (lane == first && r < size) sum += other;
+            }
+            if (lane == first) atomicAdd(reinterpret_cast<unsigned long long*>(grad) + key, (unsigned long long)sum);
+            return;
+        }
+        double sum = double(v);
         for (int r = 1; r < rounds; ++r) {                          // warp-uniform trip count
             const int src = r < size ? int(__fns(group, 0, r + 1)) : lane;
             const double other = __shfl_sync(active, double(v), src);

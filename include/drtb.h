@@ -124,6 +124,15 @@ typedef struct drtb_scene {
 #define DRTB_FLAG_STATS   4u    /* fill drtb_stats (segments, lit paths, ...)   */
 #define DRTB_FLAG_NO_BVH  8u    /* test aid: scan every triangle instead of
                                    traversing the BVH (same results, O(N) per ray) */
+#define DRTB_FLAG_DETERMINISTIC 16u /* mesh scenes with per-triangle parameters (more
+                                   than 8 parameters): sum the gradients in 64-bit
+                                   FIXED POINT (resolution 2^-32) instead of floating-
+                                   point atomics.  Integer addition is associative, so
+                                   the gradients are bit-reproducible run to run and do
+                                   not depend on the order the rays finish in; each
+                                   contribution is rounded to 2^-32 (|value| < 2^31).
+                                   Every other gradient path is deterministic already
+                                   and ignores the flag. */
 
 typedef struct drtb_render_opts {
     int32_t  spp;               /* samples per pixel  (args.hpp:32-37 `-n`)     */

@@ -46,6 +46,29 @@ def test_bvh_equals_linear_scan_on_a_medium_mesh(drt, ctx):
     assert nz.mean() > 0.05                                           # gradients are spread over the triangles
 
 
+def test_deterministic_gradient_mode_is_bit_reproducible_and_order_independent(drt, ctx):
+    """DRTB_FLAG_DETERMINISTIC ("offer a deterministic two-stage reduction for tests"): per-triangle
+    gradients summed in 64-bit fixed point.  The BVH and the linear scan finish their rays in different orders and
+    the traversal refills its lanes dynamically, yet the gradients must come out bit-identical -- and within the
+    fixed-point resolution of the floating-point atomics' result."""
+    scene = drt.tessellated_room(24, 48, width=96, height=64)          # 16 k triangles
+    ctx.upload(scene)
+    det = drt.FLAG_IMAGE | drt.FLAG_GRAD | drt.FLAG_DETERMINISTIC
+    a_img, a_grad = ctx.render(drt.make_opts(4, 4, 1.0, flags=det))
+    b_img, b_grad = ctx.render(drt.make_opts(4, 4, 1.0, flags=det | drt.FLAG_NO_BVH))
+    c_img, c_grad = ctx.render(drt.make_opts(4, 4, 1.0, flags=det))
+    assert np.array_equal(a_img, b_img) and np.array_equal(a_grad, b_grad) and np.array_equal(a_grad, c_grad)
+    f_img, f_grad = ctx.render(drt.make_opts(4, 4, 1.0))
+    assert np.array_equal(a_img, f_img)
+    assert np.abs(a_grad - f_grad).max() <= 1e-7                       # <= 2^-33 per contribution, a few hundred of them
+    assert np.abs(a_grad - f_grad).max() <= 1e-8 * np.abs(f_grad).max()
+    # the analytic-only scene (12 gradient scalars, per-chunk rows) is deterministic anyway: the flag changes nothing
+    ctx.upload(drt.cornell_box(48, 32))
+    g0 = ctx.render(drt.make_opts(8, 4, 1.0))[1]
+    g1 = ctx.render(drt.make_opts(8, 4, 1.0, flags=det))[1]
+    assert np.array_equal(g0, g1)
+
+
 def test_mesh_explicit_rays_and_jacobian(drt, ctx):
     import ctypes as C
     scene = mixed_mesh_scene()
