@@ -457,23 +457,39 @@ def run_b200_arm(a):
     if world > 1 and use_peer and use_pgrad:
         # N > 1: the ASSEMBLED image must land in ONE host buffer.  Every rank's kernel stores its pixels into rank
         # 0's full image, the gradient exchange orders "all stores have landed", and rank 0 copies the full image
-        # out.  Two full images alternate (drtb.h: the caller double-buffers): a fast rank's next render may store
-        # into rank 0's image while rank 0 still copies the previous one out.
-        peer2 = sharding.PeerImage(ctx, H, W, dist)
-        bufs = [(peer, peer.tensor(dev)), (peer2, peer2.tensor(dev))]
+        # out -- on a copy stream, so that the copy of step k runs under the render of step k + 1.  THREE full images
+        # (and three pinned host images) rotate: image j is stored into again at step k + 3, which a fast rank can
+        # begin as soon as the exchange of step k + 2 has completed everywhere; rank 0 makes its stream wait for the
+        # copy of step k before it launches render k + 2 (whose exchange is what releases the others), a wait that
+        # is always already satisfied.  (drtb.h: the caller double-buffers the full images.)
+        peer2 = [sharding.PeerImage(ctx, H, W, dist), sharding.PeerImage(ctx, H, W, dist)]
+        bufs = [(peer, peer.tensor(dev))] + [(q, q.tensor(dev)) for q in peer2]
+        h_imgs = [h_img] + [torch.empty((H, W, 3), dtype=torch.float64).pin_memory() if rank == 0 else h_img for _ in range(2)]
+        h_grads = [h_grad] + [torch.empty((P, 3), dtype=torch.float64).pin_memory() for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [None, None, None]
         e2e_api = ("drtb_set_params + drtb_render_device (image peers + gradient peers) + one D2H of the assembled "
-                   "full image on rank 0 (pinned), gradients D2H on every rank")
+                   "full image on rank 0 (pinned, on a copy stream under the next render; three rotating images), "
+                   "gradients D2H on every rank")
         flip = [0]
 
         def step_e2e():
-            pi, full = bufs[flip[0]]; flip[0] ^= 1
+            k = flip[0]; flip[0] += 1
+            j = k % 3
+            pi, full = bufs[j]
             ctx.set_params(pvals)                                            # H2D: this step's inputs
             ctx.set_image_peers(pi.ptrs)
+            if copied[(k - 2) % 3] is not None:
+                stream.wait_event(copied[(k - 2) % 3])                       # see above: satisfied long ago
             ctx.render_device(opts, 0, 0, g_dev.data_ptr(), 0, stream.cuda_stream)
-            h_grad.copy_(g_dev, non_blocking=True)                           # D2H: the summed gradients
-            if rank == 0:
-                h_img.copy_(full, non_blocking=True)                         # D2H: the whole image, assembled by the kernels
-            stream.synchronize()
+            h_grads[j].copy_(g_dev, non_blocking=True)                       # D2H: the summed gradients
+            done = torch.cuda.Event(); done.record(stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                if rank == 0:
+                    h_imgs[j].copy_(full, non_blocking=True)                 # D2H: the whole image, assembled by the kernels
+                ev_c = torch.cuda.Event(); ev_c.record(copy_stream)
+            copied[j] = ev_c
     else:
         if use_peer:
             ctx.set_image_peers([])                                          # the host-buffer API returns this rank's rows
@@ -504,15 +520,17 @@ def run_b200_arm(a):
     d2h = (H * W * 3 * 8) + P * 3 * 8 * world
     e2e_check = None
     if peer2 is not None and rank == 0:
-        # the image in the host buffer is the whole picture: compare with the device image of the verification above
-        e2e_check = bool(torch.equal(h_img, bufs[flip[0] ^ 1][1].cpu())) and bool(torch.isfinite(h_img).all())
+        # the image in the host buffer is the whole picture: compare with the device image it was copied from
+        last = (flip[0] - 1) % 3
+        e2e_check = bool(torch.equal(h_imgs[last], bufs[last][1].cpu())) and bool(torch.isfinite(h_imgs[last]).all())
 
     if pgrad is not None:
         torch.cuda.synchronize()
         pgrad.close()                                                    # collective
     if peer2 is not None:
         torch.cuda.synchronize()
-        peer2.close()
+        for q in peer2:
+            q.close()                                                    # collective
     if peer is not None:
         torch.cuda.synchronize()
         peer.close()                                                     # collective
