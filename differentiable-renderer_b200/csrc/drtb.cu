@@ -222,6 +222,9 @@ void fill_dev_scene(DevScene<R>& d, const drtb_ctx& c)
             b[0] = n[1] * t[2] - n[2] * t[1]; b[1] = n[2] * t[0] - n[0] * t[2]; b[2] = n[0] * t[1] - n[1] * t[0];
             len = std::sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
             for (int j = 0; j < 3; ++j) { d.frame[i][j] = R(t[j]); d.frame[i][3 + j] = R(b[j] / len); }
+            d.wtab[i] = R(3.14159265358979323846 * (n[0] * n[0] + n[1] * n[1] + n[2] * n[2]));   // diffuse_sample: pi |n|^2
+        } else {
+            d.wtab[i] = R(3.14159265358979323846);
         }
     }
     const drtb_camera& cam = c.camera;
@@ -380,7 +383,9 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     const bool want_gimg = want_grad && gi.d_out != nullptr;
     a.gimg = want_gimg ? gi.d_out : nullptr;
     a.gimg_param = want_gimg ? gi.param : -1;
-    const bool gen = ctx->has_specular || want_gimg;
+    // general kernels: SpecularBxDF materials, a gradient image, or a plane whose diffuse weight is not a constant
+    // (tilted non-unit normal: diffuse_sample in path.cuh) -- the all-diffuse kernels keep no weights in their records
+    const bool gen = ctx->has_specular || want_gimg || !ctx->const_weight;
 
     const bool smallp = P <= kSmallP;
     // DRTB_MIXED: float pass + double re-trace of the close calls, where both kernels exist and the float path stays
@@ -394,7 +399,9 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     constexpr bool mesh = false;                  // mesh scenes took the wavefront above
     a.mesh = mesh_view(ctx);
     size_t smem = (smallp && want_grad) ? size_t(P3) * kBlock * sizeof(double) : 0;
-    const size_t ring_bytes = queue ? kWarpsPerBlock * queue_bytes_per_warp(a.max_depth, f32 ? sizeof(float) : sizeof(double),
+    // the all-diffuse kernels queue primitive lists only, the weights are constants of the primitives (PathRecord)
+    const size_t ring_real = !gen ? 0 : f32 ? sizeof(float) : sizeof(double);
+    const size_t ring_bytes = queue ? kWarpsPerBlock * queue_bytes_per_warp(a.max_depth, ring_real,
                                                                             mesh ? sizeof(int32_t) : sizeof(uint8_t)) : 0;
     // analytic scenes with 9 .. 64 parameters: shared atomic columns, as many as keep 5 blocks on an SM
     const bool shared_atomic = !smallp && !mesh;
@@ -412,7 +419,7 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     int queue_kind = queue ? 1 : 0;
     if (queue && !mesh) {
         const int want_blocks = f32 ? DRTB_MIN_BLOCKS_F32 : DRTB_MIN_BLOCKS;
-        const size_t static_smem = (f32 ? sizeof(BlockScene<float>) : sizeof(BlockScene<double>)) + 1024;   // + 1 KB the system reserves per block
+        const size_t static_smem = (f32 ? sizeof(BlockScene<float>) : sizeof(BlockScene<double>) + 3 * kBlock * sizeof(double)) + 1024;   // (+ the double kernels' pixel columns) + 1 KB the system reserves per block
         if ((static_smem + smem + ring_bytes) * want_blocks > size_t(228) * 1024) queue_kind = 2;
     }
     // Measured and NOT adopted for records that fit (B <= 8, double): the global ring at every depth is 0.9 % faster
@@ -423,8 +430,8 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     if (queue_kind == 1 && !mesh && ctx->ring_policy == 2) queue_kind = 2;
     // records of at most 8 vertices (the headline's 8 bounces) in the global ring: the short-record instantiation
     // (render_kernels.cuh, QUEUE == 3), compiled for the all-diffuse kernels with per-thread gradient columns
-    if (queue_kind == 2 && a.max_depth <= 8 && smallp && !gen && !mixed) queue_kind = 3;
-    if (queue_kind < 2) smem += ring_bytes;
+    if (a.max_depth <= 8 && smallp && !gen && !mixed && queue_kind) queue_kind = queue_kind == 2 ? 3 : 4;
+    if (queue_kind == 1 || queue_kind == 4) smem += ring_bytes;       // the shared-memory rings
     smem = (smem + 15) & ~size_t(15);
     const long long npix = (long long)rows * W;
     const int ppw = o->spp >= 32 ? 1 : 32 / o->spp;
@@ -639,6 +646,16 @@ int drtb_scene_upload(drtb_ctx* ctx, const drtb_scene* s)
         if (p.material >= 0 && ctx->materials[p.material].type == DRTB_SPECULAR) ctx->has_specular = true;
     fill_dev_scene(ctx->sc64, *ctx);
     fill_dev_scene(ctx->sc32, *ctx);
+    // the diffuse weight of a plane is pi |n|^2 + pi (n.tg) x / cos(theta) (diffuse_sample, path.cuh): a constant unless
+    // n.tg != 0, i.e. unless the normal is neither a unit vector nor orthogonal to make_frame's helper axis
+    ctx->const_weight = true;
+    for (size_t i = 0; i < ctx->prims.size(); ++i) {
+        const drtb_prim& p = ctx->prims[i];
+        if (p.type != DRTB_PLANE) continue;
+        const double nt = p.v[0] * ctx->sc64.frame[i][0] + p.v[1] * ctx->sc64.frame[i][1] + p.v[2] * ctx->sc64.frame[i][2];
+        const double nn = std::sqrt(p.v[0] * p.v[0] + p.v[1] * p.v[1] + p.v[2] * p.v[2]);
+        if (!(std::fabs(nt) <= 1e-14 * nn)) ctx->const_weight = false;
+    }
     int rc = ensure(ctx, ctx->d_params, ctx->params_cap, std::max<size_t>(3, ctx->params.size()));
     if (rc != DRTB_OK) return rc;
     if (!ctx->params.empty())

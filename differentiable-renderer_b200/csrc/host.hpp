@@ -39,6 +39,7 @@ struct drtb_ctx {
     std::string err;
     bool has_scene = false;
     bool has_specular = false;    // some primitive carries a DRTB_SPECULAR material
+    bool const_weight = true;     // every plane's diffuse weight is a constant of the plane (drtb_scene_upload)
     std::vector<drtb_prim> prims;
     std::vector<drtb_material> materials;
     std::vector<double> params;

@@ -57,6 +57,7 @@ struct alignas(16) DevScene {
     // Indexed by SCENE index:
     R       frame[kMaxPrims][6];         // planes: make_frame(n) tangent, bitangent (bxdf.hpp:29-41), host double
     int8_t  type[kMaxPrims];             // DRTB_SPHERE | DRTB_PLANE
+    R       wtab[kMaxPrims];             // diffuse weight cos / pdf = pi |n|^2 of the primitive (diffuse_sample), host double
     int32_t color[kMaxPrims];            // param index of the albedo, -1 = null BxDF
     int32_t emis[kMaxPrims];             // param index of the emission, -1 = no emitter
     int8_t  slot[kMaxPrims];             // scene index -> scan slot
@@ -136,6 +137,7 @@ struct BlockScene {
     R       frame[kMaxPrims][6];         // plane tangent + bitangent
     R       param[kMaxParams * 3];       // staged only when n_params <= kMaxParams
     int2    em_col[kMaxPrims];           // (emission, albedo) parameter indices: one 64-bit load per vertex
+    R       wtab[kMaxPrims];             // diffuse weight of the primitive (records without weights, PathRecord)
     int8_t  type[kMaxPrims];
     int8_t  mtype[kMaxPrims];
     R       expo[kMaxPrims];
@@ -151,7 +153,7 @@ __device__ __forceinline__ void load_block_scene(BlockScene<R>& bs, const DevSce
     for (int i = threadIdx.x; i < sc.n_prims * 6; i += blockDim.x)
         bs.frame[i / 6][i % 6] = sc.frame[i / 6][i % 6];
     for (int i = threadIdx.x; i < sc.n_prims; i += blockDim.x) {
-        bs.type[i] = sc.type[i]; bs.em_col[i] = make_int2(sc.emis[i], sc.color[i]);
+        bs.type[i] = sc.type[i]; bs.em_col[i] = make_int2(sc.emis[i], sc.color[i]); bs.wtab[i] = sc.wtab[i];
         bs.mtype[i] = sc.mtype[i]; bs.expo[i] = sc.expo[i];
     }
     if (sc.n_params <= kMaxParams)
@@ -449,11 +451,28 @@ __device__ __forceinline__ void unit_frame(V3<R> n, V3<R>& tg, V3<R>& bt)
 // w = cos / pdf.  n is used RAW (the non-unit green-wall normal stays non-unit).
 // sin(asin(sqrt u)) = sqrt u, cos(asin(sqrt u)) = sqrt(1 - u); u < 1 always, so
 // one rsqrt(1 - u) yields both cos(theta) and the 1/cos(theta) that pdf needs.
-// (w is pi |n|^2 + pi (n.tg) x / cos(theta) in exact arithmetic, a constant of the
-// primitive for unit normals; taking it from a table instead of evaluating the
-// reference's dot product and division was measured and is no faster at 72
-// registers: profiles/README.md, round 2.)
+// With dir_out = x tg + y bt + cos(theta) n and bt = n x tg orthogonal to n,
+//     w = pi |n|^2 + pi (n.tg) x / cos(theta),
+// and n.tg = 0 whenever n is a unit vector or orthogonal to make_frame's helper
+// axis (every primitive of the Cornell box, raw green-wall normal included; all
+// spheres and triangles): w is then a CONSTANT of the primitive.  The all-diffuse
+// kernels exploit that: their records carry no weights at all (PathRecord), the
+// sweeps take w from DevScene::wtab, and a scene with a tilted non-unit plane
+// normal renders with the general kernels, which evaluate the reference's dot
+// product and division as below.
 // ---------------------------------------------------------------------------
+// The direction alone (records without weights, see PathRecord): w is then the primitive's table entry.
+template <typename R>
+__device__ __forceinline__ V3<R> diffuse_direction(V3<R> n, V3<R> tg, V3<R> bt, R u_theta, R sp, R cp)
+{
+    const R st = Real<R>::sqrt(u_theta);
+    const R ct = Real<R>::sqrt(R(1) - u_theta);    // u < 1 always
+    const R x = cp * st, y = sp * st;
+    return {x * tg.x + y * bt.x + ct * n.x,
+            x * tg.y + y * bt.y + ct * n.y,
+            x * tg.z + y * bt.z + ct * n.z};
+}
+
 template <typename R>
 __device__ __forceinline__ V3<R> diffuse_sample(V3<R> n, V3<R> tg, V3<R> bt, R u_theta, R sp, R cp, R& w)
 {
@@ -533,11 +552,15 @@ __device__ __forceinline__ V3<R> specular_sample(V3<R> n, V3<R> tg, V3<R> bt, V3
 template <bool MESH> struct PrimId { using type = uint8_t; };
 template <> struct PrimId<true> { using type = int32_t; };
 
-template <typename R, bool MESH, int CAP>
+// HASW = false (the all-diffuse analytic kernels): the weights are constants of the primitives (diffuse_sample), so
+// the record is the list of primitives alone -- no weight is computed, stored, queued or re-read, the lit-path ring
+// shrinks from 9 to 1 byte per vertex (and fits shared memory at 7 resident blocks), the local frame by a third.
+template <typename R, bool MESH, int CAP, bool HASW = true>
 struct PathRecord {
     using Id = typename PrimId<MESH>::type;
     static constexpr int kCap = CAP;     // kQueueDepth for the compacting kernels, kMaxDepth otherwise: the
-    R  w_[CAP];                          // per-thread local-memory footprint has to stay inside L2
+    static constexpr bool kHasW = HASW;  // per-thread local-memory footprint has to stay inside L2
+    R  w_[HASW ? CAP : 1];
     Id prim_[CAP];
     __device__ __forceinline__ R w(int v) const { return w_[v]; }
     __device__ __forceinline__ int prim(int v) const { return int(prim_[v]); }
@@ -551,10 +574,11 @@ struct PathRecord {
 constexpr int kQueueSlots = 64;    // ring capacity per warp (power of two)
 constexpr int kQueueDepth = 16;    // deepest record the ring stores; deeper runs use the direct path
 
-template <typename R, bool MESH, int CAP = kQueueDepth>
+template <typename R, bool MESH, int CAP = kQueueDepth, bool HASW = true>
 struct QueueView {                 // one record of one warp's ring
     using Id = typename PrimId<MESH>::type;
     static constexpr int kCap = CAP;   // bounds the L_{v+1} array of the sweeps (radiance_and_adjoint)
+    static constexpr bool kHasW = HASW;
     const R* w_;                   // &ring_w[slot], stride kQueueSlots
     const Id* prim_;
     __device__ __forceinline__ R w(int v) const { return w_[v * kQueueSlots]; }
@@ -575,6 +599,7 @@ template <typename R, bool MESH> struct Materials;
 template <typename R> struct Materials<R, false> {
     const BlockScene<R>* bs;
     __device__ __forceinline__ int2 em_col(int k) const { return bs->em_col[k]; }
+    __device__ __forceinline__ R w(int k) const { return bs->wtab[k]; }
     __device__ __forceinline__ R param(int i) const { return bs->param[i]; }
 };
 template <typename R> struct Materials<R, true> {
@@ -585,6 +610,7 @@ template <typename R> struct Materials<R, true> {
     {
         return k < mesh.n_prims ? bs->em_col[k] : make_int2(__ldg(mesh.emis + (k - mesh.n_prims)), __ldg(mesh.color + (k - mesh.n_prims)));
     }
+    __device__ __forceinline__ R w(int k) const { return k < mesh.n_prims ? bs->wtab[k] : Real<R>::pi(); }
     __device__ __forceinline__ R param(int i) const { return R(__ldg(params + i)); }
 };
 
@@ -601,12 +627,12 @@ struct TraceCounters { uint32_t segments = 0, truncated = 0, bvh_nodes = 0, tri_
 // lobe code are compiled in; the all-diffuse kernels do not carry them).
 // MIXED (float, analytic, all-diffuse): every closest hit is checked for a close call (ClosestMargin); the first one
 // ends the trace with cnt.close_call = 1 and the caller hands the path to the double re-trace.
-template <typename R, bool MESH, int CAP, bool SPEC = false, bool MIXED = false>
+template <typename R, bool MESH, int CAP, bool SPEC = false, bool MIXED = false, bool HASW = true>
 __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScene<R>& bs,
                                           const Materials<R, MESH>& mat, bool no_bvh,
                                           uint64_t base, uint32_t slot, V3<R> o, V3<R> d,
                                           int min_bounces, double absorb, int max_depth,
-                                          PathRecord<R, MESH, CAP>& rec, bool& lit, TraceCounters& cnt)
+                                          PathRecord<R, MESH, CAP, HASW>& rec, bool& lit, TraceCounters& cnt)
 {
     using Id = typename PrimId<MESH>::type;
     int n = 0;
@@ -658,8 +684,10 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
         // frame and the direction are skipped (warp-uniform test).  SpecularBxDF keeps them, its w can
         // be NaN and NaN * 0 poisons the path upstream.
         const bool last_vertex = DRTB_SKIP_LAST && !SPEC && absorb >= 1.0 && depth + 1 >= min_bounces;
+        static_assert(HASW || (!SPEC && !MESH), "records without weights: all-diffuse analytic scenes only");
         if (col < 0 || last_vertex) {                       // null BxDF, :25-26, 38-39
-            rec.w_[n++] = R(0);
+            if constexpr (HASW) rec.w_[n] = R(0);           // (without weights: this vertex's w only ever meets L_{v+1} = 0)
+            ++n;
             alive = false;
             continue;
         }
@@ -697,10 +725,13 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
             // upstream a NaN/inf weight poisons the path even if it never meets the light (NaN * 0):
             // such a path must run the sweeps, which then produce the reference's NaN
             lit |= !(Real<R>::abs(w) < Real<R>::inf());
-        } else {
+        } else if constexpr (HASW) {
             dout = diffuse_sample(nrm, tg, bt, u_theta, sp, cp, w);
+        } else {
+            dout = diffuse_direction(nrm, tg, bt, u_theta, sp, cp);
         }
-        rec.w_[n++] = w;
+        if constexpr (HASW) rec.w_[n] = w;
+        ++n;
         const R eps = Real<R>::origin_eps();                // 1e-3, pathtracer.hpp:99
         o = {Real<R>::fma(eps, dout.x, pt.x), Real<R>::fma(eps, dout.y, pt.y), Real<R>::fma(eps, dout.z, pt.z)};
         d = dout;
@@ -785,7 +816,9 @@ __device__ __noinline__ void radiance_and_adjoint_deep(const Mat& mat, const Rec
             const int2 ec = mat.em_col(k);
         const int em = ec.x, col = ec.y;
             const R ip = v >= min_bounces ? inv_p : R(1);
-            const R f = rec.w(v) * Real<R>::inv_pi();
+            R wv;
+            if constexpr (Rec::kHasW) wv = rec.w(v); else wv = mat.w(k);
+            const R f = wv * Real<R>::inv_pi();
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 R E = em >= 0 ? mat.param(3 * em + c) : R(0);
@@ -802,7 +835,9 @@ __device__ __noinline__ void radiance_and_adjoint_deep(const Mat& mat, const Rec
         const int2 ec = mat.em_col(k);
         const int em = ec.x, col = ec.y;
         const R ip = v >= min_bounces ? inv_p : R(1);
-        const R f = rec.w(v) * Real<R>::inv_pi();
+        R wv;
+            if constexpr (Rec::kHasW) wv = rec.w(v); else wv = mat.w(k);
+            const R f = wv * Real<R>::inv_pi();
         R Ln[3];
         radiance_from(v + 1, Ln);
 #pragma unroll
@@ -841,7 +876,9 @@ __device__ __forceinline__ void radiance_and_adjoint(const Mat& mat, const Rec& 
         const int2 ec = mat.em_col(k);
         const int em = ec.x, col = ec.y;
         const R ip = v >= min_bounces ? inv_p : R(1);
-        const R f = rec.w(v) * Real<R>::inv_pi();
+        R wv;
+            if constexpr (Rec::kHasW) wv = rec.w(v); else wv = mat.w(k);
+            const R f = wv * Real<R>::inv_pi();
         if (want_grad) { Ls[v + 1][0] = L[0]; Ls[v + 1][1] = L[1]; Ls[v + 1][2] = L[2]; }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -858,7 +895,9 @@ __device__ __forceinline__ void radiance_and_adjoint(const Mat& mat, const Rec& 
         const int2 ec = mat.em_col(k);
         const int em = ec.x, col = ec.y;
         const R ip = v >= min_bounces ? inv_p : R(1);
-        const R f = rec.w(v) * Real<R>::inv_pi();
+        R wv;
+            if constexpr (Rec::kHasW) wv = rec.w(v); else wv = mat.w(k);
+            const R f = wv * Real<R>::inv_pi();
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             R gp = g[c] * ip;

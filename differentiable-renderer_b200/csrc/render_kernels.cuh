@@ -32,7 +32,7 @@ constexpr int kShortDepth = 8;     // QUEUE == 3: record capacity of the short-r
 //           paths that are lit, so its latency does not matter, the occupancy does; 3: like 2 for records of at
 //           most kShortDepth vertices (the headline's 8 bounces): the per-thread record and the sweeps' L_{v+1}
 //           array are half as deep, 288 instead of 552 bytes of local memory per resident thread, which is what
-//           the L2 has to hold beside the rings
+//           the L2 has to hold beside the rings; 4: like 1 (shared ring) with the short records
 #ifndef DRTB_MIN_BLOCKS
 #define DRTB_MIN_BLOCKS 1
 #endif
@@ -80,15 +80,20 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
     const int passes = spp >= 32 ? (spp + 31) / 32 : 1;
     const R inv_p = a.absorb < 1.0 ? R(1.0 / (1.0 - a.absorb)) : R(0);
 
-    constexpr int kQD = QUEUE == 3 ? kShortDepth : kQueueDepth;   // record capacity of the compacting variants
+    constexpr int kQD = (QUEUE == 3 || QUEUE == 4) ? kShortDepth : kQueueDepth;   // record capacity of the compacting variants
+    constexpr bool kRingGlobal = QUEUE == 2 || QUEUE == 3;
+    // records with weights: the general and the mesh kernels; the all-diffuse analytic kernels take the weights
+    // from the per-primitive table (PathRecord, path.cuh)
+    constexpr bool kHasW = GEN || MESH;
+    constexpr size_t kRingReal = kHasW ? sizeof(R) : 0;
     // this warp's ring (QUEUE only)
     const int qdepth = a.max_depth;
     unsigned char* ring = reinterpret_cast<unsigned char*>(s_dyn + acc_doubles) +
-                          (QUEUE ? size_t(warp) * queue_bytes_per_warp(qdepth, sizeof(R), sizeof(Id)) : 0);
-    if constexpr (QUEUE >= 2)
-        ring = a.ring_scratch + (size_t(blockIdx.x) * kWarpsPerBlock + warp) * queue_bytes_per_warp(qdepth, sizeof(R), sizeof(Id));
+                          (QUEUE ? size_t(warp) * queue_bytes_per_warp(qdepth, kRingReal, sizeof(Id)) : 0);
+    if constexpr (kRingGlobal)
+        ring = a.ring_scratch + (size_t(blockIdx.x) * kWarpsPerBlock + warp) * queue_bytes_per_warp(qdepth, kRingReal, sizeof(Id));
     R* ring_w = reinterpret_cast<R*>(ring);
-    Id* ring_prim = reinterpret_cast<Id*>(ring + size_t(qdepth) * kQueueSlots * sizeof(R));
+    Id* ring_prim = reinterpret_cast<Id*>(ring + size_t(qdepth) * kQueueSlots * kRingReal);
     uint8_t* ring_n = reinterpret_cast<uint8_t*>(ring_prim + size_t(qdepth) * kQueueSlots);
     int q_head = 0, q_count = 0;                   // warp-uniform
 
@@ -172,7 +177,7 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                 __syncwarp();
                 if (lane < m) {
                     const int slot = (q_head + lane) & (kQueueSlots - 1);
-                    QueueView<R, MESH, kQD> qv{ring_w + slot, ring_prim + slot};
+                    QueueView<R, MESH, kQD, kHasW> qv{ring_w + slot, ring_prim + slot};
                     sweep(qv, ring_n[slot]);
                 }
                 __syncwarp();
@@ -184,14 +189,14 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                 const int i = i0 + pass * 32;
                 bool lit = false, close_call = false;
                 int n = 0;
-                PathRecord<R, MESH, QUEUE ? kQD : kMaxDepth> rec;
+                PathRecord<R, MESH, QUEUE ? kQD : kMaxDepth, kHasW> rec;
                 if (lane_ok && i < spp) {
                     const uint64_t key = a.key0 + ((uint64_t)y * W + x) * (uint64_t)spp + (uint64_t)i;
                     const uint64_t base = key * kKeyMul;
                     V3<R> o = {sc.eye[0], sc.eye[1], sc.eye[2]};
                     V3<R> d = camera_ray(sc, x, y, base);
                     const uint32_t seg0 = cnt.segments;
-                    n = trace_path<R, MESH, QUEUE ? kQD : kMaxDepth, GEN, MIXED>(sc, bs, mat, no_bvh, base, 2u, o, d, a.min_bounces,
+                    n = trace_path<R, MESH, QUEUE ? kQD : kMaxDepth, GEN, MIXED, kHasW>(sc, bs, mat, no_bvh, base, 2u, o, d, a.min_bounces,
                                                                                          a.absorb, a.max_depth, rec, lit, cnt);
                     if constexpr (MIXED) {
                         if (cnt.close_call) {               // this path belongs to the double re-trace, segments and all
@@ -216,7 +221,7 @@ render_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constant__ Re
                     if (lit) {
                         const int slot = (q_head + q_count + __popc(m & ((1u << lane) - 1u))) & (kQueueSlots - 1);
                         for (int v = 0; v < n; ++v) {
-                            ring_w[v * kQueueSlots + slot] = rec.w_[v];
+                            if constexpr (kHasW) ring_w[v * kQueueSlots + slot] = rec.w_[v];
                             ring_prim[v * kQueueSlots + slot] = rec.prim_[v];
                         }
                         ring_n[slot] = uint8_t(n);
@@ -697,8 +702,8 @@ int launch_variant(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, size_t s
         if (rc != DRTB_OK) return rc;
         a.grad_partial = ctx->d_partial;
     }
-    if (QUEUE >= 2) {
-        const size_t per_warp = queue_bytes_per_warp(a.max_depth, sizeof(R), MESH ? sizeof(int32_t) : sizeof(uint8_t));
+    if (QUEUE == 2 || QUEUE == 3) {
+        const size_t per_warp = queue_bytes_per_warp(a.max_depth, (GEN || MESH) ? sizeof(R) : 0, MESH ? sizeof(int32_t) : sizeof(uint8_t));
         rc = ensure(ctx, ctx->d_ring, ctx->ring_cap, size_t(grid) * kWarpsPerBlock * per_warp / sizeof(double));
         if (rc != DRTB_OK) return rc;
         a.ring_scratch = reinterpret_cast<unsigned char*>(ctx->d_ring);
@@ -791,6 +796,7 @@ int launch_analytic(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, const d
     // short records in the global ring: the all-diffuse kernel with per-thread gradient columns only (drtb.cu asks
     // for it only there)
     if (l.queue == 3 && !l.gen && l.smallp) return DRTB_LAUNCH(true, 3, false);
+    if (l.queue == 4 && !l.gen && l.smallp) return DRTB_LAUNCH(true, 4, false);
     // GEN: SpecularBxDF materials and/or a gradient image; the all-diffuse kernels do not carry that code
     if (l.gen) return l.smallp ? DRTB_BY_QUEUE(true, true) : DRTB_BY_QUEUE(false, true);
     return l.smallp ? DRTB_BY_QUEUE(true, false) : DRTB_BY_QUEUE(false, false);

@@ -436,6 +436,7 @@ wf_shade(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArgs 
 template <typename R, int CAP>
 struct WfRecordView {
     static constexpr int kCap = CAP;
+    static constexpr bool kHasW = true;   // the wavefront keeps the weights in HBM beside the primitives
     const R* w_;
     const int32_t* prim_;
     int stride;
