@@ -758,11 +758,11 @@ __device__ __forceinline__ bool roulette_absorbs(uint64_t& ctr, int depth, int m
     return Real<double>::uniform(stream_draw_ctr(ctr++)) < absorb;
 }
 
-template <typename R, int CAP>
+template <typename R, int CAP, bool HASW>
 __device__ __forceinline__ bool trace_segment(const DevScene<R>& sc, const BlockScene<R>& bs,
                                               const Materials<R, false>& mat, uint64_t& ctr, V3<R>& o, V3<R>& d,
                                               int& depth, int& n, bool& lit, int min_bounces, double absorb,
-                                              int max_depth, PathRecord<R, false, CAP>& rec, TraceCounters& cnt)
+                                              int max_depth, PathRecord<R, false, CAP, HASW>& rec, TraceCounters& cnt)
 {
     if (n >= max_depth) { ++cnt.truncated; return true; }
     R t;
@@ -775,7 +775,8 @@ __device__ __forceinline__ bool trace_segment(const DevScene<R>& sc, const Block
     lit |= em >= 0;
     rec.prim_[n] = uint8_t(k);
     if (col < 0) {                                          // null BxDF, :25-26, 38-39
-        rec.w_[n++] = R(0);
+        if constexpr (HASW) rec.w_[n] = R(0);
+        ++n;
         return true;
     }
     V3<R> nrm, tg, bt;
@@ -785,8 +786,10 @@ __device__ __forceinline__ bool trace_segment(const DevScene<R>& sc, const Block
     R sp, cp;                                               // phi = 2 * pi * uniform(), bxdf.hpp:74
     Real<R>::sincos_tab(bs.tab, stream_draw_ctr(ctr + 1), &sp, &cp);
     ctr += 2;
-    const V3<R> dout = diffuse_sample(nrm, tg, bt, u_theta, sp, cp, w);
-    rec.w_[n++] = w;
+    V3<R> dout;
+    if constexpr (HASW) { dout = diffuse_sample(nrm, tg, bt, u_theta, sp, cp, w); rec.w_[n] = w; }
+    else                dout = diffuse_direction(nrm, tg, bt, u_theta, sp, cp);
+    ++n;
     const R eps = Real<R>::origin_eps();                    // 1e-3, pathtracer.hpp:99
     o = {Real<R>::fma(eps, dout.x, pt.x), Real<R>::fma(eps, dout.y, pt.y), Real<R>::fma(eps, dout.z, pt.z)};
     d = dout;

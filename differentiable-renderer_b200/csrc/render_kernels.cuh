@@ -375,9 +375,8 @@ render_regen_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constan
     const R inv_p = R(1.0 / (1.0 - a.absorb));
     double* pxacc = s_dyn + acc_doubles + size_t(warp) * (regen_smem_per_warp() / sizeof(double));
     int2* pxy = reinterpret_cast<int2*>(pxacc + kRegenPixels * 3);
-    unsigned char* ring = a.ring_scratch + (size_t(blockIdx.x) * kWarpsPerBlock + warp) * regen_ring_per_warp(sizeof(R));
-    R* ring_w = reinterpret_cast<R*>(ring);
-    uint8_t* ring_prim = ring + size_t(kQueueDepth) * kQueueSlots * sizeof(R);
+    unsigned char* ring = a.ring_scratch + (size_t(blockIdx.x) * kWarpsPerBlock + warp) * regen_ring_per_warp(0);
+    uint8_t* ring_prim = ring;                     // primitive lists only: the weights are table entries (PathRecord)
     uint8_t* ring_n = ring_prim + size_t(kQueueDepth) * kQueueSlots;
     uint8_t* ring_px = ring_n + kQueueSlots;
     int q_head = 0, q_count = 0;                   // warp-uniform
@@ -439,7 +438,7 @@ render_regen_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constan
             int px = -1;
             if (lane < m) {
                 const int slot = (q_head + lane) & (kQueueSlots - 1);
-                QueueView<R, false> qv{ring_w + slot, ring_prim + slot};
+                QueueView<R, false, kQueueDepth, false> qv{nullptr, ring_prim + slot};
                 px = ring_px[slot];
                 sweep(qv, ring_n[slot], px, L0);
             }
@@ -454,7 +453,7 @@ render_regen_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constan
         int depth = 0, n = 0, my_px = 0;
         uint64_t ctr = 0;
         V3<R> o = {R(0), R(0), R(0)}, d = o;
-        PathRecord<R, false, kMaxDepth> rec;
+        PathRecord<R, false, kMaxDepth, false> rec;
         for (;;) {
             const unsigned dead = __ballot_sync(0xffffffffu, !alive);
             if (next_s < n_samples && (__popc(dead) >= DRTB_REFILL_LANES || dead == 0xffffffffu)) {
@@ -491,10 +490,7 @@ render_regen_kernel(const __grid_constant__ DevScene<R> sc, const __grid_constan
             const unsigned m = __ballot_sync(0xffffffffu, queued);
             if (queued) {
                 const int slot = (q_head + q_count + __popc(m & lt_mask)) & (kQueueSlots - 1);
-                for (int v = 0; v < n; ++v) {
-                    ring_w[v * kQueueSlots + slot] = rec.w_[v];
-                    ring_prim[v * kQueueSlots + slot] = rec.prim_[v];
-                }
+                for (int v = 0; v < n; ++v) ring_prim[v * kQueueSlots + slot] = rec.prim_[v];
                 ring_n[slot] = uint8_t(n);
                 ring_px[slot] = uint8_t(my_px);
             }
@@ -750,7 +746,7 @@ int launch_regen(drtb_ctx* ctx, const DevScene<R>& sc, RenderArgs& a, long long 
         CK(ctx, cudaMemset(ctx->d_task_counter, 0, sizeof(unsigned long long)));     // the first-use launches claim from it too
     }
     a.task_counter = ctx->d_task_counter;
-    int rc = ensure(ctx, ctx->d_ring, ctx->ring_cap, size_t(grid) * kWarpsPerBlock * regen_ring_per_warp(sizeof(R)) / sizeof(double));
+    int rc = ensure(ctx, ctx->d_ring, ctx->ring_cap, size_t(grid) * kWarpsPerBlock * regen_ring_per_warp(0) / sizeof(double));
     if (rc != DRTB_OK) return rc;
     a.ring_scratch = reinterpret_cast<unsigned char*>(ctx->d_ring);
     const size_t rows = !want_grad ? 0 : SMALLP ? size_t(a.n_chunks) : size_t(grid);

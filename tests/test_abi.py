@@ -97,9 +97,9 @@ def test_scene_flattening_matches_src_render_cpp():
 def test_hot_kernels_keep_their_register_budget():
     """The render kernels are latency / issue bound and sized for 7 resident blocks of 128 threads per SM
     (72 registers, both precisions): a register count past the budget would silently cost occupancy, and
-    spills cost issue slots.  The float kernels and the double kernel with the shared-memory ring must not
-    spill at all; the other double variants (global ring, no ring, regeneration) are allowed the few
-    spilled words they are measured with (<= 64 bytes, profiles/README.md round 2).
+    spills cost issue slots.  The pass-based kernels (all-diffuse, per-thread gradient columns) must not spill
+    at all in either precision; the double regeneration kernels are allowed the few spilled words they are
+    measured with (<= 96 bytes, profiles/README.md round 2).
     Read from the ptxas report of the in-tree build (lib/build.log, written by build.py)."""
     log = abi.LIB_PATH.parent / "build.log"
     if not log.exists():
@@ -115,8 +115,7 @@ def test_hot_kernels_keep_their_register_budget():
             continue
         seen += 1
         is_double = "render_kernelId" in name or "render_regen_kernelId" in name
-        shared_ring = "render_kernelIdLb1ELi1E" in name
-        allowed = 64 if is_double and not shared_ring else 0
+        allowed = 96 if "render_regen_kernelId" in name else 0
         assert int(st) <= allowed, f"{name}: {st} bytes of spill stores"
         assert int(regs) <= 72, f"{name}: {regs} registers"
     assert seen >= 8, seen
