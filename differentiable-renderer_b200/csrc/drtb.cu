@@ -418,7 +418,7 @@ int launch_render_once(drtb_ctx* ctx, const drtb_render_opts* o, const double* d
     // of 5, -36 % throughput): past the budget the ring moves to a global scratch buffer (QUEUE == 2).
     int queue_kind = queue ? 1 : 0;
     if (queue && !mesh) {
-        const int want_blocks = f32 ? DRTB_MIN_BLOCKS_F32 : DRTB_MIN_BLOCKS;
+        const int want_blocks = f32 ? DRTB_MIN_BLOCKS_F32 : gen ? DRTB_MIN_BLOCKS_GEN : DRTB_MIN_BLOCKS;
         const size_t static_smem = (f32 ? sizeof(BlockScene<float>) : sizeof(BlockScene<double>) + 3 * kBlock * sizeof(double)) + 1024;   // (+ the double kernels' pixel columns) + 1 KB the system reserves per block
         if ((static_smem + smem + ring_bytes) * want_blocks > size_t(228) * 1024) queue_kind = 2;
     }

@@ -32,6 +32,9 @@
 #ifndef DRTB_MIN_BLOCKS_F32
 #define DRTB_MIN_BLOCKS_F32 DRTB_MIN_BLOCKS
 #endif
+#ifndef DRTB_MIN_BLOCKS_GEN
+#define DRTB_MIN_BLOCKS_GEN (DRTB_MIN_BLOCKS < 5 ? DRTB_MIN_BLOCKS : 5)   // double GEN kernels (lobe code, gradient image): 96 registers
+#endif
 
 struct drtb_ctx {
     int device = 0;
