@@ -705,11 +705,11 @@ __device__ __forceinline__ int trace_path(const DevScene<R>& sc, const BlockScen
             const bool sphere = analytic_frame(bs, k, pt, nrm, tg, bt);
             if constexpr (MIXED) {                          // the frame's axis switch and the drift bound (see ClosestMargin)
                 const float cosi = fmaxf(fabsf(float(dot(d, nrm))), 0.05f);
-                const float e_hit = (e_pos + float(t) * e_dir + kRoundPos * (1.0f + float(t))) / cosi;
+                const float e_hit = (e_pos + float(t) * e_dir + kRoundPos * (1.0f + float(t))) * Real<float>::rcp(cosi);
                 const bool axis_call = sphere && fabsf(fabsf(float(nrm.x)) - fabsf(float(nrm.y))) < kFrameGap + kDriftK * e_hit;
                 if (axis_call || e_hit > kDriftMax) { cnt.close_call = 1; alive = false; continue; }
                 e_pos = e_hit;
-                e_dir = sphere ? e_hit / float(bs.prim[k][3]) + kRoundDir : kRoundDir;
+                e_dir = sphere ? e_hit * Real<float>::rcp(float(bs.prim[k][3])) + kRoundDir : kRoundDir;
             }
         }
         R u_theta = Real<R>::uniform_fast(stream_draw_ctr(ctr));

@@ -209,8 +209,15 @@ template <> struct Real<float> {
     static __device__ __forceinline__ float select(bool c, float a, float b) { return c ? a : b; }
     static __device__ __forceinline__ float mul_nz(float a, float b) { return a * b; }
     static __device__ __forceinline__ float neg_if_outside_ahead(float x, float c, float h) { return (c > 0.0f && h < 0.0f) ? -x : x; }
-    static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }
-    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    // one MUFU.RCP (2^-23 relative); __fdividef(1, x) wraps it in range handling that cost the float kernels 4 % of
+    // their instructions (profiles/r02_mixed_f32_pass_summary.txt)
+    static __device__ __forceinline__ float rcp(float x)
+    {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    static __device__ __forceinline__ float div(float a, float b) { return a * rcp(b); }
     static __device__ __forceinline__ float rsqrt(float x) { return ::rsqrtf(x); }
     static __device__ __forceinline__ float sqrt(float x)
     {
