@@ -177,6 +177,21 @@ template <typename R> __device__ __forceinline__ void wf_reload_ray(const WfBuff
 #ifndef DRTB_VOTE_E
 #define DRTB_VOTE_E 2
 #endif
+// Fatter steps per vote (round 2, gpurun A/B of tools/ab_mesh.sh, 1 M triangles): up to DRTB_TN triangles per T step
+// (1 -> 2: +3.1 % double, +7.8 % float; 3: another +0.6 / +0.9 %; 4: -7 % double, registers) and, in double, a second
+// node step per vote for the lanes that can still take one (+3 %; in float, where the T step moves tmax, -1.3 %).
+#ifndef DRTB_NN
+#define DRTB_NN 2          // node steps per N vote, double
+#endif
+#ifndef DRTB_NN_F32
+#define DRTB_NN_F32 1      // the same, float
+#endif
+#ifndef DRTB_NN_MIN
+#define DRTB_NN_MIN 16     // lanes that must be able to take the extra node step (8 / 12 / 16 / 22 measured: flat below 16)
+#endif
+#ifndef DRTB_TN
+#define DRTB_TN 3          // triangles of the pending group per T step
+#endif
 template <typename R>
 __global__ void __launch_bounds__(128, DRTB_WF_MIN_BLOCKS)
 wf_traverse(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
@@ -233,43 +248,50 @@ wf_traverse(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
                   ne = sizeof(R) == 8 ? __popc(__ballot_sync(0xffffffffu, can_e)) : 0;
         const int kind = (ne > 0 && DRTB_VOTE_E * ne >= nt && DRTB_VOTE_E * ne >= nn) ? 2 : (nt > 0 && DRTB_VOTE_T * nt >= nn) ? 1 : 0;
         if (kind == 0) {
-            if (can_n) {
-                if (next == kNone) {                  // nothing pending: pop one child group
-                    uint2 g = stack.get(sp - 1);
-                    const bool ok = take_from_popped(g, tmax, r.octinv4, next);
-                    const bool keep = ok && (g.y & kHitBits) != 0u;       // its other children stay on the stack
-                    stack.put(sp - 1, g, keep);
-                    sp -= keep ? 0 : 1;
-                }
-                if (next != kNone) {
-                    uint2 ng, tg, rest;
-                    int m1, m2;
-                    ++n_nodes;
-                    node8_step(m, r, tmax, next, ng, tg, m1, m2);
+            // up to DRTB_NN node steps per vote: the second one runs for the lanes that can still open a node (those
+            // whose first node gave them no second pending triangle group) when at least DRTB_NN_MIN of them can
+#pragma unroll 1
+            for (int rep = 0; rep < (sizeof(R) == 8 ? DRTB_NN : DRTB_NN_F32); ++rep) {
+                const bool cn = rep == 0 ? can_n : (on && tg1.y == 0u && (next != kNone || sp > 0));
+                if (rep > 0 && __popc(__ballot_sync(0xffffffffu, cn)) < DRTB_NN_MIN) break;
+                if (cn) {
+                    if (next == kNone) {                  // nothing pending: pop one child group
+                        uint2 g = stack.get(sp - 1);
+                        const bool ok = take_from_popped(g, tmax, r.octinv4, next);
+                        const bool keep = ok && (g.y & kHitBits) != 0u;       // its other children stay on the stack
+                        stack.put(sp - 1, g, keep);
+                        sp -= keep ? 0 : 1;
+                    }
+                    if (next != kNone) {
+                        uint2 ng, tg, rest;
+                        int m1, m2;
+                        ++n_nodes;
+                        node8_step(m, r, tmax, next, ng, tg, m1, m2);
 #ifdef DRTB_TRAV_DEBUG
-                    dbg_stale += (ng.y & kHitBits) == 0u && tg.y == 0u;
-                    dbg_children += __popc(ng.y >> 24);
-                    dbg_leaf_hits += __popc(tg.y);
+                        dbg_stale += (ng.y & kHitBits) == 0u && tg.y == 0u;
+                        dbg_children += __popc(ng.y >> 24);
+                        dbg_leaf_hits += __popc(tg.y);
 #endif
-                    const bool free0 = tg0.y == 0u && eg == 0u;           // tg0's base is still needed while eg is pending
-                    tg0 = free0 ? tg : tg0;
-                    tg1 = free0 ? tg1 : tg;
-                    next = kNone;
-                    if (ng.y & kHitBits) {
-                        next = take_nearest(ng, m1, m2, rest);
-                        const bool more = (rest.y & kHitBits) != 0u;    // the other children hit wait on the stack
-                        stack.put(sp, rest, more && sp < kBvhStack);
-                        overflow |= more && sp >= kBvhStack;
-                        sp += (more && sp < kBvhStack) ? 1 : 0;
+                        const bool free0 = tg0.y == 0u && eg == 0u;           // tg0's base is still needed while eg is pending
+                        tg0 = free0 ? tg : tg0;
+                        tg1 = free0 ? tg1 : tg;
+                        next = kNone;
+                        if (ng.y & kHitBits) {
+                            next = take_nearest(ng, m1, m2, rest);
+                            const bool more = (rest.y & kHitBits) != 0u;    // the other children hit wait on the stack
+                            stack.put(sp, rest, more && sp < kBvhStack);
+                            overflow |= more && sp >= kBvhStack;
+                            sp += (more && sp < kBvhStack) ? 1 : 0;
 #if DRTB_PREFETCH
-                        // the child is opened a few iterations from now (its siblings' triangles come first): start its
-                        // 128-byte line on the way to L1 now -- the top stall of this kernel is the wait for node data
-                        asm volatile("prefetch.global.L1 [%0];" :: "l"(m.nodes + (size_t)next * kNodeStride));
+                            // the child is opened a few iterations from now (its siblings' triangles come first): start its
+                            // 128-byte line on the way to L1 now -- the top stall of this kernel is the wait for node data
+                            asm volatile("prefetch.global.L1 [%0];" :: "l"(m.nodes + (size_t)next * kNodeStride));
+#endif
+                        }
+#if DRTB_PREFETCH
+                        if (tg.y) asm volatile("prefetch.global.L1 [%0];" :: "l"(m.tri32 + (size_t)(tg.x + __ffs(tg.y) - 1) * kTri32Stride));
 #endif
                     }
-#if DRTB_PREFETCH
-                    if (tg.y) asm volatile("prefetch.global.L1 [%0];" :: "l"(m.tri32 + (size_t)(tg.x + __ffs(tg.y) - 1) * kTri32Stride));
-#endif
                 }
             }
         } else if (kind == 1) {
@@ -277,14 +299,31 @@ wf_traverse(const __grid_constant__ WfArgs a, const WfBuffers<R> b)
                 const int bit = __ffs(tg0.y) - 1;
                 tg0.y &= tg0.y - 1u;
                 ++n_tests;
-                const TriF T = load_trif(m, int(tg0.x) + bit);
-                if constexpr (sizeof(R) == 8) {
-                    eg |= tri_cull_f(T, r, tmax) ? 0u : (1u << bit);
-                } else {
-                    const TriData<R> D = {{T.v0x, T.v0y, T.v0z}, {T.e1x, T.e1y, T.e1z}, {T.e2x, T.e2y, T.e2z}};
-                    tri_test_exact<R>(D, T.id, V3<R>{r.ox, r.oy, r.oz}, V3<R>{r.dx, r.dy, r.dz}, tmin, best);
-                    tmax = upper_float<R>(tmin);
+                // up to DRTB_TN triangles of the group in one step: their loads are in flight together and the group
+                // needs that many fewer (vote + step) iterations.  A lane with fewer left repeats its first one,
+                // which changes nothing (the cull is a pure function, the exact test is idempotent).
+                int bits[DRTB_TN];
+                TriF T[DRTB_TN];
+                bits[0] = bit;
+#pragma unroll
+                for (int j = 1; j < DRTB_TN; ++j) {
+                    const bool more = tg0.y != 0u;
+                    bits[j] = more ? __ffs(tg0.y) - 1 : bit;
+                    tg0.y &= tg0.y - 1u;                  // 0 & 0xffffffff = 0 when none is left
+                    n_tests += more ? 1u : 0u;
                 }
+#pragma unroll
+                for (int j = 0; j < DRTB_TN; ++j) T[j] = load_trif(m, int(tg0.x) + bits[j]);
+#pragma unroll
+                for (int j = 0; j < DRTB_TN; ++j) {
+                    if constexpr (sizeof(R) == 8) {
+                        eg |= tri_cull_f(T[j], r, tmax) ? 0u : (1u << bits[j]);
+                    } else {
+                        const TriData<R> D = {{T[j].v0x, T[j].v0y, T[j].v0z}, {T[j].e1x, T[j].e1y, T[j].e1z}, {T[j].e2x, T[j].e2y, T[j].e2z}};
+                        tri_test_exact<R>(D, T[j].id, V3<R>{r.ox, r.oy, r.oz}, V3<R>{r.dx, r.dy, r.dz}, tmin, best);
+                    }
+                }
+                if constexpr (sizeof(R) == 4) tmax = upper_float<R>(tmin);
             }
         } else if (can_e) {
             const int bit = __ffs(eg) - 1;
