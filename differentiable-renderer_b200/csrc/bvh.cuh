@@ -670,37 +670,57 @@ template <int H> __device__ __forceinline__ float plane_to_float(uint32_t w, uin
 // Slab test of child S of a wide node; ORs its hit bits into `hits` and keeps the two smallest entry
 // distances of the INTERNAL children hit as integer keys (distance bits, low 3 bits = slot).  Branch-free.
 //   wn*, wf* : the words holding child S's near / far plane per axis (swizzled by the ray's direction signs)
-//   an*, bn* : t_near = f an + bn ; af*, bf* : t_far = f af + bf      (f = plane_to_float, see node8_step)
-struct SlabCoef { float anx, any, anz, bnx, bny, bnz, afx, afy, afz, bfx, bfy, bfz; uint32_t k43; };
+//   a*, b*   : t = f a + b for a plane f of that axis               (f = plane_to_float, see node8_step)
+//   lb_lo/hi : 0x7f in byte s where child s is NOT an internal child (leaf_bytes); sl_lo/hi: 0x03020100 / 0x07060504
+// Key of a child: one PRMT builds (leaf byte << 24 | slot), one LOP3 merges it with the distance bits, one SEL
+// replaces it by the sentinel on a miss.  A leaf or empty slot so gets a key >= 0x7f000000 (1.7e38 as a float: beyond
+// any entry distance), which never becomes the nearest INTERNAL child as long as one was hit, and node8_step's
+// callers look at the keys only then.
+struct SlabCoef { float ax, ay, az, bx, by, bz; uint32_t k43, lb_lo, lb_hi, sl_lo, sl_hi; };
 template <int S>
 __device__ __forceinline__ void child_slab(uint32_t wnx, uint32_t wny, uint32_t wnz, uint32_t wfx, uint32_t wfy, uint32_t wfz,
-                                           const SlabCoef& c, float tmax, uint32_t meta4, uint32_t imask,
-                                           uint32_t& hits, int& m1, int& m2)
+                                           const SlabCoef& c, float tmax, uint32_t meta4, uint32_t& hits, int& m1, int& m2)
 {
     constexpr int H = S & 1, J = S & 3;
-    const float tnx = fmaf(plane_to_float<H>(wnx, c.k43), c.anx, c.bnx), tny = fmaf(plane_to_float<H>(wny, c.k43), c.any, c.bny),
-                tnz = fmaf(plane_to_float<H>(wnz, c.k43), c.anz, c.bnz);
-    const float tfx = fmaf(plane_to_float<H>(wfx, c.k43), c.afx, c.bfx), tfy = fmaf(plane_to_float<H>(wfy, c.k43), c.afy, c.bfy),
-                tfz = fmaf(plane_to_float<H>(wfz, c.k43), c.afz, c.bfz);
+    const float tnx = fmaf(plane_to_float<H>(wnx, c.k43), c.ax, c.bx), tny = fmaf(plane_to_float<H>(wny, c.k43), c.ay, c.by),
+                tnz = fmaf(plane_to_float<H>(wnz, c.k43), c.az, c.bz);
+    const float tfx = fmaf(plane_to_float<H>(wfx, c.k43), c.ax, c.bx), tfy = fmaf(plane_to_float<H>(wfy, c.k43), c.ay, c.by),
+                tfz = fmaf(plane_to_float<H>(wfz, c.k43), c.az, c.bz);
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
     const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
     // meta byte: internal child 1 << 5 | (24 + slot), leaf unary(n) << 5 | offset: its hit bits are (meta >> 5) << (meta & 31)
     const uint32_t mb = (meta4 >> (8 * J)) & 0xffu;
-    const uint32_t sel = tn <= tf ? 0xffffffffu : 0u;
-    hits |= ((mb >> 5) << (mb & 31u)) & sel;
-    const bool inner_hit = (tn <= tf) & ((imask >> S) & 1u);
-    const int key = inner_hit ? int((__float_as_uint(tn) & ~7u) | uint32_t(S)) : 0x7fffffff;
+    const bool hit = tn <= tf;
+    hits |= hit ? (mb >> 5) << (mb & 31u) : 0u;
+    // result bytes 3..0 = (leaf byte J, 0, 0, slot): selector nibble 8 | x replicates the sign bit of byte x, and every
+    // byte of the slot words is below 0x80, so "sign of byte 4" is the zero byte
+    uint32_t x;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(x) : "r"(S < 4 ? c.lb_lo : c.lb_hi), "r"(S < 4 ? c.sl_lo : c.sl_hi),
+        "n"((J << 12) | (0xc << 8) | (0xc << 4) | (4 + J)));
+    const uint32_t kbits = (__float_as_uint(tn) & ~7u) | x;
+    const int key = hit ? int(kbits) : 0x7fffffff;
     m2 = min(m2, max(m1, key));
     m1 = min(m1, key);
 }
 
+// 0x7f in byte s of (lo: s = 0..3, hi: s = 4..7) for every bit s of `mask`: the multiply spreads four bits to the low
+// bits of four bytes without carries (bit i lands at 7 i + i), the second one widens 1 to 0x7f.
+__device__ __forceinline__ void leaf_bytes(uint32_t mask, uint32_t& lo, uint32_t& hi)
+{
+    lo = (((mask & 0xfu) * 0x00204081u) & 0x01010101u) * 0x7fu;
+    hi = ((((mask >> 4) & 0xfu) * 0x00204081u) & 0x01010101u) * 0x7fu;
+}
+
 // One wide-node step of a lane: fetch node `node`, slab-test its 8 children.  Returns the child group
 // ng = (child base, internal hits BY SLOT << 24 | imask), the triangle group tg = (triangle base, hit bits of the
-// triangles of the leaf children) and the keys (m1, m2) of the nearest and second-nearest internal child hit.
+// triangles of the leaf children) and the keys (m1, m2) of the nearest and second-nearest internal child hit
+// (meaningful when at least one / two internal children were hit; see child_slab).
 //
 // Plane a of child s is origin_a + q 2^E; with f = 128 + q / 256 (plane_to_float) the slab distance is
 //   t = (origin_a + q 2^E - o_a) / d_a = f A + B,   A = 256 2^E / d_a,   B = (origin_a - o_a) / d_a - 128 A.
-// Near planes use (A, B)(1 - 4e-7) and far planes (A, B)(1 + 4e-7): the test is widened by a few ulp.
+// The float evaluation of t is off by at most ~3 ulp of (|origin - o| + 2 node extents) / |d_a|, i.e. 5e-7 scene
+// extents along the axis; the leaf boxes are padded by 4e-6 scene extents on every side at build time (mesh_prepare)
+// and every inner box contains its leaves' padded boxes, so the test needs no widening of its own.
 __device__ __forceinline__ void node8_step(const MeshView& m, const RayF& r, float tmax, uint32_t node, uint2& ng, uint2& tg,
                                            int& m1, int& m2)
 {
@@ -712,11 +732,11 @@ __device__ __forceinline__ void node8_step(const MeshView& m, const RayF& r, flo
                 az = __uint_as_float(((ew >> 16) & 0xffu) << 23) * r.iz;
     const float bx = fmaf(-128.0f, ax, (f0.x - r.ox) * r.ix), by = fmaf(-128.0f, ay, (f0.y - r.oy) * r.iy),
                 bz = fmaf(-128.0f, az, (f0.z - r.oz) * r.iz);
-    constexpr float kLo = 0.9999996f, kHi = 1.0000004f;
-    // 0x43000000 as a run-time value (the triangle base is < 2^28, which the compiler cannot know), so that it is
+    // constants as run-time values (the triangle base is < 2^28, which the compiler cannot know), so that they are
     // not folded back into the permutes as their one immediate
-    const uint32_t k43 = 0x43000000u | (__float_as_uint(f1.y) >> 31);
-    const SlabCoef c = {ax * kLo, ay * kLo, az * kLo, bx * kLo, by * kLo, bz * kLo, ax * kHi, ay * kHi, az * kHi, bx * kHi, by * kHi, bz * kHi, k43};
+    const uint32_t opaque = __float_as_uint(f1.y) >> 31;
+    SlabCoef c = {ax, ay, az, bx, by, bz, 0x43000000u | opaque, 0u, 0u, 0x03020100u | opaque, 0x07060504u | opaque};
+    leaf_bytes(~imask, c.lb_lo, c.lb_hi);
     const bool sx = r.ix < 0.f, sy = r.iy < 0.f, sz = r.iz < 0.f;
     // near / far plane words per axis: lo planes in w2..w4, hi planes in w5..w7
     const float4 nX = sx ? f5 : f2, fX = sx ? f2 : f5, nY = sy ? f6 : f3, fY = sy ? f3 : f6, nZ = sz ? f7 : f4, fZ = sz ? f4 : f7;
@@ -724,14 +744,14 @@ __device__ __forceinline__ void node8_step(const MeshView& m, const RayF& r, flo
     m1 = 0x7fffffff; m2 = 0x7fffffff;
     const uint32_t meta_lo = __float_as_uint(f1.z), meta_hi = __float_as_uint(f1.w);
 #define DRTB_W(V, C) __float_as_uint(V.C)
-    child_slab<0>(DRTB_W(nX, x), DRTB_W(nY, x), DRTB_W(nZ, x), DRTB_W(fX, x), DRTB_W(fY, x), DRTB_W(fZ, x), c, tmax, meta_lo, imask, hits, m1, m2);
-    child_slab<1>(DRTB_W(nX, x), DRTB_W(nY, x), DRTB_W(nZ, x), DRTB_W(fX, x), DRTB_W(fY, x), DRTB_W(fZ, x), c, tmax, meta_lo, imask, hits, m1, m2);
-    child_slab<2>(DRTB_W(nX, y), DRTB_W(nY, y), DRTB_W(nZ, y), DRTB_W(fX, y), DRTB_W(fY, y), DRTB_W(fZ, y), c, tmax, meta_lo, imask, hits, m1, m2);
-    child_slab<3>(DRTB_W(nX, y), DRTB_W(nY, y), DRTB_W(nZ, y), DRTB_W(fX, y), DRTB_W(fY, y), DRTB_W(fZ, y), c, tmax, meta_lo, imask, hits, m1, m2);
-    child_slab<4>(DRTB_W(nX, z), DRTB_W(nY, z), DRTB_W(nZ, z), DRTB_W(fX, z), DRTB_W(fY, z), DRTB_W(fZ, z), c, tmax, meta_hi, imask, hits, m1, m2);
-    child_slab<5>(DRTB_W(nX, z), DRTB_W(nY, z), DRTB_W(nZ, z), DRTB_W(fX, z), DRTB_W(fY, z), DRTB_W(fZ, z), c, tmax, meta_hi, imask, hits, m1, m2);
-    child_slab<6>(DRTB_W(nX, w), DRTB_W(nY, w), DRTB_W(nZ, w), DRTB_W(fX, w), DRTB_W(fY, w), DRTB_W(fZ, w), c, tmax, meta_hi, imask, hits, m1, m2);
-    child_slab<7>(DRTB_W(nX, w), DRTB_W(nY, w), DRTB_W(nZ, w), DRTB_W(fX, w), DRTB_W(fY, w), DRTB_W(fZ, w), c, tmax, meta_hi, imask, hits, m1, m2);
+    child_slab<0>(DRTB_W(nX, x), DRTB_W(nY, x), DRTB_W(nZ, x), DRTB_W(fX, x), DRTB_W(fY, x), DRTB_W(fZ, x), c, tmax, meta_lo, hits, m1, m2);
+    child_slab<1>(DRTB_W(nX, x), DRTB_W(nY, x), DRTB_W(nZ, x), DRTB_W(fX, x), DRTB_W(fY, x), DRTB_W(fZ, x), c, tmax, meta_lo, hits, m1, m2);
+    child_slab<2>(DRTB_W(nX, y), DRTB_W(nY, y), DRTB_W(nZ, y), DRTB_W(fX, y), DRTB_W(fY, y), DRTB_W(fZ, y), c, tmax, meta_lo, hits, m1, m2);
+    child_slab<3>(DRTB_W(nX, y), DRTB_W(nY, y), DRTB_W(nZ, y), DRTB_W(fX, y), DRTB_W(fY, y), DRTB_W(fZ, y), c, tmax, meta_lo, hits, m1, m2);
+    child_slab<4>(DRTB_W(nX, z), DRTB_W(nY, z), DRTB_W(nZ, z), DRTB_W(fX, z), DRTB_W(fY, z), DRTB_W(fZ, z), c, tmax, meta_hi, hits, m1, m2);
+    child_slab<5>(DRTB_W(nX, z), DRTB_W(nY, z), DRTB_W(nZ, z), DRTB_W(fX, z), DRTB_W(fY, z), DRTB_W(fZ, z), c, tmax, meta_hi, hits, m1, m2);
+    child_slab<6>(DRTB_W(nX, w), DRTB_W(nY, w), DRTB_W(nZ, w), DRTB_W(fX, w), DRTB_W(fY, w), DRTB_W(fZ, w), c, tmax, meta_hi, hits, m1, m2);
+    child_slab<7>(DRTB_W(nX, w), DRTB_W(nY, w), DRTB_W(nZ, w), DRTB_W(fX, w), DRTB_W(fY, w), DRTB_W(fZ, w), c, tmax, meta_hi, hits, m1, m2);
 #undef DRTB_W
     ng = make_uint2(__float_as_uint(f1.x), (hits & 0xff000000u) | imask);
     tg = make_uint2(__float_as_uint(f1.y), hits & 0x00ffffffu);
