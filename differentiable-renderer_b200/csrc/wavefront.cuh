@@ -178,13 +178,14 @@ template <typename R> __device__ __forceinline__ void wf_reload_ray(const WfBuff
 #define DRTB_VOTE_E 2
 #endif
 // Fatter steps per vote (round 2, gpurun A/B of tools/ab_mesh.sh, 1 M triangles): up to DRTB_TN triangles per T step
-// (1 -> 2: +3.1 % double, +7.8 % float; 3: another +0.6 / +0.9 %; 4: -7 % double, registers) and, in double, a second
-// node step per vote for the lanes that can still take one (+3 %; in float, where the T step moves tmax, -1.3 %).
+// (1 -> 2: +3.1 % double, +7.8 % float; 3: another +0.6 / +0.9 %; 4: -13 % double, registers) and a second node step
+// per vote for the lanes that can still take one (+3 % double; float -1.3 % while the kernel spilled, +1.2 % since
+// the node step's diet; a third one changes nothing).
 #ifndef DRTB_NN
 #define DRTB_NN 2          // node steps per N vote, double
 #endif
 #ifndef DRTB_NN_F32
-#define DRTB_NN_F32 1      // the same, float
+#define DRTB_NN_F32 2      // the same, float
 #endif
 #ifndef DRTB_NN_MIN
 #define DRTB_NN_MIN 16     // lanes that must be able to take the extra node step (8 / 12 / 16 / 22 measured: flat below 16)
