@@ -172,9 +172,15 @@ static __global__ void bin_leaves_kernel(const uint32_t* __restrict__ sorted_tri
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
+    // the scale of the mesh's coordinates: its extent or its distance from the origin, whichever is larger
     float ext = 0.f;
-    for (int a = 0; a < 3; ++a) ext = fmaxf(ext, ordered_to_float(bounds[3 + a]) - ordered_to_float(bounds[a]));
-    const float pad = 4e-6f * ext + FLT_MIN;          // covers float rounding of the ray and of the slab test
+    for (int a = 0; a < 3; ++a) {
+        const float lo = ordered_to_float(bounds[a]), hi = ordered_to_float(bounds[3 + a]);
+        ext = fmaxf(ext, fmaxf(hi - lo, fmaxf(fabsf(lo), fabsf(hi))));
+    }
+    // covers the float rounding of the ray and of the slab test for ray origins within a few `ext` of the mesh (the
+    // slab distance of axis a is off by <= 2^-21 (|o_a| + ext) / |d_a|); node8_step's relative widening covers the rest
+    const float pad = 4e-6f * ext + FLT_MIN;
     const uint32_t tri = sorted_tri[p];
     const float4 l = leaf_lo[tri], h = leaf_hi[tri];
     t.lo[p] = make_float4(l.x - pad, l.y - pad, l.z - pad, __int_as_float(1));
@@ -590,9 +596,10 @@ __device__ __forceinline__ bool tri_cull_f(const TriF& T, const RayF& r, float t
     const uint32_t s = __float_as_uint(det) & 0x80000000u;
     const float us = __uint_as_float(__float_as_uint(up) ^ s), vs = __uint_as_float(__float_as_uint(vp) ^ s),
                 ts = __uint_as_float(__float_as_uint(tp) ^ s);
-    const bool out = us < -Eu || vs < -Ev || us + vs > ad + (Eu + Ev + Ed) || ts < -Et ||
-                     ts > fmaf(tmaxf, ad + Ed, Et) * 1.000001f;
-    return ad > Ed && out;
+    // bitwise, not short-circuit: the compiler turned the || chain into branches that ran at 5-8 of 32 lanes
+    const bool out = (us < -Eu) | (vs < -Ev) | (us + vs > ad + (Eu + Ev + Ed)) | (ts < -Et) |
+                     (ts > fmaf(tmaxf, ad + Ed, Et) * 1.000001f);
+    return (ad > Ed) & out;
 }
 
 template <typename R> __device__ __forceinline__ float upper_float(R t);
@@ -676,6 +683,7 @@ template <int H> __device__ __forceinline__ float plane_to_float(uint32_t w, uin
 // replaces it by the sentinel on a miss.  A leaf or empty slot so gets a key >= 0x7f000000 (1.7e38 as a float: beyond
 // any entry distance), which never becomes the nearest INTERNAL child as long as one was hit, and node8_step's
 // callers look at the keys only then.
+constexpr float kSlabWiden = 1.0f + 1.0f / 524288.0f;
 struct SlabCoef { float ax, ay, az, bx, by, bz; uint32_t k43, lb_lo, lb_hi, sl_lo, sl_hi; };
 template <int S>
 __device__ __forceinline__ void child_slab(uint32_t wnx, uint32_t wny, uint32_t wnz, uint32_t wfx, uint32_t wfy, uint32_t wfz,
@@ -690,7 +698,7 @@ __device__ __forceinline__ void child_slab(uint32_t wnx, uint32_t wny, uint32_t 
     const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
     // meta byte: internal child 1 << 5 | (24 + slot), leaf unary(n) << 5 | offset: its hit bits are (meta >> 5) << (meta & 31)
     const uint32_t mb = (meta4 >> (8 * J)) & 0xffu;
-    const bool hit = tn <= tf;
+    const bool hit = tn <= tf * kSlabWiden;
     hits |= hit ? (mb >> 5) << (mb & 31u) : 0u;
     // result bytes 3..0 = (leaf byte J, 0, 0, slot): selector nibble 8 | x replicates the sign bit of byte x, and every
     // byte of the slot words is below 0x80, so "sign of byte 4" is the zero byte
@@ -718,9 +726,12 @@ __device__ __forceinline__ void leaf_bytes(uint32_t mask, uint32_t& lo, uint32_t
 //
 // Plane a of child s is origin_a + q 2^E; with f = 128 + q / 256 (plane_to_float) the slab distance is
 //   t = (origin_a + q 2^E - o_a) / d_a = f A + B,   A = 256 2^E / d_a,   B = (origin_a - o_a) / d_a - 128 A.
-// The float evaluation of t is off by at most ~3 ulp of (|origin - o| + 2 node extents) / |d_a|, i.e. 5e-7 scene
-// extents along the axis; the leaf boxes are padded by 4e-6 scene extents on every side at build time (mesh_prepare)
-// and every inner box contains its leaves' padded boxes, so the test needs no widening of its own.
+// The float evaluation of t on axis a is off by at most 2^-21 (|o_a| + mesh scale) / |d_a|.  For a ray that starts
+// within a few mesh scales of the mesh that is inside the padding the leaf boxes get at build time (4e-6 mesh scales
+// on every side, bin_leaves_kernel; every inner box contains its leaves' padded boxes).  For a ray that starts far
+// away the error is relative to t instead (|o_a| ~ t |d_a|), and the far bound is widened by kSlabWiden = 1 + 2^-19
+// in the one compare -- one multiply per child where scaling the twelve slab coefficients by (1 -/+ 4e-7) cost twelve
+// per node and six registers.
 __device__ __forceinline__ void node8_step(const MeshView& m, const RayF& r, float tmax, uint32_t node, uint2& ng, uint2& tg,
                                            int& m1, int& m2)
 {

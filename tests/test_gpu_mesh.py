@@ -132,3 +132,24 @@ def test_million_triangle_build_and_render(drt, ctx):
     a, _ = ctx.trace_rays(drt.make_opts(1, 2, 1.0), orig, dirs, keys, jac=False)
     b, _ = ctx.trace_rays(drt.make_opts(1, 2, 1.0, flags=drt.FLAG_IMAGE | drt.FLAG_NO_BVH), orig, dirs, keys, jac=False)
     assert np.array_equal(a, b) and a.max() > 0
+
+
+def test_bvh_equals_linear_scan_for_far_ray_origins_and_an_offset_mesh(drt, ctx):
+    """The float slab test must stay conservative when the float rounding of the ray is NOT small against the mesh:
+    a mesh far from the coordinate origin (|coordinates| ~ 100 extents) and rays that start ~500 extents away, aimed
+    at triangle VERTICES -- points that lie exactly on the faces of their leaf boxes.  The leaf padding scales with
+    the coordinate magnitude and the slab compare is widened relative to t (bvh.cuh, node8_step)."""
+    scene = drt.tessellated_room(24, 48, width=16, height=16)          # 16 k triangles, extent 6
+    scene.mesh.vertices += np.array([500.0, -300.0, 200.0])
+    ctx.upload(scene)
+    rng = np.random.default_rng(5)
+    m = 1 << 16
+    v = scene.mesh.vertices[rng.integers(0, scene.mesh.vertices.shape[0], size=m)]
+    out = rng.normal(size=(m, 3)); out /= np.linalg.norm(out, axis=1, keepdims=True)
+    orig = v + out * rng.uniform(1000.0, 3000.0, size=(m, 1))
+    dirs = -out + rng.normal(size=(m, 3)) * 1e-9
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    keys = rng.integers(0, 2**62, size=m, dtype=np.uint64)
+    a, _ = ctx.trace_rays(drt.make_opts(1, 2, 1.0), orig, dirs, keys, jac=False)
+    b, _ = ctx.trace_rays(drt.make_opts(1, 2, 1.0, flags=drt.FLAG_IMAGE | drt.FLAG_NO_BVH), orig, dirs, keys, jac=False)
+    assert np.array_equal(a, b) and np.isfinite(a).all()
