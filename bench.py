@@ -452,7 +452,8 @@ def run_b200_arm(a):
     h_grad = torch.empty((P, 3), dtype=torch.float64).pin_memory()
     g_dev = torch.empty((P, 3), dtype=torch.float64, device=dev)
     pvals = scene.param_values()
-    e2e_api = "drtb_set_params + drtb_render (host buffers, pinned)"
+    e2e_api = ("drtb_set_params + drtb_render (host buffers, pinned; the kernel stores the image straight into the pinned "
+               "host buffer over PCIe, the gradients follow by one D2H copy)")
     peer2 = None
     if world > 1 and use_peer and use_pgrad:
         # N > 1: the ASSEMBLED image must land in ONE host buffer.  Every rank's kernel stores its pixels into rank

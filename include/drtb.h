@@ -238,7 +238,11 @@ int32_t drtb_shard_rows(int32_t height, int32_t shard_index, int32_t shard_count
  *              OVERWRITTEN with this call's sums (the caller adds them to
  *              VariableNode::m_grad, vector.hpp:185-188)
  *   stats    : NULL or filled
- * Blocking.  Host->device and device->host copies happen inside the call. */
+ * Blocking.  Host->device and device->host copies happen inside the call.
+ * A PINNED `img` (cudaHostAlloc / cudaHostRegister) is written by the render
+ * kernel itself, pixel by pixel under the compute, and no image copy follows
+ * the kernel (analytic scenes, DRTB_F64 / DRTB_F32); pageable memory works as
+ * well and costs one device->host copy after the kernel.  Same bits. */
 int drtb_render(drtb_ctx* ctx, const drtb_render_opts* opts,
                 const double* seed_img, double* img, double* grad,
                 drtb_stats* stats);

@@ -180,3 +180,25 @@ def test_reserve_makes_the_first_render_as_fast_as_the_second(drt, ctx):
             second = fresh.render(drt.make_opts(spp, mb, ab), stats=True)[2].kernel_ms
             times[(spp, mb, ab)] = (first, second)
             assert first <= 3.0 * second + 0.25, times
+
+
+@pytest.mark.parametrize("opts_kw", [dict(spp=32, min_bounces=4, absorb=1.0), dict(spp=8, min_bounces=4, absorb=1.0),
+                                     dict(spp=16, min_bounces=1, absorb=0.5),
+                                     dict(spp=32, min_bounces=4, absorb=1.0, shard_index=1, shard_count=3)])
+@pytest.mark.parametrize("precision", ["F64", "F32", "MIXED"])
+def test_pinned_host_image_is_written_by_the_kernel_and_equals_the_copied_one(drt, ctx, opts_kw, precision):
+    """drtb_render with a PINNED host image lets the analytic-scene kernels store the pixels straight into it (no
+    D2H copy; DRTB_MIXED and mesh scenes keep the copy): the bits must be those of the pageable-buffer path."""
+    import torch
+    scene = drt.cornell_box(96, 64)
+    ctx.upload(scene)
+    o = drt.make_opts(precision=getattr(drt, precision), **opts_kw)
+    img, grad = ctx.render(o)
+    rows = drt.shard_rows(64, o.shard_index, max(1, o.shard_count), max(1, o.band_rows))
+    h_img = torch.full((rows, 96, 3), float("nan"), dtype=torch.float64).pin_memory()
+    h_grad = torch.full((scene.n_params, 3), float("nan"), dtype=torch.float64).pin_memory()
+    ctx.render_host_ptrs(o, 0, h_img.data_ptr(), h_grad.data_ptr())
+    if precision == "MIXED":          # the re-trace list is filled in a different order every run: same sums to rounding
+        assert rel_err(h_img.numpy(), img).max() <= 1e-12 and rel_err(h_grad.numpy(), grad).max() <= 1e-12
+    else:
+        assert np.array_equal(h_img.numpy(), img) and np.array_equal(h_grad.numpy(), grad)
