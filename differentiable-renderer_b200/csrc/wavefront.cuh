@@ -175,7 +175,7 @@ template <typename R> __device__ __forceinline__ void wf_reload_ray(const WfBuff
 #define DRTB_VOTE_T 2      // a T step runs when DRTB_VOTE_T * (lanes with a triangle to test) >= lanes that can open a node
 #endif
 #ifndef DRTB_VOTE_E
-#define DRTB_VOTE_E 2
+#define DRTB_VOTE_E 3      // an E step runs when DRTB_VOTE_E * (lanes with a survivor) >= the lanes of either other kind (1 / 2 / 3: 1 105 / 1 148 / 1 156 Msegments/s)
 #endif
 // Fatter steps per vote (round 2, gpurun A/B of tools/ab_mesh.sh, 1 M triangles): up to DRTB_TN triangles per T step
 // (1 -> 2: +3.1 % double, +7.8 % float; 3: another +0.6 / +0.9 %; 4: -13 % double, registers) and a second node step
