@@ -36,8 +36,19 @@ __global__ void iota_kernel(int* __restrict__ v, int n)
 
 // Wavefront stage 4: radiance recurrence + adjoint over the records one batch
 // left in HBM, the per-pixel sums of src/render.cpp:78-82 and the gradient sums.
-// Same warp-task shape as render_kernel (a warp owns whole pixels, lanes own
-// samples), so the image is summed in a fixed order.
+//
+// Only the paths that reached a light carry anything (10 % of them in config 4), so a warp that swept its own 32
+// slots kept 3 lanes busy.  A warp therefore owns a CHUNK of consecutive pixels (<= kAdjPixels, ~kAdjSlots path slots),
+// reads the state words of the chunk 32 at a time, queues the lit slots in a small shared-memory ring and sweeps
+// 32 queued records at once.  The ring is in slot order, so a pixel's samples are summed one after the other in
+// sample order (add_to_pixels: lanes holding the same pixel add in lane order), which fixes the order of every
+// floating-point sum whatever the chunk or the launch geometry.
+constexpr int kAdjPixels = 32;
+#ifndef DRTB_ADJ_SLOTS
+#define DRTB_ADJ_SLOTS 512
+#endif
+constexpr int kAdjSlots = DRTB_ADJ_SLOTS;       // a 4 M-path batch is 8192 chunks for the 4736 warps of the launch
+constexpr int kAdjRing = 64;
 template <typename R, bool SMALLP, int CAP>
 __global__ void __launch_bounds__(kBlock)
 wf_adjoint(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArgs a, const WfBuffers<R> b, int partial_row0)
@@ -45,6 +56,8 @@ wf_adjoint(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArg
     extern __shared__ double s_dyn[];
     __shared__ BlockScene<R> bs;
     __shared__ double s_red[kSmallP * 3][kWarpsPerBlock];
+    __shared__ double s_px[kWarpsPerBlock][2][kAdjPixels * 3];       // radiance and gradient-image sums of the chunk's pixels
+    __shared__ int s_ring[kWarpsPerBlock][kAdjRing];                  // queued lit slots: slot within the chunk | n << 20
     const bool want_grad = (a.flags & DRTB_FLAG_GRAD) != 0;
     const int P3 = sc.n_params * 3;
     double* s_acc = s_dyn;
@@ -53,72 +66,86 @@ wf_adjoint(const __grid_constant__ DevScene<R> sc, const __grid_constant__ WfArg
     for (int i = threadIdx.x; i < acc_doubles; i += kBlock) s_acc[i] = 0.0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int spp = a.spp;
     const long long npix = a.n_paths / spp, pix0 = a.first_path / spp;
-    const int ppw = spp >= 32 ? 1 : 32 / spp;
-    const int passes = spp >= 32 ? (spp + 31) / 32 : 1;
-    const long long n_tasks = (npix + ppw - 1) / ppw;
+    const int C = max(1, min(kAdjPixels, kAdjSlots / spp));           // pixels per chunk
+    const long long n_tasks = (npix + C - 1) / C;
     const long long n_warps = (long long)gridDim.x * kWarpsPerBlock;
     const R inv_p = a.absorb < 1.0 ? R(1.0 / (1.0 - a.absorb)) : R(0);
     SmemSink ssink{s_acc + threadIdx.x};
     AtomicSink asink{a.grad_atomic, (a.flags & DRTB_FLAG_DETERMINISTIC) != 0};
     Materials<R, true> mat;
     mat.bs = &bs; mat.mesh = a.mesh; mat.params = a.params;
+    double* pxacc = s_px[warp][0];
+    double* pxg = s_px[warp][1];
+    int* ring = s_ring[warp];
     uint32_t n_lit = 0;
     for (long long task = (long long)blockIdx.x * kWarpsPerBlock + warp; task < n_tasks; task += n_warps) {
-        const int sub = spp >= 32 ? 0 : lane / spp;
-        const int i0 = spp >= 32 ? lane : lane % spp;
-        const long long lp = task * ppw + sub;                // pixel within the batch
-        const bool lane_ok = sub < ppw && lp < npix;
-        const long long pix = pix0 + lp;                      // pixel within the shard
-        R g0[3] = {R(0), R(0), R(0)};
-        if (lane_ok && want_grad) {
+        const long long cpix0 = task * C;                     // first pixel of the chunk, within the batch
+        const int K = int(min((long long)C, npix - cpix0));
+        const long long slot0 = cpix0 * spp;
+        const int n_slots = K * spp;
+        for (int k = lane; k < K * 3; k += 32) { pxacc[k] = 0.0; pxg[k] = 0.0; }
+        __syncwarp();
+        int q_head = 0, q_count = 0;                          // warp-uniform
+        // lanes holding the same pixel add one after the other, in lane order (px < 0: nothing to add)
+        auto add_to_pixels = [&](int px, const R* L0, const double* g) {
+            const unsigned grp = __match_any_sync(0xffffffffu, px);
+            const int rank = __popc(grp & lt_mask);
+            const int rounds = __reduce_max_sync(0xffffffffu, px < 0 ? 0 : __popc(grp));
+            for (int r = 0; r < rounds; ++r) {
+                if (px >= 0 && rank == r) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) g0[c] = R(a.seed_scale * (a.seed_img ? a.seed_img[pix * 3 + c] : 1.0));
-        }
-        double acc[3] = {0.0, 0.0, 0.0};
-        double gacc[3] = {0.0, 0.0, 0.0};                     // gradient image (gimg_param == -1: stays zero)
-        PixelSink<SmemSink> ps{ssink, a.gimg_param, gacc};
-        PixelSink<AtomicSink> pa{asink, a.gimg_param, gacc};
-        for (int pass = 0; pass < passes; ++pass) {
-            const int i = i0 + pass * 32;
-            if (!(lane_ok && i < spp)) continue;
-            const long long p = lp * spp + i;
-            const uint32_t st = b.state[p];
-            if (!(st & kStLit)) continue;
-            const int n = int((st >> 16) & 0xffu);
-            const WfRecordView<R, CAP> rec{b.rec_w + p, b.rec_prim + p, a.batch};
-            R L0[3];
-            if (SMALLP) radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ps);
-            else        radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, pa);
-            acc[0] += double(L0[0]); acc[1] += double(L0[1]); acc[2] += double(L0[2]);
-            n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
-        }
-        auto write_pixel = [&](double* dst, double* v, bool mean) {
-            if (spp >= 32) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) v[c] = warp_sum(v[c]);
-                if (lane == 0 && lane_ok) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) dst[pix * 3 + c] = mean ? v[c] / double(spp) : v[c];
+                    for (int c = 0; c < 3; ++c) { pxacc[3 * px + c] += double(L0[c]); pxg[3 * px + c] += g[c]; }
                 }
-            } else {
-                double tot[3] = {v[0], v[1], v[2]};
-                for (int j = 1; j < spp; ++j) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        double o = __shfl_down_sync(0xffffffffu, v[c], j);
-                        if (i0 + j < spp) tot[c] += o;
-                    }
-                }
-                if (lane_ok && i0 == 0) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) dst[pix * 3 + c] = mean ? tot[c] / double(spp) : tot[c];
-                }
+                __syncwarp();
             }
         };
-        if (a.img) write_pixel(a.img, acc, true);
-        if (a.gimg) write_pixel(a.gimg, gacc, false);
+        auto drain = [&](int m) {
+            __syncwarp();
+            R L0[3] = {R(0), R(0), R(0)};
+            double gacc[3] = {0.0, 0.0, 0.0};                 // gradient image (gimg_param == -1: stays zero)
+            int px = -1;
+            if (lane < m) {
+                const int e = ring[(q_head + lane) & (kAdjRing - 1)];
+                const int s = e & 0xfffff, n = e >> 20;
+                px = s / spp;
+                const long long p = slot0 + s;
+                R g0[3] = {R(0), R(0), R(0)};
+                if (want_grad) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) g0[c] = R(a.seed_scale * (a.seed_img ? a.seed_img[(pix0 + cpix0 + px) * 3 + c] : 1.0));
+                }
+                PixelSink<SmemSink> ps{ssink, a.gimg_param, gacc};
+                PixelSink<AtomicSink> pa{asink, a.gimg_param, gacc};
+                const WfRecordView<R, CAP> rec{b.rec_w + p, b.rec_prim + p, a.batch};
+                if (SMALLP) radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, ps);
+                else        radiance_and_adjoint(mat, rec, n, a.min_bounces, inv_p, want_grad, g0, L0, pa);
+                n_lit += (L0[0] != R(0)) | (L0[1] != R(0)) | (L0[2] != R(0));
+            }
+            add_to_pixels(px, L0, gacc);
+            q_head = (q_head + m) & (kAdjRing - 1);
+            q_count -= m;
+        };
+        for (int s0 = 0; s0 < n_slots; s0 += 32) {
+            const int s = s0 + lane;
+            uint32_t st = 0;
+            if (s < n_slots) st = b.state[slot0 + s];
+            const bool lit = (st & kStLit) != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, lit);
+            if (lit) ring[(q_head + q_count + __popc(m & lt_mask)) & (kAdjRing - 1)] = s | int((st >> 16) & 0xffu) << 20;
+            q_count += __popc(m);
+            if (q_count >= 32) drain(32);
+        }
+        if (q_count > 0) drain(q_count);
+        __syncwarp();
+        for (int k = lane; k < K * 3; k += 32) {
+            const long long at = (pix0 + cpix0) * 3 + k;      // pixel within the shard
+            if (a.img) a.img[at] = pxacc[k] / double(spp);
+            if (a.gimg) a.gimg[at] = pxg[k];
+        }
+        __syncwarp();
     }
     if (SMALLP && want_grad) {
         for (int j = 0; j < P3; ++j) {
