@@ -94,6 +94,8 @@ SYMBOLS = [
     ("drtb_set_image_peers", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]),
     ("drtb_grad_exchange_bytes", C.c_size_t, [C.c_int32, C.c_int32]),
     ("drtb_set_grad_peers", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
+    ("drtb_host_alloc", C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    ("drtb_host_free", C.c_int, [C.c_void_p]),
     ("drtb_ipc_alloc", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
     ("drtb_ipc_open", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("drtb_ipc_close", C.c_int, [C.c_void_p, C.c_void_p]),

@@ -878,6 +878,26 @@ int drtb_set_grad_peers(drtb_ctx* ctx, void* const* exchange, int32_t n, int32_t
     return DRTB_OK;
 }
 
+int drtb_host_alloc(size_t bytes, void** ptr)
+{
+    if (!ptr || bytes == 0) return DRTB_ERR_INVALID;
+    *ptr = nullptr;
+    const cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        *ptr = nullptr;
+        return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? DRTB_ERR_NO_DEVICE : DRTB_ERR_CUDA;
+    }
+    return DRTB_OK;
+}
+
+int drtb_host_free(void* ptr)
+{
+    if (!ptr) return DRTB_OK;
+    if (cudaFreeHost(ptr) != cudaSuccess) { (void)cudaGetLastError(); return DRTB_ERR_CUDA; }
+    return DRTB_OK;
+}
+
 int drtb_ipc_alloc(drtb_ctx* ctx, size_t bytes, void** d_ptr, void* handle)
 {
     if (!ctx) return DRTB_ERR_INVALID;

@@ -109,7 +109,7 @@ int main(int argc, const char* argv[])
 
     Camera<T> cam(args.width, args.height);
     cam.look_at(Vector<T, 3>{0, 0, 0}, Vector<T, 3>{0, 0, 1});
-    std::vector<Vector<double, 3>> img(args.width * args.height);
+    gpu::PinnedImage img(args.width * args.height);       // pinned: the kernel writes the pixels into it, no copy after the render
 
     Pathtracer<T> tracer(args.absorb_prob, args.min_bounces);
 

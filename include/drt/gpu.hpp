@@ -5,11 +5,14 @@
 // status codes into exceptions.  There is no CPU fallback: without a GPU every
 // call throws std::runtime_error carrying drtb_last_error().
 #pragma once
+#include <algorithm>
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -237,6 +240,33 @@ inline Device& device(int index = 0)
     if (!slot) slot.reset(new Device(index));
     return *slot;
 }
+
+// An image buffer in pinned host memory (drtb_host_alloc): drt::render / drtb_render let the kernel store the pixels
+// straight into it, so no device->host copy follows the render.  NEW relative to the reference, which renders into
+// a plain `new Vector<double, 3>[w * h]` (src/render.cpp:69) -- that works here as well and costs the copy.
+class PinnedImage {
+public:
+    explicit PinnedImage(std::size_t pixels) : n_(pixels)
+    {
+        void* p = nullptr;
+        if (drtb_host_alloc(std::max<std::size_t>(pixels, 1) * sizeof(Vector<double, 3>), &p) != DRTB_OK)
+            throw std::runtime_error("drt::gpu::PinnedImage: drtb_host_alloc failed");
+        data_ = static_cast<Vector<double, 3>*>(p);
+        for (std::size_t i = 0; i < n_; ++i) new (data_ + i) Vector<double, 3>();
+    }
+    ~PinnedImage() { drtb_host_free(data_); }
+    PinnedImage(const PinnedImage&) = delete;
+    PinnedImage& operator=(const PinnedImage&) = delete;
+    Vector<double, 3>* data() { return data_; }
+    const Vector<double, 3>* data() const { return data_; }
+    std::size_t size() const { return n_; }
+    Vector<double, 3>& operator[](std::size_t i) { return data_[i]; }
+    const Vector<double, 3>& operator[](std::size_t i) const { return data_[i]; }
+
+private:
+    Vector<double, 3>* data_ = nullptr;
+    std::size_t n_ = 0;
+};
 
 } // namespace gpu
 } // namespace drt

@@ -247,6 +247,13 @@ int drtb_render(drtb_ctx* ctx, const drtb_render_opts* opts,
                 const double* seed_img, double* img, double* grad,
                 drtb_stats* stats);
 
+/* Pinned host memory for drtb_render's buffers without the CUDA headers
+ * (cudaHostAlloc, portable: every GPU of the box can address it).  An image
+ * allocated here takes the kernel-written path described above.
+ * drtb_host_free(NULL) is a no-op. */
+int drtb_host_alloc(size_t bytes, void** ptr);
+int drtb_host_free(void* ptr);
+
 /* Same, DEVICE buffers on ctx's device, enqueued on `stream` (a cudaStream_t
  * passed as void*; NULL = the legacy default stream).  Asynchronous: returns
  * after the launches; the caller synchronises the stream.  d_stats is NULL or

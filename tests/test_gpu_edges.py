@@ -202,3 +202,25 @@ def test_pinned_host_image_is_written_by_the_kernel_and_equals_the_copied_one(dr
         assert rel_err(h_img.numpy(), img).max() <= 1e-12 and rel_err(h_grad.numpy(), grad).max() <= 1e-12
     else:
         assert np.array_equal(h_img.numpy(), img) and np.array_equal(h_grad.numpy(), grad)
+
+
+def test_host_alloc_gives_a_pinned_image_the_kernel_writes(drt, ctx):
+    """drtb_host_alloc / drtb_host_free: pinned memory for C callers without the CUDA headers."""
+    import ctypes as C
+    from drt_b200 import abi
+    lib = abi.load_library()
+    scene = drt.cornell_box(64, 48)
+    ctx.upload(scene)
+    o = drt.make_opts(32, 4, 1.0)
+    img, grad = ctx.render(o)
+    p = C.c_void_p()
+    assert lib.drtb_host_alloc(img.nbytes, C.byref(p)) == 0 and p.value
+    try:
+        view = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(img.size,))
+        view[:] = np.nan
+        g2 = np.empty_like(grad)
+        ctx.render_host_ptrs(o, 0, p.value, g2.ctypes.data)
+        assert np.array_equal(view.reshape(img.shape), img) and np.array_equal(g2, grad)
+    finally:
+        assert lib.drtb_host_free(p) == 0
+    assert lib.drtb_host_free(None) == 0 and lib.drtb_host_alloc(0, C.byref(p)) == abi.ERR_INVALID
